@@ -1,0 +1,185 @@
+/*
+ * gpmpc_b200.h -- C ABI of libgpmpc_b200.so: batched posterior sampling of GP dynamics on B200 (sm_100a).
+ *
+ * The reference (manish-pra/sampling-gpmpc) has no FFI for this path: its seam is Python duck typing
+ * (SURVEY.md section 8b).  Each entry point below names the reference code it replaces; the Python
+ * binding a maintainer would add is a ctypes stub (sampling_gpmpc_b200/engine.py).
+ *
+ * Conventions
+ *   - All numeric arrays are float64, contiguous, row-major, in exactly the reference's layouts:
+ *     a "batch element" is b = s*g_ny + j (sample s, GP output j)  <-> torch batch_shape (ns, g_ny);
+ *     test inputs  x  [B][H][d];  posterior quantities  [B][H][T]  with T fastest (GPyTorch's
+ *     interleaved multitask order: scalar index = point*T + task, task 0 = value, task a = d/dx_a).
+ *   - Pointers marked DEVICE are CUDA device pointers owned by the caller (e.g. torch tensors); the
+ *     library borrows them for the duration of the call.  Pointers marked HOST are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every call is
+ *     asynchronous w.r.t. the host and ordered on that stream; nothing here synchronises unless
+ *     its comment says so.
+ *   - Return value: 0 ok; <0 invalid argument / capacity / CUDA error (gpmpc_last_error() has text).
+ *     Numerical status never crosses as a return code: it is written per batch element into the
+ *     caller's `jitter_level` array and the handle's device status word (gpmpc_status()).
+ *   - One handle per Agent per GPU; not thread-safe; no internal threads.
+ *   - There is no CPU fallback: every entry point fails with GPMPC_ERR_CUDA without a device.
+ */
+#ifndef GPMPC_B200_H
+#define GPMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPMPC_MAX_D 6   /* GP input dimension (BASELINE.json: "input dim <= 6") */
+#define GPMPC_MAX_T 7   /* tasks per point: 1 (value only) or d+1 (value + gradient) */
+#define GPMPC_MAX_NX 8  /* state / input dims of the dynamics for the assembly kernel */
+
+#define GPMPC_OK 0
+#define GPMPC_ERR_ARG (-1)
+#define GPMPC_ERR_CAPACITY (-2)
+#define GPMPC_ERR_CUDA (-3)
+#define GPMPC_ERR_STATE (-4)
+
+/* bits of the device status word (gpmpc_status) */
+#define GPMPC_ST_TRAIN_JITTER 1u   /* real-data block needed jitter (psd_safe_cholesky ladder, level in bits 8..9) */
+#define GPMPC_ST_TRAIN_NOT_PD 2u   /* real-data block not PD after the ladder (GPyTorch: NotPSDError) */
+#define GPMPC_ST_SAMPLE_NOT_PD 4u  /* some posterior covariance not PD after the ladder (jitter_level[b] == 4) */
+#define GPMPC_ST_APPEND_NOT_PD 8u  /* a bordered block (Sigma* + noise) was not PD when conditioning */
+#define GPMPC_ST_NAN_INPUT 16u     /* NaN reached a Cholesky (GPyTorch: NanError) */
+
+typedef struct gpmpc_handle gpmpc_handle;
+
+typedef struct {
+  int32_t ns;          /* dynamics samples held by this handle (this rank's shard) */
+  int32_t g_ny;        /* GP outputs per sample */
+  int32_t d;           /* GP input dimension g_nx + g_nu */
+  int32_t T;           /* tasks per point: 1 or d+1 */
+  int32_t n_real;      /* real (measured) training points, shared by all samples */
+  int32_t cap_points;  /* capacity: hallucinated points per batch element (grown by gpmpc_reserve) */
+} gpmpc_dims;
+
+/* sample_gp's post-processing switches (src/agent.py:646-708); a negative threshold disables, like the yaml */
+typedef struct {
+  double beta;              /* Dyn_gp_beta: truncate to mean +- beta*sqrt(variance); <0 = no truncation */
+  double variance_is_zero;  /* Dyn_gp_variance_is_zero */
+  int32_t unclamped_sqrt_1x1; /* 1 = GPyTorch's no-base-samples 1x1 path (sqrt without clamp), else 0 */
+  int32_t reserved;
+} gpmpc_sample_opts;
+
+/* env hooks of Agent.dyn_fg_jacobians as plain data (src/agent.py:532-564, src/environments/*.py) */
+typedef struct {
+  int32_t nx, nu, g_ny, d;
+  int32_t g_idx_inputs[GPMPC_MAX_D];        /* columns of [x,u] that feed the GP (get_g_xu_hat) */
+  int32_t pad_g[GPMPC_MAX_NX];              /* where transformed [g, dg] land in [f, df/dx, df/du] */
+  int32_t n_pad;                            /* entries of pad_g in use */
+  int32_t transform;                        /* 0 identity, 1 car-residual: [v g, v dg/dphi, g, v dg/ddelta] */
+  double B_d[GPMPC_MAX_NX * GPMPC_MAX_NX];  /* (nx, g_ny) row-major */
+  double F_known[GPMPC_MAX_NX * 2 * GPMPC_MAX_NX]; /* (nx, nx+nu) row-major: f(x,u) = F [x;u] */
+  int32_t use_feedback;                     /* rollouts: u = u_ff - K (x_equi - x)  (simulate_forward_sampling_car.py:122) */
+  int32_t reserved;
+  double K_fb[GPMPC_MAX_NX * GPMPC_MAX_NX]; /* (nu, nx) row-major */
+  double x_equi[GPMPC_MAX_NX];
+} gpmpc_env;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Allocates the persistent per-sample state on the current CUDA device.
+ * Replaces: Agent.__init__'s empty Hallcinated_*_train + real_data_batch (src/agent.py:52-67,204-214). */
+int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out);
+int gpmpc_destroy(gpmpc_handle* h);
+const char* gpmpc_last_error(const gpmpc_handle* h); /* h may be NULL: error of the last failed create */
+
+/* ---- model definition -------------------------------------------------------------------------- */
+
+/* Hyper-parameters per GP output (HOST arrays): lengthscale[g_ny*d], outputscale[g_ny],
+ * noise[g_ny*T] = task_noises[t] + noise (the diagonal MultitaskGaussianLikelihood(rank=0) adds to the
+ * training block), jitter = Dyn_gp_jitter.
+ * Replaces: BatchMultitaskGPModelWithDerivatives_fromParams.__init__ (src/GP_model.py:121-143) and
+ * gpytorch.settings.cholesky_jitter (src/agent.py:634-638).  The reference tiles these over samples;
+ * they are identical for every sample, so the library keeps one copy per output. */
+int gpmpc_set_hypers(gpmpc_handle* h, const double* lengthscale, const double* outputscale,
+                     const double* noise, double jitter);
+
+/* Real training data (DEVICE): X[n_real*d], Y[g_ny*n_real*T] with NaN = unobserved slot.  Factorises the
+ * shared block once per output (kernel K0) and clears the hallucinated set.  SYNCHRONISES once to read the
+ * observed-slot count.  Replaces: the real-data part of every ExactGP re-fit (src/agent.py:223-248 ->
+ * gpytorch ExactGP / DefaultPredictionStrategy, psd_safe_cholesky of K_oo + Sigma). */
+int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void* stream);
+
+/* Drops all hallucinated points (src/agent.py:261-272: the reset when sqp_iter == 0). */
+int gpmpc_reset_hallucinated(gpmpc_handle* h);
+/* Ensures room for `cap_points` hallucinated points per batch element (re-lays the factor out). */
+int gpmpc_reserve(gpmpc_handle* h, int32_t cap_points, void* stream);
+/* 1 (default): appended points extend the factor.  0: they are only recorded (the reference's
+ * use_model_without_derivatives "real data only" model, src/agent.py:221-226). */
+int gpmpc_set_condition_on_hallucinated(gpmpc_handle* h, int32_t on);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* Posterior of every batch element at its own H test points, joint over the q = H*T scalars.
+ * x DEVICE [B*H*d]; outputs DEVICE mean[B*H*T], var[B*H*T] (diag clamped at 1e-10 like .variance).
+ * If eps != NULL also draws y = mean + chol(Sigma*) eps with GPyTorch's jitter ladder and applies
+ * sample_gp's post-processing (opts); y DEVICE [B*H*T], jitter_level DEVICE int32 [B] (0..3, 4 = not PD).
+ * The joint covariance stays cached in the handle for gpmpc_sample / gpmpc_append.
+ * Replaces: self.model_i(x_input) and .sample(base_samples) (src/agent.py:640-641) and the
+ * post-processing at src/agent.py:646-663,701-708. */
+int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, double* var,
+                    const double* eps, const gpmpc_sample_opts* opts, double* y, int32_t* jitter_level,
+                    void* stream);
+
+/* Draw from the posterior cached by the last gpmpc_posterior (MultitaskMultivariateNormal.sample). */
+int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* opts, double* y,
+                 int32_t* jitter_level, void* stream);
+
+/* Condition every batch element on its H new points: x DEVICE [B*H*d], y DEVICE [B*H*T] (labels as they
+ * stand after post-processing).  point_active HOST uint8[H] or NULL (= all): points with 0 are recorded in
+ * the data set but do not enter the factor (GPyTorch's any-over-batch NaN mask).
+ * Appends T rows per point to each element's bordered Cholesky factor: [W^T | chol(Sigma* + noise)].
+ * Replaces: Agent.update_hallucinated_Dyn_dataset + the next train_hallucinated_dynGP re-fit
+ * (src/agent.py:164-202,216-248). */
+int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_t* point_active,
+                 int32_t H, void* stream);
+
+/* Fused rollout step (H = 1): posterior + draw + post-processing + append in ONE launch, one warp per
+ * batch element, the element's factor rows streamed once from HBM.  Same outputs as gpmpc_posterior.
+ * Replaces one iteration of the loops at benchmarking/simulate_true_reachable_set.py:179-259 and
+ * benchmarking/simulate_forward_sampling_car.py:117-138 (model call .. update_hallucinated_Dyn_dataset). */
+int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_sample_opts* opts,
+               double* mean, double* var, double* y, int32_t* jitter_level, void* stream);
+
+/* dyn_fg_jacobians' assembly: out DEVICE [ns][nx][H][1+nx+nu] = df_known + B_d pad(transform(y_gp)).
+ * xu DEVICE [ns][nx][H][nx+nu] (the reference's tiled layout; row 0 of the nx copies is read),
+ * y_gp DEVICE [ns][g_ny][H][T].  Replaces src/agent.py:537-554 and the env hooks in SURVEY.md 8(a) a14. */
+int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, const double* y_gp, int32_t H,
+                   double* out, void* stream);
+
+/* Whole forward rollout on the stream, no host round trips: for t < n_steps
+ *   xu_t = [x_t, u_t (+ feedback)], traj[:, :, t] = x_t, y = step(xu_t[g_idx]), x_{t+1} = F xu_t + B_d pad(y)[0].
+ * x0 DEVICE [ns*nx]; u_ff DEVICE [n_steps*nu]; eps DEVICE [n_steps][B*T]; traj DEVICE [ns][nx][n_steps+1].
+ * Replaces the loop at benchmarking/simulate_forward_sampling_car.py:117-138. */
+int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
+                  const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
+                  void* stream);
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+
+int32_t gpmpc_num_hallucinated(const gpmpc_handle* h);  /* points recorded per batch element */
+int32_t gpmpc_num_factor_rows(const gpmpc_handle* h);   /* observed hallucinated scalars in the factor */
+int32_t gpmpc_num_real_observed(const gpmpc_handle* h); /* m: observed real scalars */
+/* Copies the recorded hallucinated set to DEVICE X[B][np][d], Y[B][np][T]
+ * (serves model.train_inputs[0] / train_targets, src/visu.py:483-484). */
+int gpmpc_export_hallucinated(const gpmpc_handle* h, double* X, double* Y, void* stream);
+/* Reads (and optionally clears) the device status word.  SYNCHRONISES the stream. */
+int gpmpc_status(gpmpc_handle* h, uint32_t* status, int32_t clear, void* stream);
+/* Bytes of persistent device state, and algorithmic HBM bytes / flops of the last hot-path launch
+ * (the figures DESIGN.md's roofline uses). */
+int64_t gpmpc_state_bytes(const gpmpc_handle* h);
+int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops);
+/* Number of kernels this library launched since create (bench.py's gpu_launches). */
+int64_t gpmpc_launch_count(const gpmpc_handle* h);
+const char* gpmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPMPC_B200_H */

@@ -1,0 +1,352 @@
+"""Host-side mirror of the reference ``Agent``'s hot-path interface (src/agent.py), over the CUDA engine.
+
+Same method names, argument meaning and return layouts as the reference, so ``src/solver.py:84-94`` and the
+rollout scripts can drive it unchanged:
+
+    train_hallucinated_dynGP(sqp_iter, use_model_without_derivatives=False)      agent.py:216-272
+    get_batch_x_hat(x_h, u_h) / get_batch_x_hat_u_diff(x_h, u_h)                  agent.py:480-527
+    dyn_fg_jacobians(xu_hat, sqp_iter) -> gp_val, y_grad, u_grad (numpy)           agent.py:532-564
+    get_batch_gp_sensitivities(xu_hat, sqp_iter)                                  agent.py:566-627
+    sample_gp(x_input, base_samples)                                              agent.py:629-730
+    update_hallucinated_Dyn_dataset(newX, newY)                                   agent.py:164-202
+    mpc_iteration(i), random_vector_within_bounds(), epistimic_random_vector      agent.py:76-104,529-530
+    Hallcinated_X_train / Hallcinated_Y_train, model_i.train_inputs / train_targets, model_i_call.mean/.variance
+
+What differs is only *how*: the reference throws the GPyTorch model away and re-fits it on
+[real || hallucinated] data on every call; here ``train_hallucinated_dynGP`` is bookkeeping, because the
+engine keeps each sample's bordered Cholesky factor on the GPU and ``update_hallucinated_Dyn_dataset``
+appends rows to it.  All arithmetic happens in libgpmpc_b200.so; torch holds memory and moves bytes.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .engine import GPEngine, make_env_struct
+from .envs import EnvSpec, env_spec_from_env_model, make_env_spec
+
+F64 = torch.float64
+
+
+def gp_hypers_from_params(params: dict, g_ny: int, d: int, use_grad: bool):
+    """The yaml -> hyper-parameter broadcast of GP_model.py:121-143, per GP output (the reference tiles the
+    same values over every sample).  Returns lengthscale (g_ny,d), outputscale (g_ny,), noise (g_ny,T)."""
+    ag = params["agent"]
+    ls = np.asarray(ag["Dyn_gp_lengthscale"]["both"], dtype=np.float64).reshape(-1, d)
+    ls = np.broadcast_to(ls, (g_ny, d)).copy()
+    os_ = np.broadcast_to(np.asarray(ag["Dyn_gp_outputscale"]["both"], dtype=np.float64).reshape(-1), (g_ny,)).copy()
+    val = ag["Dyn_gp_task_noises"]["val"]
+    val = np.asarray(val if use_grad else [val[0]], dtype=np.float64) * ag["Dyn_gp_task_noises"]["multiplier"]
+    noise = np.broadcast_to(val + ag["Dyn_gp_noise"], (g_ny, val.shape[0])).copy()
+    return ls, os_, noise
+
+
+class _ModelView:
+    """What callers read off ``agent.model_i`` (src/visu.py:483-484, src/agent.py:642-643)."""
+
+    def __init__(self, agent: "Agent", version: int, with_hallucinated: bool):
+        self._agent, self._version, self._with_h = agent, version, with_hallucinated
+        self.batch_shape = agent.batch_shape
+
+    def _data(self):
+        ag = self._agent
+        if ag._data_version != self._version:
+            raise RuntimeError("model_i's training-data snapshot is gone: the factor was updated after "
+                               "train_hallucinated_dynGP (call it again before reading train_inputs)")
+        X, Y = ag.Dyn_gp_X_train_batch, ag.Dyn_gp_Y_train_batch
+        if self._with_h:
+            Xh, Yh = ag.engine.export_hallucinated()
+            X, Y = torch.cat([X, Xh], 2), torch.cat([Y, Yh], 2)
+        return X, Y
+
+    @property
+    def train_inputs(self):
+        return (self._data()[0],)
+
+    @property
+    def train_targets(self):
+        return self._data()[1]
+
+    def eval(self):
+        return self
+
+
+class _PosteriorView:
+    """``agent.model_i_call``: .mean / .variance / .stddev like the MultitaskMultivariateNormal the reference keeps."""
+
+    def __init__(self, mean, variance, jitter_level=None):
+        self.mean, self.variance, self.jitter_level = mean, variance, jitter_level
+
+    @property
+    def stddev(self):
+        return self.variance.sqrt()
+
+    def confidence_region(self):
+        s2 = self.stddev.mul(2)
+        return self.mean.sub(s2), self.mean.add(s2)
+
+
+class Agent:
+    def __init__(self, params: dict, env_model=None, *, spec: Optional[EnvSpec] = None,
+                 X_real: Optional[torch.Tensor] = None, Y_real: Optional[torch.Tensor] = None,
+                 epistimic_random_vector: Optional[torch.Tensor] = None, generate_base_samples: bool = True,
+                 rank: int = 0, world_size: int = 1, device: Optional[torch.device] = None):
+        self.params = params
+        ag = params["agent"]
+        self.g_nx, self.g_nu, self.g_ny = ag["g_dim"]["nx"], ag["g_dim"]["nu"], ag["g_dim"]["ny"]
+        self.nx, self.nu = ag["dim"]["nx"], ag["dim"]["nu"]
+        self.ns_global = ag["num_dyn_samples"]
+        # contiguous shard of the sample index; global indices are kept for eps slicing
+        self.rank, self.world_size = rank, world_size
+        per = -(-self.ns_global // world_size)
+        self.s_lo, self.s_hi = min(rank * per, self.ns_global), min((rank + 1) * per, self.ns_global)
+        self.ns = self.s_hi - self.s_lo
+        self.in_dim_x = self.g_nx + self.g_nu
+        self.in_dim_y = 1 if params["env"]["use_model_without_derivatives"] else 1 + self.in_dim_x
+        self.batch_shape = torch.Size([self.ns, self.g_ny])
+        self.torch_device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.use_cuda = True
+
+        if spec is None:
+            spec = env_spec_from_env_model(env_model, params) if env_model is not None else make_env_spec(params)
+        self.spec = spec
+        self.env_model = env_model
+        if X_real is None:
+            X_real, Y_real = (env_model.initial_training_data() if env_model is not None
+                              else spec.initial_training_data(params))
+        self.Dyn_gp_X_train = X_real.to(self.torch_device, F64)
+        self.Dyn_gp_Y_train = Y_real.to(self.torch_device, F64)
+        if self.in_dim_y == 1:
+            self.Dyn_gp_Y_train = self.Dyn_gp_Y_train[:, :, [0]]
+        n_real = self.Dyn_gp_X_train.shape[0]
+
+        self.engine = GPEngine(self.ns, self.g_ny, self.in_dim_x, self.in_dim_y, n_real, cap_points=0,
+                               device=self.torch_device)
+        ls, os_, noise = gp_hypers_from_params(params, self.g_ny, self.in_dim_x, use_grad=self.in_dim_y > 1)
+        self.engine.set_hypers(ls, os_, noise, ag["Dyn_gp_jitter"])
+        self.engine.set_real_data(self.Dyn_gp_X_train, self.Dyn_gp_Y_train.contiguous())
+        self.engine.reserve(params["optimizer"]["H"] * max(1, params["optimizer"]["SEMPC"]["max_sqp_iter"]))
+        self.env_struct = make_env_struct(spec)
+        self.outputscale = os_
+
+        self._data_version = 0      # bumps whenever the engine's data set changes
+        self._pending_reset = False  # sqp_iter == 0: data set is logically empty, factor still holds the old one
+        self._appended_since_train = False
+        self.model_i = None
+        self.model_i_call = None
+        self.mpc_iter = 0
+        if epistimic_random_vector is not None:
+            self.epistimic_random_vector = epistimic_random_vector[:, :, self.s_lo:self.s_hi].to(self.torch_device, F64)
+        elif generate_base_samples:
+            self.epistimic_random_vector = self.random_vector_within_bounds()[:, :, self.s_lo:self.s_hi]
+        else:
+            self.epistimic_random_vector = None
+
+    # ---- views the reference exposes as attributes ---------------------------------------------
+    @property
+    def Dyn_gp_X_train_batch(self):  # real_data_batch, agent.py:204-214 (a view: nothing is tiled in memory)
+        return self.Dyn_gp_X_train.expand(self.ns, self.g_ny, *self.Dyn_gp_X_train.shape)
+
+    @property
+    def Dyn_gp_Y_train_batch(self):
+        return self.Dyn_gp_Y_train.expand(self.ns, *self.Dyn_gp_Y_train.shape)
+
+    def _hallucinated(self):
+        if self._pending_reset:
+            return (torch.empty(self.ns, self.g_ny, 0, self.in_dim_x, dtype=F64, device=self.torch_device),
+                    torch.empty(self.ns, self.g_ny, 0, self.in_dim_y, dtype=F64, device=self.torch_device))
+        return self.engine.export_hallucinated()
+
+    @property
+    def Hallcinated_X_train(self):
+        return self._hallucinated()[0]
+
+    @property
+    def Hallcinated_Y_train(self):
+        return self._hallucinated()[1]
+
+    # ---- a2: agent.py:76-104, same generator stream (one torch.normal per candidate) --------------
+    def random_vector_within_bounds(self) -> torch.Tensor:
+        H = self.params["optimizer"]["H"]
+        n_dyn, beta = self.ns_global, self.params["agent"]["Dyn_gp_beta"]
+        n_mpc = self.params["common"]["num_MPC_itrs"]
+        n_itrs = self.params["optimizer"]["SEMPC"]["max_sqp_iter"]
+        dev = self.torch_device if self.params["common"]["use_cuda"] else torch.device("cpu")
+        out = torch.empty(n_mpc, n_itrs, n_dyn, self.g_ny, H, self.in_dim_y, dtype=F64, device=dev)
+        for j in range(n_mpc):
+            for i in range(n_itrs):
+                k = 0
+                while k < n_dyn:
+                    w = torch.normal(0, 1, size=(1, self.g_ny, H, self.in_dim_y), dtype=F64, device=dev)
+                    if torch.all(w >= -beta) and torch.all(w <= beta):
+                        out[j, i, k] = w[0]
+                        k += 1
+        return out.to(self.torch_device)
+
+    def mpc_iteration(self, i):
+        self.mpc_iter = i
+
+    # ---- a4 ------------------------------------------------------------------------------------
+    def train_hallucinated_dynGP(self, sqp_iter, use_model_without_derivatives=False):
+        """Reference: build a new GPyTorch model on [real || hallucinated] (agent.py:216-258), then, if
+        sqp_iter == 0, empty the hallucinated set (agent.py:261-272) -- so this call's model still contains the
+        previous MPC step's points.  Here the factor already *is* that model; the reset is deferred to the next
+        append so the coming posterior call sees the same training set the reference's model_i would."""
+        if use_model_without_derivatives != (self.in_dim_y == 1):
+            raise NotImplementedError("use_model_without_derivatives must agree with params['env'] (as in the reference scripts)")
+        if self._pending_reset:  # two trains without an append in between: the old model is simply dropped
+            self.engine.reset_hallucinated()
+            self._data_version += 1
+            self._pending_reset = False
+        self.engine.set_condition_on_hallucinated(not use_model_without_derivatives)
+        self.model_i = _ModelView(self, self._data_version, with_hallucinated=not use_model_without_derivatives)
+        self._appended_since_train = False
+        if sqp_iter == 0:
+            self._pending_reset = True
+
+    # ---- a13 -----------------------------------------------------------------------------------
+    def get_batch_x_hat(self, x_h, u_h):
+        H = self.params["optimizer"]["H"]
+        x_h = torch.as_tensor(np.asarray(x_h), dtype=F64)
+        u_h = torch.as_tensor(np.asarray(u_h), dtype=F64)
+        xb = x_h.transpose(0, 1).reshape(self.ns_global, self.nx, H)[self.s_lo:self.s_hi].transpose(1, 2)
+        ub = torch.ones(self.ns, H, 1, dtype=F64) * u_h
+        ret = torch.cat([xb, ub], 2)
+        return torch.stack([ret] * self.nx, dim=1).to(self.torch_device)
+
+    def get_batch_x_hat_u_diff(self, x_h, u_h):
+        H = self.params["optimizer"]["H"]
+        x_h = torch.as_tensor(np.asarray(x_h), dtype=F64)
+        u_h = torch.as_tensor(np.asarray(u_h), dtype=F64)
+        xb = x_h.transpose(0, 1).reshape(self.ns_global, self.nx, H)[self.s_lo:self.s_hi].transpose(1, 2)
+        ub = u_h.transpose(0, 1).reshape(self.ns_global, H, self.nu)[self.s_lo:self.s_hi]
+        ret = torch.cat([xb, ub], 2)
+        return torch.stack([ret] * self.nx, dim=1).to(self.torch_device)
+
+    def get_g_xu_hat(self, xu_hat):
+        return xu_hat[:, 0:self.g_ny, :, list(self.spec.g_idx_inputs)].contiguous()
+
+    # ---- a9 ------------------------------------------------------------------------------------
+    def sample_gp(self, x_input, base_samples=None):
+        ag = self.params["agent"]
+        if self._appended_since_train:
+            raise NotImplementedError("sample_gp after update_hallucinated_Dyn_dataset without a new "
+                                      "train_hallucinated_dynGP: the reference would still use the old model")
+        if ag["Dyn_gp_min_data_dist"] >= 0.0:
+            return self._sample_gp_min_dist(x_input, base_samples)
+        if base_samples is None:  # GPyTorch draws torch.randn(*batch, q, 1) inside .sample()
+            base_samples = torch.randn(*x_input.shape[:-1], self.in_dim_y, dtype=F64, device=self.torch_device)
+            opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"], unclamped_sqrt_1x1=True)
+        else:
+            opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
+        mean, var, y, jl = self.engine.posterior(x_input, base_samples, opts)
+        self.model_i_call = _PosteriorView(mean, var, jl)
+        self.model_i_samples = y
+        return y
+
+    def _sample_gp_min_dist(self, x_input, base_samples):
+        """Dyn_gp_min_data_dist >= 0 (agent.py:666-698): the nearest fully observed training point's targets
+        replace the draw when it is closer than the threshold.  The distance test is a cross-point search that
+        is not fused yet: draw without truncation in the kernel, overwrite, then truncate (agent.py:701-708)."""
+        ag = self.params["agent"]
+        if base_samples is None:
+            base_samples = torch.randn(*x_input.shape[:-1], self.in_dim_y, dtype=F64, device=self.torch_device)
+        opts = self.engine.opts(-1.0, ag["Dyn_gp_variance_is_zero"])
+        mean, var, y, jl = self.engine.posterior(x_input, base_samples, opts)
+        x_train, y_train = self.model_i.train_inputs[0], self.model_i.train_targets
+        H = x_input.shape[2]
+        dist_norm = torch.linalg.vector_norm(x_input[:, :, None, :, :] - x_train[:, :, :, None, :], dim=-1)
+        isnan = torch.any(torch.isnan(y_train), dim=3).unsqueeze(-1).expand(-1, -1, -1, H)
+        dist_norm = dist_norm.masked_fill(isnan, float("inf"))
+        too_small = torch.any(dist_norm <= ag["Dyn_gp_min_data_dist"], dim=2).unsqueeze(-1).expand(-1, -1, -1, self.in_dim_y)
+        idx = torch.min(dist_norm, dim=2)[1]
+        closest = torch.gather(y_train, 2, idx.unsqueeze(-1).expand(-1, -1, -1, self.in_dim_y))
+        y = torch.where(too_small, closest, y)
+        sd = torch.sqrt(var)
+        y = torch.min(torch.max(y, mean - ag["Dyn_gp_beta"] * sd), mean + ag["Dyn_gp_beta"] * sd)
+        self.model_i_call = _PosteriorView(mean, var, jl)
+        self.model_i_samples = y
+        return y
+
+    # ---- a11 -----------------------------------------------------------------------------------
+    def update_hallucinated_Dyn_dataset(self, newX, newY):
+        min_distance = self.params["agent"]["Dyn_gp_min_data_dist"]
+        active = None
+        if min_distance >= 0.0:
+            # agent.py:166-191: NaN the labels of near-duplicates per sample, drop a point only if it is
+            # filtered for ALL samples; GPyTorch then masks a slot that is NaN for ANY batch element (A.4)
+            Xh, _ = self._hallucinated()
+            X_cond = torch.cat([self.Dyn_gp_X_train_batch, Xh], 2)
+            dist_norm = torch.linalg.vector_norm(newX[:, :, None, :, :] - X_cond[:, :, :, None, :], dim=-1)
+            filt = torch.any(dist_norm <= min_distance, dim=2)  # (ns, g_ny, H)
+            newY = newY.clone()
+            newY[filt.unsqueeze(-1).expand_as(newY)] = float("nan")
+            flags = torch.stack([torch.all(filt.reshape(-1, filt.shape[-1]), dim=0),
+                                 torch.any(filt.reshape(-1, filt.shape[-1]), dim=0)]).to(torch.int32)
+            if self.world_size > 1:  # the reference's all/any run over every sample, i.e. over all ranks
+                import torch.distributed as dist
+                f_all, f_any = flags[0].clone(), flags[1].clone()
+                dist.all_reduce(f_all, op=dist.ReduceOp.MIN)
+                dist.all_reduce(f_any, op=dist.ReduceOp.MAX)
+                flags = torch.stack([f_all, f_any])
+            flags = flags.cpu().numpy().astype(bool)
+            keep = ~flags[0]
+            if not keep.all():
+                newX, newY = newX[:, :, keep, :], newY[:, :, keep, :]
+            active = (~flags[1][keep]).astype(np.uint8)
+        if self._pending_reset:
+            self.engine.reset_hallucinated()
+            self._pending_reset = False
+        if newX.shape[2] > 0:
+            self.engine.append(newX.contiguous(), newY.contiguous(), active)
+        self._data_version += 1
+        self._appended_since_train = True
+
+    # ---- a10 -----------------------------------------------------------------------------------
+    def get_batch_gp_sensitivities(self, xu_hat, sqp_iter):
+        ag = self.params["agent"]
+        g_xu_hat = self.get_g_xu_hat(xu_hat)
+        H = self.params["optimizer"]["H"]
+        update = True
+        if (ag["true_dyn_as_sample"] or ag["mean_as_dyn_sample"]) and self.ns_global == 1:
+            y_sample = torch.zeros(1, self.g_ny, H, self.in_dim_y, dtype=F64, device=self.torch_device)
+            update = False
+        elif (ag["true_dyn_as_sample"] and ag["mean_as_dyn_sample"]) and self.ns_global == 2:
+            y_sample = torch.zeros(2, self.g_ny, H, self.in_dim_y, dtype=F64, device=self.torch_device)[self.s_lo:self.s_hi]
+            update = False
+        else:
+            y_sample = self.sample_gp(g_xu_hat, base_samples=self.epistimic_random_vector[self.mpc_iter][sqp_iter])
+        if not update:
+            mean, var = self.engine.posterior(g_xu_hat)
+            self.model_i_call = _PosteriorView(mean, var)
+        idx = 0  # global sample index of the next overwrite (agent.py:607-623)
+        if ag["true_dyn_as_sample"]:
+            if self.s_lo <= idx < self.s_hi:
+                true_dyn = self.spec.prior_data(g_xu_hat[idx - self.s_lo, 0].cpu()).to(self.torch_device)
+                if self.in_dim_y == 1:
+                    true_dyn = true_dyn[:, :, [0]]
+                y_sample[idx - self.s_lo] = true_dyn
+            idx += 1
+        if ag["mean_as_dyn_sample"]:
+            if self.s_lo <= idx < self.s_hi:
+                y_sample[idx - self.s_lo] = self.model_i_call.mean[idx - self.s_lo]
+            idx += 1
+        if update:
+            self.update_hallucinated_Dyn_dataset(g_xu_hat, y_sample)
+        return y_sample
+
+    # ---- a12 -----------------------------------------------------------------------------------
+    def dyn_fg_jacobians_device(self, xu_hat, sqp_iter) -> torch.Tensor:
+        """(ns, nx, H, 1+nx+nu) on the device: [f, df/dx, df/du] of every sampled dynamics."""
+        y_gp = self.get_batch_gp_sensitivities(xu_hat, sqp_iter)
+        return self.engine.assemble(self.env_struct, xu_hat, y_gp)
+
+    def dyn_fg_jacobians(self, xu_hat, sqp_iter):
+        y = self.dyn_fg_jacobians_device(xu_hat, sqp_iter)
+        host = torch.empty(y.shape, dtype=F64, pin_memory=True)
+        host.copy_(y, non_blocking=True)  # ONE device->host copy (the reference does three, agent.py:555-557)
+        torch.cuda.current_stream().synchronize()
+        h = host.numpy()
+        return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]

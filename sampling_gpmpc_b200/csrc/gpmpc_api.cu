@@ -1,0 +1,561 @@
+// libgpmpc_b200.so -- host side of the C ABI declared in include/gpmpc_b200.h.
+// Plain CUDA runtime, no torch types: the Python host (sampling_gpmpc_b200/engine.py) binds this with ctypes
+// and passes torch tensors' data_ptr() / the current torch stream handle.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gpmpc_assemble.cuh"
+#include "gpmpc_block.cuh"
+#include "gpmpc_step.cuh"
+
+namespace {
+std::string g_create_error;
+}
+
+struct gpmpc_handle {
+  DevState st{};
+  gpmpc_dims dims{};
+  int device = 0;
+  bool have_hypers = false, have_real = false;
+  bool condition = true;
+  std::string err;
+  // host mirrors / bookkeeping
+  std::vector<double> h_ls, h_os, h_noise;
+  long long factor_version = 0;  // bumped whenever the factor changes
+  long long cache_version = -1;  // factor_version the posterior cache was built against
+  int cache_H = 0;
+  int ws_n = 0, ws_q = 0, ws_H = 0;  // workspace capacity
+  long long launches = 0;
+  double last_bytes = 0.0, last_flops = 0.0;
+  // rollout scratch
+  double *r_xu = nullptr, *r_xstar = nullptr, *r_y = nullptr;
+  int r_ns = 0;
+  unsigned char* d_active = nullptr;
+  int d_active_cap = 0;
+  int max_dyn_smem = 0;
+};
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                           \
+      return GPMPC_ERR_CUDA;                                                                   \
+    }                                                                                          \
+  } while (0)
+
+static int fail(gpmpc_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+template <typename Tp>
+static cudaError_t dev_alloc(Tp** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  return cudaMalloc((void**)p, count * sizeof(Tp));
+}
+
+static void free_factor_state(gpmpc_handle* h) {
+  DevState& st = h->st;
+  cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task);
+  cudaFree(st.Lh); cudaFree(st.beta_h);
+  st.Xh = st.Yh = st.Lh = st.beta_h = nullptr;
+  st.hobs_pt = st.hobs_task = nullptr;
+}
+
+// (re)allocates the per-element state for `cap_points`, keeping what is already stored
+static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stream) {
+  DevState old = h->st;
+  DevState& st = h->st;
+  const int c_cap = cap_points * st.T;
+  const int ldL = ((st.m + c_cap + 3) / 4) * 4;
+  double *Xh, *Yh, *Lh, *beta_h;
+  int *hp, *ht;
+  const size_t B = (size_t)st.B;
+  CUDA_TRY(h, dev_alloc(&Xh, B * cap_points * st.d));
+  CUDA_TRY(h, dev_alloc(&Yh, B * cap_points * st.T));
+  CUDA_TRY(h, dev_alloc(&Lh, B * c_cap * (size_t)ldL));
+  CUDA_TRY(h, dev_alloc(&beta_h, B * c_cap));
+  CUDA_TRY(h, dev_alloc(&hp, (size_t)c_cap));
+  CUDA_TRY(h, dev_alloc(&ht, (size_t)c_cap));
+  if (old.Xh && old.np > 0) {
+    CUDA_TRY(h, cudaMemcpy2DAsync(Xh, (size_t)cap_points * st.d * 8, old.Xh, (size_t)old.cap_points * st.d * 8,
+                                  (size_t)old.np * st.d * 8, B, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(Yh, (size_t)cap_points * st.T * 8, old.Yh, (size_t)old.cap_points * st.T * 8,
+                                  (size_t)old.np * st.T * 8, B, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (old.Lh && old.c > 0) {
+    // rows keep their content; only the row stride and the per-element stride change
+    for (size_t b = 0; b < B; ++b)
+      CUDA_TRY(h, cudaMemcpy2DAsync(Lh + b * c_cap * (size_t)ldL, (size_t)ldL * 8,
+                                    old.Lh + b * old.c_cap * (size_t)old.ldL, (size_t)old.ldL * 8,
+                                    (size_t)(st.m + old.c) * 8, old.c, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(beta_h, (size_t)c_cap * 8, old.beta_h, (size_t)old.c_cap * 8,
+                                  (size_t)old.c * 8, B, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hp, old.hobs_pt, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpyAsync(ht, old.hobs_task, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (old.Xh) {
+    CUDA_TRY(h, cudaStreamSynchronize(stream));
+    free_factor_state(h);
+  }
+  st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
+  st.cap_points = cap_points; st.c_cap = c_cap; st.ldL = ldL;
+  h->dims.cap_points = cap_points;
+  return GPMPC_OK;
+}
+
+static int ensure_workspace(gpmpc_handle* h, int H) {
+  DevState& st = h->st;
+  const int n = st.m + st.c, q = H * st.T;
+  if (n <= h->ws_n && q <= h->ws_q && H <= h->ws_H && st.W) return GPMPC_OK;
+  const int new_n = std::max(n + n / 2, h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
+  st.W = st.S = st.C = st.mu = st.xc = nullptr;
+  const size_t B = (size_t)st.B;
+  CUDA_TRY(h, dev_alloc(&st.W, B * new_n * (size_t)new_q));
+  CUDA_TRY(h, dev_alloc(&st.S, B * (size_t)new_q * new_q));
+  CUDA_TRY(h, dev_alloc(&st.C, B * (size_t)new_q * new_q));
+  CUDA_TRY(h, dev_alloc(&st.mu, B * (size_t)new_q));
+  CUDA_TRY(h, dev_alloc(&st.xc, B * (size_t)new_H * st.d));
+  h->ws_n = new_n; h->ws_q = new_q; h->ws_H = new_H;
+  h->cache_version = -1;
+  return GPMPC_OK;
+}
+
+// algorithmic work of one conditioning step per batch element (DESIGN.md "roofline" section)
+static void count_work(gpmpc_handle* h, int H, bool append) {
+  const DevState& st = h->st;
+  const double m = st.m, c = st.c, q = (double)H * st.T, B = st.B, d = st.d, n = m + c;
+  double bytes = 8.0 * (c * m + c * (c + 1) / 2.0)            // own factor rows, read once
+                 + 8.0 * (H * d + 3.0 * q)                      // x in; mean, var, y out
+                 + 8.0 * c / st.T * d;                          // hallucinated inputs for the kernel vector
+  if (append) bytes += 8.0 * (q * n + q * (q + 1) / 2.0 + q);   // new rows + beta
+  double flops = q * m * m + 2.0 * q * c * m + q * c * c + q * q * n + q * q * q / 3.0 + 2.0 * q * n +
+                 q * (n + q) * (3.0 * d + 12.0);
+  h->last_bytes = bytes * B;
+  h->last_flops = flops * B;
+}
+
+extern "C" {
+
+const char* gpmpc_version(void) { return "gpmpc_b200 0.1 (sm_100a)"; }
+
+const char* gpmpc_last_error(const gpmpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
+  if (!dims || !out) return fail(nullptr, GPMPC_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (dims->ns < 1 || dims->g_ny < 1 || dims->d < 1 || dims->d > GPMPC_MAX_D || dims->n_real < 1 ||
+      dims->cap_points < 0 || !(dims->T == 1 || dims->T == dims->d + 1))
+    return fail(nullptr, GPMPC_ERR_ARG, "bad dims (need 1<=d<=6, T in {1,d+1}, ns,g_ny,n_real>=1)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, GPMPC_ERR_CUDA, "no CUDA device: gpmpc_b200 has no CPU fallback");
+  gpmpc_handle* h = new gpmpc_handle();
+  h->dims = *dims;
+  cudaGetDevice(&h->device);
+  cudaDeviceGetAttribute(&h->max_dyn_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  DevState& st = h->st;
+  st.ns = dims->ns; st.g_ny = dims->g_ny; st.d = dims->d; st.T = dims->T; st.n_real = dims->n_real;
+  st.B = dims->ns * dims->g_ny;
+  st.cap_points = dims->cap_points;
+  st.jitter = 1e-6;
+  unsigned* status;
+  if (dev_alloc(&status, 1) != cudaSuccess || cudaMemset(status, 0, 4) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, GPMPC_ERR_CUDA, "cudaMalloc(status) failed");
+  }
+  st.status = status;
+  *out = h;
+  return GPMPC_OK;
+}
+
+int gpmpc_destroy(gpmpc_handle* h) {
+  if (!h) return GPMPC_OK;
+  DevState& st = h->st;
+  free_factor_state(h);
+  cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
+  cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
+  cudaFree(st.Loo); cudaFree(st.LooT); cudaFree(st.beta_o); cudaFree(st.status);
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
+  cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active);
+  delete h;
+  return GPMPC_OK;
+}
+
+int gpmpc_set_hypers(gpmpc_handle* h, const double* lengthscale, const double* outputscale,
+                     const double* noise, double jitter) {
+  if (!h || !lengthscale || !outputscale || !noise) return fail(h, GPMPC_ERR_ARG, "null argument");
+  DevState& st = h->st;
+  for (int i = 0; i < st.g_ny * st.d; ++i)
+    if (!(lengthscale[i] > 0.0)) return fail(h, GPMPC_ERR_ARG, "lengthscale must be > 0");
+  for (int i = 0; i < st.g_ny; ++i)
+    if (!(outputscale[i] > 0.0)) return fail(h, GPMPC_ERR_ARG, "outputscale must be > 0");
+  h->h_ls.assign(lengthscale, lengthscale + st.g_ny * st.d);
+  h->h_os.assign(outputscale, outputscale + st.g_ny);
+  h->h_noise.assign(noise, noise + st.g_ny * st.T);
+  double *ls, *os, *nz;
+  if (!st.ls) {
+    CUDA_TRY(h, dev_alloc(&ls, (size_t)st.g_ny * st.d));
+    CUDA_TRY(h, dev_alloc(&os, (size_t)st.g_ny));
+    CUDA_TRY(h, dev_alloc(&nz, (size_t)st.g_ny * st.T));
+    st.ls = ls; st.os = os; st.noise = nz;
+  }
+  CUDA_TRY(h, cudaMemcpy((void*)st.ls, lengthscale, sizeof(double) * st.g_ny * st.d, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy((void*)st.os, outputscale, sizeof(double) * st.g_ny, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy((void*)st.noise, noise, sizeof(double) * st.g_ny * st.T, cudaMemcpyHostToDevice));
+  st.jitter = jitter;
+  h->have_hypers = true;
+  h->have_real = false;  // factor must be rebuilt
+  return GPMPC_OK;
+}
+
+int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void* stream_) {
+  if (!h || !X || !Y) return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (!h->have_hypers) return fail(h, GPMPC_ERR_STATE, "call gpmpc_set_hypers first");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevState& st = h->st;
+  const int n = st.n_real, T = st.T, g_ny = st.g_ny, d = st.d;
+  std::vector<double> hy((size_t)g_ny * n * T);
+  CUDA_TRY(h, cudaMemcpyAsync(hy.data(), Y, hy.size() * 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(h, cudaStreamSynchronize(stream));
+  // a slot is observed only if it is non-NaN for every batch element (here: every output)
+  std::vector<int> pt, task;
+  for (int p = 0; p < n; ++p)
+    for (int t = 0; t < T; ++t) {
+      bool ok = true;
+      for (int j = 0; j < g_ny; ++j) ok = ok && !std::isnan(hy[((size_t)j * n + p) * T + t]);
+      if (ok) { pt.push_back(p); task.push_back(t); }
+    }
+  const int m = (int)pt.size();
+  if (m == 0) return fail(h, GPMPC_ERR_ARG, "no observed real data");
+  std::vector<double> yobs((size_t)g_ny * m);
+  for (int j = 0; j < g_ny; ++j)
+    for (int i = 0; i < m; ++i) yobs[(size_t)j * m + i] = hy[((size_t)j * n + pt[i]) * T + task[i]];
+
+  cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
+  cudaFree(st.Loo); cudaFree(st.LooT); cudaFree(st.beta_o);
+  double *Xr, *yo; int *op, *ot;
+  CUDA_TRY(h, dev_alloc(&Xr, (size_t)n * d));
+  CUDA_TRY(h, dev_alloc(&op, (size_t)m));
+  CUDA_TRY(h, dev_alloc(&ot, (size_t)m));
+  CUDA_TRY(h, dev_alloc(&yo, (size_t)g_ny * m));
+  CUDA_TRY(h, dev_alloc(&st.Loo, (size_t)g_ny * m * m));
+  CUDA_TRY(h, dev_alloc(&st.LooT, (size_t)g_ny * ((size_t)m * (m + 1) / 2)));
+  CUDA_TRY(h, dev_alloc(&st.beta_o, (size_t)g_ny * m));
+  CUDA_TRY(h, cudaMemcpyAsync(Xr, X, (size_t)n * d * 8, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(h, cudaMemcpyAsync(op, pt.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(h, cudaMemcpyAsync(ot, task.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(h, cudaMemcpyAsync(yo, yobs.data(), yobs.size() * 8, cudaMemcpyHostToDevice, stream));
+  st.Xr = Xr; st.obs_pt = op; st.obs_task = ot; st.y_obs = yo;
+  const bool m_changed = (m != st.m);
+  st.m = m;
+  st.c = 0; st.np = 0;
+  if (m_changed || !st.Lh) {
+    // ldL depends on m: (re)allocate the per-element state from scratch
+    free_factor_state(h);
+    int rc = alloc_factor_state(h, st.cap_points, stream);
+    if (rc) return rc;
+  }
+  k_factor_real<<<g_ny, BLK_THREADS, 0, stream>>>(st);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaStreamSynchronize(stream));  // host staging vectors go out of scope
+  h->have_real = true;
+  h->factor_version++;
+  h->ws_n = 0;  // force workspace re-evaluation
+  return GPMPC_OK;
+}
+
+int gpmpc_reset_hallucinated(gpmpc_handle* h) {
+  if (!h) return GPMPC_ERR_ARG;
+  h->st.c = 0;
+  h->st.np = 0;
+  h->factor_version++;
+  return GPMPC_OK;
+}
+
+int gpmpc_reserve(gpmpc_handle* h, int32_t cap_points, void* stream) {
+  if (!h || cap_points < 0) return fail(h, GPMPC_ERR_ARG, "bad capacity");
+  if (!h->have_real) { h->st.cap_points = std::max(h->st.cap_points, cap_points); return GPMPC_OK; }
+  if (cap_points <= h->st.cap_points) return GPMPC_OK;
+  return alloc_factor_state(h, cap_points, (cudaStream_t)stream);
+}
+
+int gpmpc_set_condition_on_hallucinated(gpmpc_handle* h, int32_t on) {
+  if (!h) return GPMPC_ERR_ARG;
+  h->condition = on != 0;
+  return GPMPC_OK;
+}
+
+static int check_ready(gpmpc_handle* h) {
+  if (!h) return GPMPC_ERR_ARG;
+  if (!h->have_real) return fail(h, GPMPC_ERR_STATE, "call gpmpc_set_hypers and gpmpc_set_real_data first");
+  return GPMPC_OK;
+}
+
+int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, double* var,
+                    const double* eps, const gpmpc_sample_opts* opts, double* y, int32_t* jitter_level,
+                    void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / H");
+  if (eps && (!opts || !y)) return fail(h, GPMPC_ERR_ARG, "eps given without opts / y");
+  rc = ensure_workspace(h, H);
+  if (rc) return rc;
+  DevState st = h->st;
+  st.W_stride = (long long)h->ws_n * (H * st.T);
+  gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
+  k_posterior<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, x, H, mean, var, eps, o, y, jitter_level);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  h->cache_version = h->factor_version;
+  h->cache_H = H;
+  count_work(h, H, false);
+  return GPMPC_OK;
+}
+
+int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* opts, double* y,
+                 int32_t* jitter_level, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!eps || !opts || !y) return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (h->cache_version != h->factor_version || h->cache_H < 1)
+    return fail(h, GPMPC_ERR_STATE, "gpmpc_sample needs a preceding gpmpc_posterior on the current factor");
+  DevState st = h->st;
+  st.W_stride = (long long)h->ws_n * (h->cache_H * st.T);
+  k_sample<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, h->cache_H, eps, *opts, y, jitter_level);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_t* point_active, int32_t H,
+                 void* stream_) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || !y || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / H");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevState& hst = h->st;
+  if (H * hst.T > 512) return fail(h, GPMPC_ERR_ARG, "gpmpc_append supports at most 512 new scalars per call");
+  int n_active = 0;
+  for (int i = 0; i < H; ++i) n_active += (!point_active || point_active[i]) ? 1 : 0;
+  if (hst.np + H > hst.cap_points) {
+    rc = alloc_factor_state(h, std::max(hst.np + H, hst.cap_points * 2), stream);
+    if (rc) return rc;
+  }
+  const bool grow = h->condition && n_active > 0;
+  unsigned char* d_act = nullptr;
+  if (grow) {
+    rc = ensure_workspace(h, H);
+    if (rc) return rc;
+    if (point_active && n_active < H) {
+      if (h->d_active_cap < H) {
+        cudaFree(h->d_active);
+        CUDA_TRY(h, dev_alloc(&h->d_active, (size_t)H));
+        h->d_active_cap = H;
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_active, point_active, (size_t)H, cudaMemcpyHostToDevice, stream));
+      d_act = h->d_active;
+    }
+  }
+  DevState st = h->st;
+  st.W_stride = (long long)h->ws_n * (H * st.T);
+  const int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
+  k_append<<<st.B, BLK_THREADS, 0, stream>>>(st, x, y, d_act, H, st.np, reuse, grow ? 1 : 0);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  if (d_act) CUDA_TRY(h, cudaStreamSynchronize(stream));  // caller may reuse point_active's host memory
+  count_work(h, H, grow);
+  hst.np += H;
+  if (grow) {
+    hst.c += n_active * hst.T;
+    h->factor_version++;
+  }
+  return GPMPC_OK;
+}
+
+}  // extern "C"
+
+template <int D, int T>
+static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                       const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                       cudaStream_t stream) {
+  const int m = st.m, n = st.m + st.c;
+  const int n_pad = ((n + 1) & ~1) + 2;
+  const size_t tri = (size_t)m * (m + 1) / 2;
+  size_t shared_tab = ((size_t)m * D + m) * 8 + (size_t)((m + 1) & ~1) * 4;
+  size_t per_warp = (size_t)T * n_pad * 8;
+  int loo_in_smem = 1;
+  size_t smem = tri * 8 + shared_tab + STEP_WARPS * per_warp;
+  if (smem > 100 * 1024) {  // keep >= 2 CTAs per SM; the shared factor then comes from L2
+    loo_in_smem = 0;
+    smem = shared_tab + STEP_WARPS * per_warp;
+  }
+  if ((int)smem > h->max_dyn_smem) return fail(h, GPMPC_ERR_CAPACITY, "factor too large for the fused step kernel");
+  auto kern = k_step<D, T>;
+  static size_t configured = 0;  // per instantiation
+  if (smem > 48 * 1024 && smem > configured) {
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+    configured = h->max_dyn_smem;
+  }
+  dim3 grid((st.ns + STEP_WARPS - 1) / STEP_WARPS, st.g_ny);
+  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, n_pad, loo_in_smem);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+static int dispatch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                         const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                         cudaStream_t stream) {
+#define STEP_CASE(D_)                                                                            \
+  case D_:                                                                                       \
+    return st.T == 1 ? launch_step<D_, 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream)      \
+                     : launch_step<D_, D_ + 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
+  switch (st.d) {
+    STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6)
+  }
+#undef STEP_CASE
+  return fail(h, GPMPC_ERR_ARG, "unsupported d");
+}
+
+extern "C" {
+
+int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_sample_opts* opts,
+               double* mean, double* var, double* y, int32_t* jitter_level, void* stream_) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x) return fail(h, GPMPC_ERR_ARG, "null x");
+  if (eps && (!opts || !y)) return fail(h, GPMPC_ERR_ARG, "eps given without opts / y");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevState& hst = h->st;
+  if (eps && hst.np + 1 > hst.cap_points) {
+    rc = alloc_factor_state(h, std::max(hst.np + 1, hst.cap_points * 2), stream);
+    if (rc) return rc;
+  }
+  const int grow = (eps && h->condition) ? 1 : 0;
+  gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
+  count_work(h, 1, grow);
+  rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream);
+  if (rc) return rc;
+  if (eps) {
+    hst.np += 1;
+    if (grow) {
+      hst.c += hst.T;
+      h->factor_version++;
+    }
+  }
+  return GPMPC_OK;
+}
+
+int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, const double* y_gp, int32_t H,
+                   double* out, void* stream) {
+  if (!h || !env || !xu || !y_gp || !out || H < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (env->nx > GPMPC_MAX_NX || env->nx + env->nu > 2 * GPMPC_MAX_NX || env->g_ny != h->st.g_ny)
+    return fail(h, GPMPC_ERR_ARG, "bad env dims");
+  const long long total = (long long)h->st.ns * env->nx * H;
+  const int threads = 128;
+  const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148LL * 16);
+  k_assemble<<<blocks, threads, 0, (cudaStream_t)stream>>>(*env, h->st.ns, H, h->st.T, xu, y_gp, out);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
+                  const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
+                  void* stream_) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!env || !x0 || !u_ff || !eps || !opts || !traj || n_steps < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (env->g_ny != h->st.g_ny || env->d != h->st.d) return fail(h, GPMPC_ERR_ARG, "env does not match handle");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DevState& hst = h->st;
+  const int ns = hst.ns, nz = env->nx + env->nu;
+  if (h->r_ns < ns) {
+    cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y);
+    CUDA_TRY(h, dev_alloc(&h->r_xu, (size_t)ns * 2 * GPMPC_MAX_NX));
+    CUDA_TRY(h, dev_alloc(&h->r_xstar, (size_t)hst.B * GPMPC_MAX_D));
+    CUDA_TRY(h, dev_alloc(&h->r_y, (size_t)hst.B * GPMPC_MAX_T));
+    h->r_ns = ns;
+  }
+  (void)nz;
+  if (h->condition && hst.np + n_steps > hst.cap_points) {
+    rc = alloc_factor_state(h, hst.np + n_steps, stream);
+    if (rc) return rc;
+  } else if (!h->condition && hst.np + n_steps > hst.cap_points) {
+    rc = alloc_factor_state(h, hst.np + n_steps, stream);
+    if (rc) return rc;
+  }
+  const int threads = 128, blocks = (ns + threads - 1) / threads;
+  const size_t eps_stride = (size_t)hst.B * hst.T;
+  double bytes = 0.0, flops = 0.0;
+  k_rollout_state<<<blocks, threads, 0, stream>>>(*env, ns, hst.T, 0, n_steps, 0, x0, u_ff, h->r_y, h->r_xu,
+                                                   h->r_xstar, traj);
+  h->launches++;
+  for (int t = 0; t < n_steps; ++t) {
+    rc = gpmpc_step(h, h->r_xstar, eps + (size_t)t * eps_stride, opts, nullptr, nullptr, h->r_y, nullptr, stream);
+    if (rc) return rc;
+    bytes += h->last_bytes;
+    flops += h->last_flops;
+    k_rollout_state<<<blocks, threads, 0, stream>>>(*env, ns, hst.T, t + 1, n_steps, 1, x0, u_ff, h->r_y,
+                                                     h->r_xu, h->r_xstar, traj);
+    h->launches++;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  h->last_bytes = bytes;
+  h->last_flops = flops;
+  return GPMPC_OK;
+}
+
+int32_t gpmpc_num_hallucinated(const gpmpc_handle* h) { return h ? h->st.np : -1; }
+int32_t gpmpc_num_factor_rows(const gpmpc_handle* h) { return h ? h->st.c : -1; }
+int32_t gpmpc_num_real_observed(const gpmpc_handle* h) { return h ? h->st.m : -1; }
+
+int gpmpc_export_hallucinated(const gpmpc_handle* h_, double* X, double* Y, void* stream) {
+  gpmpc_handle* h = const_cast<gpmpc_handle*>(h_);
+  if (!h || !X || !Y) return fail(h, GPMPC_ERR_ARG, "null argument");
+  const DevState& st = h->st;
+  if (st.np == 0) return GPMPC_OK;
+  CUDA_TRY(h, cudaMemcpy2DAsync(X, (size_t)st.np * st.d * 8, st.Xh, (size_t)st.cap_points * st.d * 8,
+                                (size_t)st.np * st.d * 8, st.B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CUDA_TRY(h, cudaMemcpy2DAsync(Y, (size_t)st.np * st.T * 8, st.Yh, (size_t)st.cap_points * st.T * 8,
+                                (size_t)st.np * st.T * 8, st.B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GPMPC_OK;
+}
+
+int gpmpc_status(gpmpc_handle* h, uint32_t* status, int32_t clear, void* stream) {
+  if (!h || !status) return fail(h, GPMPC_ERR_ARG, "null argument");
+  CUDA_TRY(h, cudaMemcpyAsync(status, h->st.status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  if (clear) CUDA_TRY(h, cudaMemsetAsync(h->st.status, 0, 4, (cudaStream_t)stream));
+  CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+  return GPMPC_OK;
+}
+
+int64_t gpmpc_state_bytes(const gpmpc_handle* h) {
+  if (!h) return -1;
+  const DevState& st = h->st;
+  const int64_t B = st.B;
+  return 8 * (B * st.c_cap * (int64_t)st.ldL + B * st.c_cap + B * st.cap_points * (int64_t)(st.d + st.T)) +
+         8 * (int64_t)st.g_ny * ((int64_t)st.m * st.m + (int64_t)st.m * (st.m + 1) / 2 + st.m);
+}
+
+int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops) {
+  if (!h) return GPMPC_ERR_ARG;
+  if (bytes) *bytes = h->last_bytes;
+  if (flops) *flops = h->last_flops;
+  return GPMPC_OK;
+}
+
+int64_t gpmpc_launch_count(const gpmpc_handle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

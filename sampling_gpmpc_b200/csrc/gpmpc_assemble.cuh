@@ -1,0 +1,89 @@
+// K3: what Agent.dyn_fg_jacobians does around the GP call, as one elementwise kernel, and the state
+// bookkeeping of a forward rollout (so a whole horizon runs on the stream without host round trips).
+#pragma once
+#include "gpmpc_state.cuh"
+
+// transform_sensitivity (identity: pendulum1D.py:240-241; residual car: car_model_residual.py:211-224)
+// followed by the scatter into pad_g (src/agent.py:545-550).  Returns entry p of the padded row.
+__device__ __forceinline__ double transformed_entry(const gpmpc_env& env, const double* __restrict__ yg, int T,
+                                                    double v, int p) {
+  if (env.transform == 1) {
+    // [v g, v dg/dphi, g, v dg/ddelta]; with T == 1 torch broadcasting copies g into every slot
+    if (p == 2) return yg[0];
+    int src = p == 0 ? 0 : (p == 1 ? 1 : 2);
+    if (src > T - 1) src = T - 1;
+    return v * yg[src];
+  }
+  return yg[p < T ? p : T - 1];
+}
+
+// out[s][i][h][:] = [f_i, df_i/dx, df_i/du] + sum_j B_d[i][j] * pad(transform(y_gp[s][j][h][:]))
+__global__ void k_assemble(gpmpc_env env, int ns, int H, int T, const double* __restrict__ xu,
+                           const double* __restrict__ y_gp, double* __restrict__ out) {
+  const int nx = env.nx, nu = env.nu, nz = nx + nu, w = 1 + nz;
+  const long long total = (long long)ns * nx * H;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(idx % H);
+    const int i = (int)((idx / H) % nx);
+    const long long s = idx / ((long long)H * nx);
+    const double* z = xu + ((s * nx + 0) * H + h) * nz;  // row 0 of the nx tiled copies
+    double* o = out + ((s * nx + i) * H + h) * w;
+    double f = 0.0;
+    for (int k = 0; k < nz; ++k) {
+      const double Fik = env.F_known[i * nz + k];
+      f += Fik * z[k];
+      o[1 + k] = Fik;
+    }
+    o[0] = f;
+    const double v = nz > 3 ? z[3] : 0.0;
+    for (int j = 0; j < env.g_ny; ++j) {
+      const double bij = env.B_d[i * env.g_ny + j];
+      if (bij == 0.0) continue;
+      const double* yg = y_gp + ((s * env.g_ny + j) * H + h) * T;
+      for (int p = 0; p < env.n_pad; ++p) o[env.pad_g[p]] += bij * transformed_entry(env, yg, T, v, p);
+    }
+  }
+}
+
+// Rollout bookkeeping, one thread per sample.  phase 0: x_cur = x0.  phase 1: x_cur = F xu + B_d pad(y)[0].
+// Then (if t < n_steps) builds xu_t = [x_cur, u_t (+feedback)], records traj[:, :, t] and gathers the GP input.
+__global__ void k_rollout_state(gpmpc_env env, int ns, int T, int t, int n_steps, int phase,
+                                const double* __restrict__ x0, const double* __restrict__ u_ff,
+                                const double* __restrict__ y_gp, double* __restrict__ xu,
+                                double* __restrict__ xstar, double* __restrict__ traj) {
+  const int nx = env.nx, nu = env.nu, nz = nx + nu;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  double xc[GPMPC_MAX_NX];
+  double* z = xu + (size_t)s * nz;
+  if (phase == 0) {
+    for (int i = 0; i < nx; ++i) xc[i] = x0[(size_t)s * nx + i];
+  } else {
+    const double v = nz > 3 ? z[3] : 0.0;
+    for (int i = 0; i < nx; ++i) {
+      double f = 0.0;
+      for (int k = 0; k < nz; ++k) f += env.F_known[i * nz + k] * z[k];
+      for (int j = 0; j < env.g_ny; ++j) {
+        const double bij = env.B_d[i * env.g_ny + j];
+        if (bij != 0.0) {
+          const double* yg = y_gp + ((size_t)s * env.g_ny + j) * T;
+          for (int p = 0; p < env.n_pad; ++p)
+            if (env.pad_g[p] == 0) f += bij * transformed_entry(env, yg, T, v, p);
+        }
+      }
+      xc[i] = f;
+    }
+  }
+  for (int i = 0; i < nx; ++i) traj[((size_t)s * nx + i) * (n_steps + 1) + t] = xc[i];
+  if (t >= n_steps) return;
+  for (int i = 0; i < nx; ++i) z[i] = xc[i];
+  for (int k = 0; k < nu; ++k) {
+    double u = u_ff[(size_t)t * nu + k];
+    if (env.use_feedback)
+      for (int i = 0; i < nx; ++i) u -= env.K_fb[k * nx + i] * (env.x_equi[i] - xc[i]);
+    z[nx + k] = u;
+  }
+  for (int j = 0; j < env.g_ny; ++j)
+    for (int a = 0; a < env.d; ++a) xstar[((size_t)s * env.g_ny + j) * env.d + a] = z[env.g_idx_inputs[a]];
+}

@@ -1,0 +1,336 @@
+// General (any H, any n) kernels: one CTA per batch element, state and workspace in global memory
+// (L2-resident at the SQP sizes: B <= a few hundred elements).  These serve the SQP linearisation
+// (q = H*T = 51..150 joint test scalars) and are the reference semantics for the fused rollout kernel.
+//
+//   k_factor_real : K0  chol(K_oo + Sigma) per GP output, once per real-data change
+//   k_posterior   : K_{o*}, W = L^{-1} K_{o*}, Sigma* = K** - W^T W, mean = W^T beta  (+ optional draw)
+//   k_sample      : chol(Sigma*) with GPyTorch's jitter ladder, y = mean + L eps, post-processing
+//   k_append      : chol(Sigma* + noise) -> new bordered rows [W^T | L_nn], beta_h
+#pragma once
+#include "gpmpc_state.cuh"
+
+#define BLK_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// In-place lower Cholesky of the n x n matrix A (row-major, leading dim ld), cooperative over the CTA.
+// LAPACK potrf semantics as used by torch.linalg.cholesky_ex: returns k+1 if pivot k is <= 0 or NaN.
+// ------------------------------------------------------------------------------------------------
+__device__ int block_cholesky(double* A, int n, int ld) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    double akk = A[(size_t)k * ld + k];
+    if (!(akk > 0.0)) return k + 1;  // uniform: every thread reads the same value
+    double lkk = sqrt(akk);
+    __syncthreads();
+    if (tid == 0) A[(size_t)k * ld + k] = lkk;
+    for (int i = k + 1 + tid; i < n; i += nt) A[(size_t)i * ld + k] /= lkk;
+    __syncthreads();
+    const int rem = n - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      int i = k + 1 + idx / rem, cc = k + 1 + idx % rem;
+      if (cc <= i) A[(size_t)i * ld + cc] -= A[(size_t)i * ld + k] * A[(size_t)cc * ld + k];
+    }
+  }
+  __syncthreads();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: shared real-data block.  grid = g_ny, block = BLK_THREADS.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
+  const int j = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int m = st.m, d = st.d;
+  double* A = st.Loo + (size_t)j * m * m;
+  const double* ls = st.ls + j * d;
+  const double os = st.os[j];
+  const double* noise = st.noise + j * st.T;
+  int level = 0;
+  for (;;) {
+    // psd_safe_cholesky: try 0 without jitter, then total jitter*10^(level-1) on the diagonal
+    double add = level == 0 ? 0.0 : st.jitter * pow(10.0, (double)(level - 1));
+    for (int idx = tid; idx < m * m; idx += nt) {
+      int i = idx / m, cc = idx % m;
+      double v = 0.0;
+      if (cc <= i) {
+        v = cov_scalar(st.Xr + (size_t)st.obs_pt[i] * d, st.obs_task[i], st.Xr + (size_t)st.obs_pt[cc] * d,
+                       st.obs_task[cc], ls, os, d);
+        if (cc == i) v += noise[st.obs_task[i]] + add;
+      }
+      A[idx] = v;
+    }
+    int info = block_cholesky(A, m, m);
+    if (info == 0) break;
+    if (level == GP_MAX_TRIES) {
+      if (tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_NOT_PD);
+      break;
+    }
+    ++level;
+    __syncthreads();
+  }
+  if (level > 0 && tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_JITTER | ((unsigned)level << 8));
+  // packed column-major copy for the fused rollout kernel
+  double* LT = st.LooT + (size_t)j * ((size_t)m * (m + 1) / 2);
+  for (int idx = tid; idx < m * m; idx += nt) {
+    int i = idx / m, cc = idx % m;
+    if (cc <= i) LT[packed_col(cc, m) + (i - cc)] = A[idx];
+  }
+  // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
+  if (tid < 32) {
+    const double* y = st.y_obs + (size_t)j * m;
+    double* beta = st.beta_o + (size_t)j * m;
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int k = tid; k < i; k += 32) acc += A[(size_t)i * m + k] * beta[k];
+      acc = warp_sum(acc);
+      if (tid == 0) beta[i] = (y[i] - acc) / A[(size_t)i * m + i];
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Posterior pieces (device functions shared by k_posterior and k_append's recompute path)
+// ------------------------------------------------------------------------------------------------
+#define FS_ROWS 16
+
+// W[i][r] = cov(train scalar i, test scalar r); then W <- L^{-1} W; S = K** - W^T W; mu = W^T beta.
+__device__ void block_posterior(const DevState& st, int b, const double* __restrict__ x, int H) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int j = b % st.g_ny, d = st.d, T = st.T;
+  const int n = st.m + st.c, q = H * T;
+  double* W = st.W + (size_t)b * st.W_stride;
+  double* S = st.S + (size_t)b * q * q;
+  double* mu = st.mu + (size_t)b * q;
+  double* xc = st.xc + (size_t)b * H * d;
+  const double* ls = st.ls + j * d;
+  const double os = st.os[j];
+  const double* xb = x + (size_t)b * H * d;
+
+  for (int idx = tid; idx < H * d; idx += nt) xc[idx] = xb[idx];
+  for (int idx = tid; idx < n * q; idx += nt) {
+    int i = idx / q, r = idx % q, ta;
+    const double* xa = train_scalar(st, b, i, ta);
+    W[idx] = cov_scalar(xa, ta, xb + (size_t)(r / T) * d, r % T, ls, os, d);
+  }
+  __syncthreads();
+
+  // blocked forward substitution against the bordered factor
+  for (int i0 = 0; i0 < n; i0 += FS_ROWS) {
+    const int rb = min(FS_ROWS, n - i0);
+    for (int idx = tid; idx < rb * q; idx += nt) {
+      int a = idx / q, r = idx % q;
+      const double* Lrow = factor_row(st, b, j, i0 + a);
+      double acc = 0.0;
+      for (int k = 0; k < i0; ++k) acc += Lrow[k] * W[(size_t)k * q + r];
+      W[(size_t)(i0 + a) * q + r] -= acc;
+    }
+    __syncthreads();
+    for (int r = tid; r < q; r += nt) {  // a thread owns column r: no sync needed inside the block
+      for (int a = 0; a < rb; ++a) {
+        const double* Lrow = factor_row(st, b, j, i0 + a);
+        double v = W[(size_t)(i0 + a) * q + r];
+        for (int bb = 0; bb < a; ++bb) v -= Lrow[i0 + bb] * W[(size_t)(i0 + bb) * q + r];
+        W[(size_t)(i0 + a) * q + r] = v / Lrow[i0 + a];
+      }
+    }
+    __syncthreads();
+  }
+
+  // Sigma* (lower triangle) and mean
+  const double* beta_o = st.beta_o + (size_t)j * st.m;
+  const double* beta_h = st.beta_h + (size_t)b * st.c_cap;
+  for (int idx = tid; idx < q * q; idx += nt) {
+    int r = idx / q, s = idx % q;
+    if (s > r) continue;
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += W[(size_t)i * q + r] * W[(size_t)i * q + s];
+    double kss = cov_scalar(xb + (size_t)(r / T) * d, r % T, xb + (size_t)(s / T) * d, s % T, ls, os, d);
+    S[idx] = kss - acc;
+  }
+  for (int r = tid; r < q; r += nt) {
+    double acc = 0.0;
+    for (int i = 0; i < st.m; ++i) acc += W[(size_t)i * q + r] * beta_o[i];
+    for (int i = st.m; i < n; ++i) acc += W[(size_t)i * q + r] * beta_h[i - st.m];
+    mu[r] = acc;
+  }
+  __syncthreads();
+}
+
+// chol(Sigma*) with the psd_safe_cholesky ladder, y = mu + L eps, then sample_gp's post-processing
+// (zero-variance -> mean, truncation to mean +- beta sqrt(var); src/agent.py:646-663,701-708).
+__device__ void block_sample(const DevState& st, int b, int H, const double* __restrict__ eps,
+                             gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T = st.T, q = H * T;
+  const double* S = st.S + (size_t)b * q * q;
+  double* C = st.C + (size_t)b * q * q;
+  const double* mu = st.mu + (size_t)b * q;
+  const double* e = eps + (size_t)b * q;
+  double* yb = y + (size_t)b * q;
+  int level = 0;
+  if (q == 1) {
+    // LinearOperator._cholesky of a 1x1: clamp_min(0).sqrt(); zero_mean_mvn_samples: plain sqrt
+    if (tid == 0) C[0] = opts.unclamped_sqrt_1x1 ? sqrt(S[0]) : sqrt(fmax(S[0], 0.0));
+    __syncthreads();
+  } else {
+    for (;;) {
+      double add = level == 0 ? 0.0 : st.jitter * pow(10.0, (double)(level - 1));
+      for (int idx = tid; idx < q * q; idx += nt) {
+        int r = idx / q, s = idx % q;
+        double v = s <= r ? S[idx] : 0.0;
+        if (s == r) v += add;
+        C[idx] = v;
+      }
+      int info = block_cholesky(C, q, q);
+      if (info == 0) break;
+      // NaN anywhere makes GPyTorch raise NanError instead of climbing the ladder
+      if (level == GP_MAX_TRIES) {
+        level = 4;
+        if (tid == 0) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+        break;
+      }
+      ++level;
+      __syncthreads();
+    }
+  }
+  if (tid == 0 && jitter_level) jitter_level[b] = level;
+  for (int r = tid; r < q; r += nt) {
+    double acc = mu[r];
+    if (level < 4)
+      for (int s = 0; s <= r; ++s) acc += C[(size_t)r * q + s] * e[s];
+    else
+      acc = nan("");
+    yb[r] = acc;
+  }
+  __syncthreads();
+  for (int h = tid; h < H; h += nt) {
+    bool zero = opts.variance_is_zero >= 0.0;
+    if (zero)
+      for (int t = 0; t < T; ++t) {
+        double v = fmax(S[(size_t)(h * T + t) * q + h * T + t], GP_MIN_VARIANCE);
+        zero = zero && (v <= opts.variance_is_zero);
+      }
+    for (int t = 0; t < T; ++t) {
+      int r = h * T + t;
+      double v = fmax(S[(size_t)r * q + r], GP_MIN_VARIANCE), mr = mu[r], yy = yb[r];
+      if (zero) yy = mr;
+      if (opts.beta >= 0.0) {
+        double sd = sqrt(v);
+        yy = fmin(fmax(yy, mr - opts.beta * sd), mr + opts.beta * sd);
+      }
+      yb[r] = yy;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(BLK_THREADS)
+k_posterior(DevState st, const double* __restrict__ x, int H, double* __restrict__ mean,
+            double* __restrict__ var, const double* __restrict__ eps, gpmpc_sample_opts opts,
+            double* __restrict__ y, int* __restrict__ jitter_level) {
+  const int b = blockIdx.x, q = H * st.T;
+  block_posterior(st, b, x, H);
+  const double* S = st.S + (size_t)b * q * q;
+  const double* mu = st.mu + (size_t)b * q;
+  for (int r = threadIdx.x; r < q; r += blockDim.x) {
+    if (mean) mean[(size_t)b * q + r] = mu[r];
+    if (var) var[(size_t)b * q + r] = fmax(S[(size_t)r * q + r], GP_MIN_VARIANCE);
+  }
+  if (eps) block_sample(st, b, H, eps, opts, y, jitter_level);
+}
+
+__global__ void __launch_bounds__(BLK_THREADS)
+k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts opts, double* __restrict__ y,
+         int* __restrict__ jitter_level) {
+  block_sample(st, blockIdx.x, H, eps, opts, y, jitter_level);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Conditioning: append the active points' T scalars each to element b's factor.
+//   reuse != 0 : the workspace may hold W, S, mu for exactly these x (checked per element on device)
+//   active     : DEVICE uint8[H] or NULL; pt_base = index of the first new point in Xh/Yh
+// New rows k = c + r':  Lh[k][0..n) = W[:, act(r')],  Lh[k][n + s'] = chol(S_act + noise)[r'][s'].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLK_THREADS)
+k_append(DevState st, const double* __restrict__ x, const double* __restrict__ ylab,
+         const unsigned char* __restrict__ active, int H, int pt_base, int reuse, int grow_factor) {
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int j = b % st.g_ny, d = st.d, T = st.T, q = H * T;
+  const int n = st.m + st.c;
+  __shared__ int sh_same;
+  __shared__ int sh_act[512];  // active test scalars (q' <= 512 checked by the host)
+  __shared__ int sh_qa;
+
+  // record the points (labels keep their NaNs)
+  for (int idx = tid; idx < H * d; idx += nt)
+    st.Xh[((size_t)b * st.cap_points + pt_base) * d + idx] = x[(size_t)b * H * d + idx];
+  for (int idx = tid; idx < H * T; idx += nt)
+    st.Yh[((size_t)b * st.cap_points + pt_base) * T + idx] = ylab[(size_t)b * q + idx];
+  if (!grow_factor) return;
+
+  if (tid == 0) {
+    sh_same = reuse;
+    int qa = 0;
+    for (int h = 0; h < H; ++h)
+      if (!active || active[h])
+        for (int t = 0; t < T; ++t) sh_act[qa++] = h * T + t;
+    sh_qa = qa;
+  }
+  __syncthreads();
+  if (reuse) {
+    const double* xc = st.xc + (size_t)b * H * d;
+    for (int idx = tid; idx < H * d; idx += nt)
+      if (xc[idx] != x[(size_t)b * H * d + idx]) sh_same = 0;  // benign race: all writers store 0
+    __syncthreads();
+  }
+  if (!sh_same) block_posterior(st, b, x, H);
+  const int qa = sh_qa;
+  if (qa == 0) return;
+
+  const double* W = st.W + (size_t)b * st.W_stride;
+  const double* S = st.S + (size_t)b * q * q;
+  double* C = st.C + (size_t)b * q * q;  // used as qa x qa, leading dim qa
+  const double* mu = st.mu + (size_t)b * q;
+  const double* noise = st.noise + j * T;
+  for (int idx = tid; idx < qa * qa; idx += nt) {
+    int rr = idx / qa, ss = idx % qa;
+    double v = 0.0;
+    if (ss <= rr) {
+      v = S[(size_t)sh_act[rr] * q + sh_act[ss]];
+      if (ss == rr) v += noise[sh_act[rr] % T];
+    }
+    C[idx] = v;
+  }
+  int info = block_cholesky(C, qa, qa);
+  if (info != 0) {
+    if (tid == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
+    return;
+  }
+  double* Lnew = st.Lh + ((size_t)b * st.c_cap + st.c) * st.ldL;
+  for (int idx = tid; idx < qa * n; idx += nt) {
+    int rr = idx / n, k = idx % n;
+    Lnew[(size_t)rr * st.ldL + k] = W[(size_t)k * q + sh_act[rr]];
+  }
+  for (int idx = tid; idx < qa * qa; idx += nt) {
+    int rr = idx / qa, ss = idx % qa;
+    if (ss <= rr) Lnew[(size_t)rr * st.ldL + n + ss] = C[idx];
+  }
+  // beta_new = L_nn^{-1} (y - mu)
+  if (tid < 32) {
+    double* beta = st.beta_h + (size_t)b * st.c_cap + st.c;
+    const double* yb = ylab + (size_t)b * q;
+    for (int rr = 0; rr < qa; ++rr) {
+      double acc = 0.0;
+      for (int ss = tid; ss < rr; ss += 32) acc += C[(size_t)rr * qa + ss] * beta[ss];
+      acc = warp_sum(acc);
+      if (tid == 0) beta[rr] = (yb[sh_act[rr]] - mu[sh_act[rr]] - acc) / C[(size_t)rr * qa + rr];
+      __syncwarp();
+    }
+  }
+  if (b == 0)
+    for (int rr = tid; rr < qa; rr += nt) {
+      st.hobs_pt[st.c + rr] = pt_base + sh_act[rr] / T;
+      st.hobs_task[st.c + rr] = sh_act[rr] % T;
+    }
+}

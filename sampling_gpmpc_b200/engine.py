@@ -1,0 +1,314 @@
+"""ctypes binding of libgpmpc_b200.so (include/gpmpc_b200.h) -- the only way this package computes.
+
+There is deliberately no fallback: importing works anywhere (so CPU-only tooling can inspect the ABI),
+but constructing a ``GPEngine`` without the built library or without a CUDA device raises.
+torch is used for device memory and streams only; every number comes out of the hand-written kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpmpc_b200.so")
+
+MAX_D, MAX_T, MAX_NX = 6, 7, 8
+
+ST_TRAIN_JITTER, ST_TRAIN_NOT_PD, ST_SAMPLE_NOT_PD, ST_APPEND_NOT_PD, ST_NAN_INPUT = 1, 2, 4, 8, 16
+
+
+class GpmpcDims(C.Structure):
+    _fields_ = [("ns", C.c_int32), ("g_ny", C.c_int32), ("d", C.c_int32), ("T", C.c_int32),
+                ("n_real", C.c_int32), ("cap_points", C.c_int32)]
+
+
+class GpmpcSampleOpts(C.Structure):
+    _fields_ = [("beta", C.c_double), ("variance_is_zero", C.c_double),
+                ("unclamped_sqrt_1x1", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GpmpcEnv(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("g_ny", C.c_int32), ("d", C.c_int32),
+                ("g_idx_inputs", C.c_int32 * MAX_D), ("pad_g", C.c_int32 * MAX_NX), ("n_pad", C.c_int32),
+                ("transform", C.c_int32), ("B_d", C.c_double * (MAX_NX * MAX_NX)),
+                ("F_known", C.c_double * (MAX_NX * 2 * MAX_NX)), ("use_feedback", C.c_int32),
+                ("reserved", C.c_int32), ("K_fb", C.c_double * (MAX_NX * MAX_NX)), ("x_equi", C.c_double * MAX_NX)]
+
+
+# every symbol include/gpmpc_b200.h declares: name -> (restype, argtypes)
+_P, _D, _I = C.c_void_p, C.c_void_p, C.c_int32
+ABI = {
+    "gpmpc_create": (C.c_int, [C.POINTER(GpmpcDims), C.POINTER(_P)]),
+    "gpmpc_destroy": (C.c_int, [_P]),
+    "gpmpc_last_error": (C.c_char_p, [_P]),
+    "gpmpc_set_hypers": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]),
+    "gpmpc_set_real_data": (C.c_int, [_P, _D, _D, _P]),
+    "gpmpc_reset_hallucinated": (C.c_int, [_P]),
+    "gpmpc_reserve": (C.c_int, [_P, _I, _P]),
+    "gpmpc_set_condition_on_hallucinated": (C.c_int, [_P, _I]),
+    "gpmpc_posterior": (C.c_int, [_P, _D, _I, _D, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _P]),
+    "gpmpc_sample": (C.c_int, [_P, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _P]),
+    "gpmpc_append": (C.c_int, [_P, _D, _D, C.POINTER(C.c_uint8), _I, _P]),
+    "gpmpc_step": (C.c_int, [_P, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _D, _D, _P]),
+    "gpmpc_assemble": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _I, _D, _P]),
+    "gpmpc_rollout": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _P]),
+    "gpmpc_num_hallucinated": (C.c_int32, [_P]),
+    "gpmpc_num_factor_rows": (C.c_int32, [_P]),
+    "gpmpc_num_real_observed": (C.c_int32, [_P]),
+    "gpmpc_export_hallucinated": (C.c_int, [_P, _D, _D, _P]),
+    "gpmpc_status": (C.c_int, [_P, C.POINTER(C.c_uint32), _I, _P]),
+    "gpmpc_state_bytes": (C.c_int64, [_P]),
+    "gpmpc_last_launch_work": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "gpmpc_launch_count": (C.c_int64, [_P]),
+    "gpmpc_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the C-ABI library and type every declared symbol.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  sampling_gpmpc_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError = header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+class GPEngineError(RuntimeError):
+    pass
+
+
+class NotPSDError(GPEngineError):
+    """Counterpart of linear_operator's NotPSDError (posterior covariance not PD after the jitter ladder)."""
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float64, torch.int32, torch.uint8) and t.is_contiguous(), \
+        "gpmpc_b200 takes contiguous CUDA float64/int32 tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def make_env_struct(spec, feedback_K=None, x_equi=None) -> GpmpcEnv:
+    e = GpmpcEnv()
+    e.nx, e.nu, e.g_ny, e.d = spec.nx, spec.nu, spec.g_ny, spec.d
+    for i, v in enumerate(spec.g_idx_inputs):
+        e.g_idx_inputs[i] = v
+    for i, v in enumerate(spec.pad_g):
+        e.pad_g[i] = v
+    e.n_pad = len(spec.pad_g)
+    e.transform = spec.transform
+    for i, v in enumerate(np.asarray(spec.B_d, dtype=np.float64).reshape(-1)):
+        e.B_d[i] = v
+    for i, v in enumerate(np.asarray(spec.F_known, dtype=np.float64).reshape(-1)):
+        e.F_known[i] = v
+    if feedback_K is not None:
+        e.use_feedback = 1
+        for i, v in enumerate(np.asarray(feedback_K, dtype=np.float64).reshape(-1)):
+            e.K_fb[i] = v
+        for i, v in enumerate(np.asarray(x_equi, dtype=np.float64).reshape(-1)):
+            e.x_equi[i] = v
+    return e
+
+
+class GPEngine:
+    """One handle = one Agent's GP on one GPU: shared real-data factor + per-sample bordered factors."""
+
+    def __init__(self, ns: int, g_ny: int, d: int, T: int, n_real: int, cap_points: int = 0,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("sampling_gpmpc_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.ns, self.g_ny, self.d, self.T, self.n_real = ns, g_ny, d, T, n_real
+        self.B = ns * g_ny
+        dims = GpmpcDims(ns, g_ny, d, T, n_real, cap_points)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.gpmpc_create(C.byref(dims), C.byref(h))
+        if rc != 0:
+            raise GPEngineError(f"gpmpc_create failed ({rc}): {self.lib.gpmpc_last_error(None).decode()}")
+        self.h = h
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            self.lib.gpmpc_destroy(h)
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise GPEngineError(f"{what} failed ({rc}): {self.lib.gpmpc_last_error(self.h).decode()}")
+
+    # ---- model definition ----------------------------------------------------------------------
+    def set_hypers(self, lengthscale, outputscale, noise, jitter: float):
+        ls = np.ascontiguousarray(np.asarray(lengthscale, dtype=np.float64).reshape(self.g_ny, self.d))
+        os_ = np.ascontiguousarray(np.asarray(outputscale, dtype=np.float64).reshape(self.g_ny))
+        nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float64).reshape(self.g_ny, self.T))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self.lib.gpmpc_set_hypers(self.h, dp(ls), dp(os_), dp(nz), float(jitter)), "gpmpc_set_hypers")
+        self.outputscale = os_
+
+    def set_real_data(self, X: torch.Tensor, Y: torch.Tensor):
+        X = X.to(self.device, torch.float64).contiguous()
+        Y = Y.to(self.device, torch.float64).contiguous()
+        assert X.shape == (self.n_real, self.d) and Y.shape == (self.g_ny, self.n_real, self.T)
+        self._check(self.lib.gpmpc_set_real_data(self.h, _ptr(X), _ptr(Y), _stream()), "gpmpc_set_real_data")
+
+    def reset_hallucinated(self):
+        self._check(self.lib.gpmpc_reset_hallucinated(self.h), "gpmpc_reset_hallucinated")
+
+    def reserve(self, cap_points: int):
+        self._check(self.lib.gpmpc_reserve(self.h, int(cap_points), _stream()), "gpmpc_reserve")
+
+    def set_condition_on_hallucinated(self, on: bool):
+        self._check(self.lib.gpmpc_set_condition_on_hallucinated(self.h, int(on)), "gpmpc_set_condition")
+
+    # ---- hot path ------------------------------------------------------------------------------
+    @staticmethod
+    def opts(beta=-1.0, variance_is_zero=-1.0, unclamped_sqrt_1x1=False) -> GpmpcSampleOpts:
+        return GpmpcSampleOpts(float(beta), float(variance_is_zero), int(unclamped_sqrt_1x1), 0)
+
+    def _x(self, x: torch.Tensor, H: int) -> torch.Tensor:
+        x = x.to(self.device, torch.float64).reshape(self.B, H, self.d)
+        return x if x.is_contiguous() else x.contiguous()
+
+    def posterior(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None, opts: Optional[GpmpcSampleOpts] = None):
+        """x (ns,g_ny,H,d) -> mean, var (ns,g_ny,H,T) [, y (ns,g_ny,H,T), jitter_level (ns,g_ny)]."""
+        H = x.shape[-2]
+        xx = self._x(x, H)
+        shp = (self.ns, self.g_ny, H, self.T)
+        mean = torch.empty(shp, dtype=torch.float64, device=self.device)
+        var = torch.empty(shp, dtype=torch.float64, device=self.device)
+        y = jl = None
+        if eps is not None:
+            eps = eps.to(self.device, torch.float64).reshape(self.B, H * self.T).contiguous()
+            y = torch.empty(shp, dtype=torch.float64, device=self.device)
+            jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
+            opts = opts or self.opts()
+        rc = self.lib.gpmpc_posterior(self.h, _ptr(xx), H, _ptr(mean), _ptr(var), _ptr(eps),
+                                      C.byref(opts) if opts is not None else None, _ptr(y), _ptr(jl), _stream())
+        self._check(rc, "gpmpc_posterior")
+        return (mean, var) if eps is None else (mean, var, y, jl)
+
+    def sample(self, eps: torch.Tensor, H: int, opts: Optional[GpmpcSampleOpts] = None):
+        eps = eps.to(self.device, torch.float64).reshape(self.B, H * self.T).contiguous()
+        y = torch.empty((self.ns, self.g_ny, H, self.T), dtype=torch.float64, device=self.device)
+        jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
+        opts = opts or self.opts()
+        self._check(self.lib.gpmpc_sample(self.h, _ptr(eps), C.byref(opts), _ptr(y), _ptr(jl), _stream()), "gpmpc_sample")
+        return y, jl
+
+    def append(self, x: torch.Tensor, y: torch.Tensor, point_active: Optional[np.ndarray] = None):
+        H = x.shape[-2]
+        xx = self._x(x, H)
+        yy = y.to(self.device, torch.float64).reshape(self.B, H * self.T).contiguous()
+        act = None
+        if point_active is not None:
+            pa = np.ascontiguousarray(np.asarray(point_active, dtype=np.uint8).reshape(H))
+            act = pa.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._check(self.lib.gpmpc_append(self.h, _ptr(xx), _ptr(yy), act, H, _stream()), "gpmpc_append")
+
+    def step(self, x: torch.Tensor, eps: Optional[torch.Tensor], opts: Optional[GpmpcSampleOpts] = None,
+             want_moments: bool = True):
+        """Fused H=1 step: x (ns,g_ny,1,d) [, eps (ns,g_ny,1,T)] -> mean, var [, y, jitter_level]."""
+        xx = self._x(x, 1)
+        shp = (self.ns, self.g_ny, 1, self.T)
+        mean = torch.empty(shp, dtype=torch.float64, device=self.device) if want_moments else None
+        var = torch.empty(shp, dtype=torch.float64, device=self.device) if want_moments else None
+        y = jl = None
+        if eps is not None:
+            eps = eps.to(self.device, torch.float64).reshape(self.B, self.T).contiguous()
+            y = torch.empty(shp, dtype=torch.float64, device=self.device)
+            jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
+            opts = opts or self.opts()
+        rc = self.lib.gpmpc_step(self.h, _ptr(xx), _ptr(eps), C.byref(opts) if opts is not None else None,
+                                 _ptr(mean), _ptr(var), _ptr(y), _ptr(jl), _stream())
+        self._check(rc, "gpmpc_step")
+        return (mean, var) if eps is None else (mean, var, y, jl)
+
+    def assemble(self, env: GpmpcEnv, xu: torch.Tensor, y_gp: torch.Tensor) -> torch.Tensor:
+        """xu (ns,nx,H,nx+nu), y_gp (ns,g_ny,H,T) -> (ns,nx,H,1+nx+nu) = [f, df/dx, df/du] (dyn_fg_jacobians)."""
+        ns, nx, H, nz = xu.shape
+        xu = xu.to(self.device, torch.float64).contiguous()
+        y_gp = y_gp.to(self.device, torch.float64).contiguous()
+        out = torch.empty((ns, nx, H, 1 + nz), dtype=torch.float64, device=self.device)
+        self._check(self.lib.gpmpc_assemble(self.h, C.byref(env), _ptr(xu), _ptr(y_gp), H, _ptr(out), _stream()),
+                    "gpmpc_assemble")
+        return out
+
+    def rollout(self, env: GpmpcEnv, x0: torch.Tensor, u_ff: torch.Tensor, eps: torch.Tensor,
+                opts: GpmpcSampleOpts, traj: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x0 (ns,nx), u_ff (n_steps,nu), eps (n_steps,ns,g_ny,1,T) -> traj (ns,nx,n_steps+1)."""
+        n_steps = u_ff.shape[0]
+        x0 = x0.to(self.device, torch.float64).contiguous()
+        u_ff = u_ff.to(self.device, torch.float64).contiguous()
+        eps = eps.to(self.device, torch.float64).reshape(n_steps, self.B * self.T).contiguous()
+        if traj is None:
+            traj = torch.empty((self.ns, env.nx, n_steps + 1), dtype=torch.float64, device=self.device)
+        rc = self.lib.gpmpc_rollout(self.h, C.byref(env), _ptr(x0), _ptr(u_ff), _ptr(eps), C.byref(opts), n_steps,
+                                    _ptr(traj), _stream())
+        self._check(rc, "gpmpc_rollout")
+        return traj
+
+    # ---- introspection -------------------------------------------------------------------------
+    @property
+    def num_hallucinated(self) -> int:
+        return self.lib.gpmpc_num_hallucinated(self.h)
+
+    @property
+    def num_factor_rows(self) -> int:
+        return self.lib.gpmpc_num_factor_rows(self.h)
+
+    @property
+    def num_real_observed(self) -> int:
+        return self.lib.gpmpc_num_real_observed(self.h)
+
+    def export_hallucinated(self):
+        n = self.num_hallucinated
+        X = torch.empty((self.ns, self.g_ny, n, self.d), dtype=torch.float64, device=self.device)
+        Y = torch.empty((self.ns, self.g_ny, n, self.T), dtype=torch.float64, device=self.device)
+        if n:
+            self._check(self.lib.gpmpc_export_hallucinated(self.h, _ptr(X), _ptr(Y), _stream()), "gpmpc_export")
+        return X, Y
+
+    def status(self, clear: bool = False) -> int:
+        s = C.c_uint32(0)
+        self._check(self.lib.gpmpc_status(self.h, C.byref(s), int(clear), _stream()), "gpmpc_status")
+        return int(s.value)
+
+    def raise_on_status(self):
+        s = self.status(clear=True)
+        if s & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD):
+            raise NotPSDError(f"matrix not positive definite after the jitter ladder (status {s:#x})")
+        return s
+
+    @property
+    def state_bytes(self) -> int:
+        return self.lib.gpmpc_state_bytes(self.h)
+
+    def last_launch_work(self):
+        b, f = C.c_double(0), C.c_double(0)
+        self.lib.gpmpc_last_launch_work(self.h, C.byref(b), C.byref(f))
+        return b.value, f.value
+
+    @property
+    def launch_count(self) -> int:
+        return self.lib.gpmpc_launch_count(self.h)

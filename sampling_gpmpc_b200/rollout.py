@@ -1,0 +1,81 @@
+"""Forward rollouts of sampled GP dynamics -- the large-batch callers of the hot path.
+
+``ForwardRollout`` is the loop of benchmarking/simulate_forward_sampling_car.py:117-138 (and, with
+``condition=True``, of benchmarking/simulate_true_reachable_set.py:179-259): per horizon step build
+[x, u (+ feedback)], evaluate every sampled dynamics function at its own state, draw, (condition,) and
+take the value as the next state.  The whole horizon is queued on one CUDA stream by gpmpc_rollout;
+nothing returns to the host until the trajectories are read.
+
+Multi-GPU: the dynamics samples are independent, so each rank owns a contiguous block of
+the sample index and there is NO collective on the data path; ``all_gather_trajectories`` is the single
+exchange, for consumers that need every trajectory (convex hulls, constraint tightening).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .agent import gp_hypers_from_params
+from .engine import GPEngine, make_env_struct
+from .envs import make_env_spec
+
+F64 = torch.float64
+
+
+def shard_bounds(ns_global: int, rank: int, world_size: int):
+    """Contiguous block of sample indices owned by ``rank`` (global indices are kept, so gathered arrays
+    are laid out exactly like the single-GPU result)."""
+    per = -(-ns_global // world_size)
+    return min(rank * per, ns_global), min((rank + 1) * per, ns_global)
+
+
+class ForwardRollout:
+    def __init__(self, params: dict, condition: bool, rank: int = 0, world_size: int = 1,
+                 device: Optional[torch.device] = None, X_real=None, Y_real=None):
+        self.params = params
+        ag = params["agent"]
+        self.spec = make_env_spec(params)
+        self.ns_global = ag["num_dyn_samples"]
+        self.rank, self.world_size = rank, world_size
+        self.s_lo, self.s_hi = shard_bounds(self.ns_global, rank, world_size)
+        self.ns = self.s_hi - self.s_lo
+        self.steps = params["common"]["num_MPC_itrs"]
+        self.T = 1 if params["env"]["use_model_without_derivatives"] else 1 + self.spec.d
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if X_real is None:
+            X_real, Y_real = self.spec.initial_training_data(params)
+        Y_real = Y_real[:, :, : self.T] if self.T == 1 else Y_real
+        self.engine = GPEngine(self.ns, self.spec.g_ny, self.spec.d, self.T, X_real.shape[0],
+                               cap_points=self.steps, device=self.device)
+        ls, os_, noise = gp_hypers_from_params(params, self.spec.g_ny, self.spec.d, use_grad=self.T > 1)
+        self.engine.set_hypers(ls, os_, noise, ag["Dyn_gp_jitter"])
+        self.engine.set_real_data(X_real, Y_real.contiguous())
+        self.engine.set_condition_on_hallucinated(condition)
+        self.condition = condition
+        fb = ag.get("feedback", {}).get("use", False)
+        K = np.asarray(params["optimizer"]["terminal_tightening"]["K"]) if fb else None
+        self.env = make_env_struct(self.spec, K, params["env"]["goal_state"] if fb else None)
+        self.opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
+        self.x0 = torch.tensor(params["env"]["start"], dtype=F64, device=self.device).expand(self.ns, -1).contiguous()
+
+    def run(self, u_ff: torch.Tensor, eps: torch.Tensor, traj: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """u_ff (steps, nu); eps (steps, ns_global or ns, g_ny, 1, T) standard-normal draws (the reference's
+        epistimic_random_vector[:, 1]).  Returns this rank's trajectories (ns, nx, steps+1) on the device."""
+        if eps.shape[1] == self.ns_global and self.world_size > 1:
+            eps = eps[:, self.s_lo:self.s_hi]
+        self.engine.reset_hallucinated()
+        return self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
+
+    def all_gather_trajectories(self, traj: torch.Tensor) -> torch.Tensor:
+        """(ns_local, nx, steps+1) per rank -> (ns_global, nx, steps+1) on every rank: one NCCL all-gather."""
+        if self.world_size == 1:
+            return traj
+        import torch.distributed as dist
+        per = -(-self.ns_global // self.world_size)
+        pad = torch.zeros((per, *traj.shape[1:]), dtype=traj.dtype, device=traj.device)
+        pad[: traj.shape[0]] = traj
+        out = torch.empty((self.world_size * per, *traj.shape[1:]), dtype=traj.dtype, device=traj.device)
+        dist.all_gather_into_tensor(out, pad)
+        return out[: self.ns_global]
