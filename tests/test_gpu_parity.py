@@ -33,7 +33,16 @@ def _make_agent(params, z):
                  epistimic_random_vector=torch.tensor(z["eps"]))
 
 
-@pytest.mark.parametrize("case", CASES)
+# Fixtures whose joint posterior covariance is numerically singular AND is factorised without jitter
+# (lambda_min(Sigma*) ~ 1e-13 against rounding noise ~1e-15 in Sigma* itself): there the reference's own draw
+# moves by 10^2..10^4 x the 1e-9 tolerance under a rounding-level perturbation of Sigma*, and jitter decisions
+# flip (measured in DESIGN.md "Conditioning").  Free-running replay is only meaningful for the others; the
+# ill-conditioned ones are covered by test_one_step_parity_under_identical_history below.
+ILL_CONDITIONED = ["pendulum2D_sqp", "car_sqp"]
+WELL_CONDITIONED = [c for c in CASES if c not in ILL_CONDITIONED]
+
+
+@pytest.mark.parametrize("case", WELL_CONDITIONED)
 def test_agent_replay_matches_golden(case):
     """Same iterates as the fixture, through the product Agent (block kernels + assembly kernel)."""
     z, params = load_case(case)
@@ -42,7 +51,15 @@ def test_agent_replay_matches_golden(case):
     s_val = float(np.sqrt(os_.max()))
     worst = {"mean": 0.0, "variance": 0.0, "y_sample": 0.0, "gp_val": 0.0, "y_grad": 0.0, "u_grad": 0.0}
 
+    per_call = []
+
     def check(k, ag, res):
+        gp_val, y_grad, u_grad = res
+        before = dict(worst)
+        _check(k, ag, res)
+        per_call.append({q: round(v, 6) for q, v in worst.items() if v > before[q]})
+
+    def _check(k, ag, res):
         gp_val, y_grad, u_grad = res
         xscale = max(1.0, float(np.abs(z[f"x_h_{k}"]).max()))
         mean = ag.model_i_call.mean.cpu().numpy()
@@ -63,7 +80,7 @@ def test_agent_replay_matches_golden(case):
 
     replay(agent, z, params, on_call=check)
     status = agent.engine.status()
-    REPORT[f"golden/{case}"] = dict(worst, status=status)
+    REPORT[f"golden/{case}"] = dict(worst, status=status, per_call=per_call)
     _dump_report()
     assert status & ~0x301 == 0, f"engine status {status:#x}"
     for k, v in worst.items():
@@ -147,3 +164,81 @@ def test_rollout_properties_at_scale():
     assert torch.equal(t1[perm], t2), "sample s's trajectory must depend only on its own base samples"
     assert torch.isfinite(t1).all()
     assert fr.engine.status() == 0
+
+
+def _root_sensitivity(S, level, jitter, eps, os_j, draws=6, rel=1e-15):
+    """How far the ORACLE's own draw moves when Sigma* is perturbed at its rounding level (rel * outputscale,
+    the size of the cancellation error in K** - W^T W), and whether its jitter decision survives that.
+    S (ns,q,q), level (ns,), eps (ns,q).  Returns (dy_max per element, marginal mask)."""
+    add = torch.where(level > 0, jitter * 10.0 ** (level.double() - 1), torch.zeros_like(level, dtype=torch.float64))
+    Sj = S + torch.diag_embed(add[:, None].expand(-1, S.shape[-1]))
+    L0, _ = torch.linalg.cholesky_ex(Sj)
+    _, info_nojit = torch.linalg.cholesky_ex(S)
+    dy = torch.zeros(S.shape[0], dtype=torch.float64)
+    marginal = torch.zeros(S.shape[0], dtype=torch.bool)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(draws):
+        N = torch.randn(S.shape, generator=g, dtype=torch.float64)
+        N = (N + N.transpose(-1, -2)) / 2
+        L1, info1 = torch.linalg.cholesky_ex(Sj + rel * os_j * N)
+        _, info2 = torch.linalg.cholesky_ex(S + rel * os_j * N)
+        marginal |= (info1 > 0) | ((info2 > 0) != (info_nojit > 0))
+        d = ((L1 - L0) @ eps.unsqueeze(-1)).abs().amax(dim=(-1, -2))
+        dy = torch.maximum(dy, torch.where(info1 > 0, torch.zeros_like(d), d))
+    return dy, marginal
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c not in ("car_residual_truedyn", "car_residual_fs")])
+def test_one_step_parity_under_identical_history(case):
+    """Every call compared GIVEN THE SAME HISTORY: both sides condition on the oracle's labels (teacher
+    forcing), so means / variances / Jacobian tasks must agree to 1e-9 at every call no matter how
+    ill-conditioned the draw is.  The draw itself is held to max(1e-9 scaled, 50 x the oracle's own sensitivity
+    to a 1e-15*outputscale perturbation of Sigma*); jitter levels must agree wherever the oracle's own decision
+    is stable under that perturbation."""
+    from oracle.agent_ref import RefAgent
+    from sampling_gpmpc_b200.envs import make_env_spec
+    z, params = load_case(case)
+    spec = make_env_spec(params)
+    gpu = _make_agent(params, z)
+    ref = RefAgent(params, spec, torch.tensor(z["X_real"]), torch.tensor(z["Y_real"]),
+                   epistimic_random_vector=torch.tensor(z["eps"]))
+    os_ = outputscales(params)
+    n_sqp = params["optimizer"]["SEMPC"]["max_sqp_iter"]
+    jitter = params["agent"]["Dyn_gp_jitter"]
+    worst = {"mean": 0.0, "variance": 0.0, "y_sample_over_allowed": 0.0}
+    flips = marginal_flips = total = 0
+    for k in range(n_calls(z)):
+        mpc, sqp = divmod(k, n_sqp)
+        for a in (gpu, ref):
+            a.mpc_iteration(mpc)
+            a.train_hallucinated_dynGP(sqp)
+        bx = ref.get_batch_x_hat(z[f"x_h_{k}"], z[f"u_h_{k}"])
+        g_ref = ref.get_g_xu_hat(bx).contiguous()
+        eps = ref.epistimic_random_vector[mpc][sqp]
+        y_ref = ref.sample_gp(g_ref, eps)
+        y_gpu = gpu.sample_gp(g_ref.cuda(), eps.cuda()).cpu()
+        mean, var = gpu.model_i_call.mean.cpu().numpy(), gpu.model_i_call.variance.cpu().numpy()
+        lvl_g, lvl_r = gpu.model_i_call.jitter_level.cpu(), ref.model_i_call.jitter_level
+        for j in range(mean.shape[1]):
+            worst["mean"] = max(worst["mean"], scaled_close(mean[:, j], ref.model_i_call.mean[:, j].numpy(), np.sqrt(os_[j]), RTOL))
+            worst["variance"] = max(worst["variance"], scaled_close(var[:, j], ref.model_i_call.variance[:, j].numpy(), os_[j], RTOL))
+            S = ref.model_i_call.covariance_matrix[:, j]
+            dy, marginal = _root_sensitivity(S, lvl_r[:, j], jitter, eps[:, j].reshape(S.shape[0], -1), os_[j])
+            same = lvl_g[:, j] == lvl_r[:, j]
+            total += same.numel()
+            flips += int((~same).sum())
+            marginal_flips += int((~same & marginal).sum())
+            assert bool((same | marginal).all()), f"{case} call {k}: jitter decision differs on a well-conditioned element"
+            allowed = np.maximum(RTOL * np.maximum(np.abs(y_ref[:, j].numpy()), np.sqrt(os_[j])), 50.0 * dy.numpy()[:, None, None])
+            err = np.abs(y_gpu[:, j].numpy() - y_ref[:, j].numpy()) / allowed
+            err = err[same.numpy()]
+            if err.size:
+                worst["y_sample_over_allowed"] = max(worst["y_sample_over_allowed"], float(err.max()))
+        # teacher forcing: both condition on the oracle's labels
+        ref.update_hallucinated_Dyn_dataset(g_ref, y_ref)
+        gpu.update_hallucinated_Dyn_dataset(g_ref.cuda(), y_ref.cuda())
+    REPORT[f"one_step/{case}"] = dict(worst, jitter_flips=flips, marginal_flips=marginal_flips, elements=total,
+                                      status=gpu.engine.status())
+    _dump_report()
+    for q, v in worst.items():
+        assert v <= 1.0, f"{case}: {q} off by {v:.3g} x allowed"
