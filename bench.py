@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- conditioned sample-steps/s of the GP-sampling hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[3], the metric's own configuration): the car forward rollout of
+benchmarking/simulate_forward_sampling_car.py with true iterative conditioning -- every sampled point
+(value + 2 derivative tasks) becomes training data of its own dynamics sample -- on the shapes of
+params_car_residual_fs.yaml: g_ny=3 outputs, d=2, T=3, m=45 shared real observations, 50 horizon steps,
+125 000 dynamics samples per GPU (10^6 over 8 GPUs, weak scaling: samples are independent, no collective on
+the data path).  One bench "step" = one whole 50-step rollout of this rank's samples.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference-equivalent CPU torch path (oracle, full re-fit)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "conditioned_sample_steps_per_sec"
+UNIT = "sample-steps/s"
+HORIZON = 50
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ns-per-gpu", type=int, default=125000)
+    ap.add_argument("--cpu-samples", type=int, default=48, help="bounded sample for the CPU legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the as-shipped / SQP side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(ns_per_gpu, n_gpus):
+    return {
+        "workload": "car forward rollout with iterative conditioning (params_car_residual_fs shapes, "
+                    "use_model_without_derivatives=False): g_ny=3, d=2, T=3, m=45 shared real observations, "
+                    f"{HORIZON} horizon steps, factor grows to c=150 rows per (sample, output)",
+        "ns_per_gpu": ns_per_gpu, "ns_total": ns_per_gpu * n_gpus, "horizon": HORIZON,
+        "parallelism": f"samples sharded contiguously over {n_gpus} GPU(s), no data-path collective",
+        "l2": "per-GPU factor state (~88 GB at 125k samples) >> 126 MB L2: inputs larger than L2, no flush needed",
+    }
+
+
+def synthetic_inputs(ns, horizon, T, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    eps = torch.empty(horizon, ns, 3, 1, T, dtype=torch.float64).pin_memory()
+    torch.randn(eps.shape, generator=g, dtype=torch.float64, out=eps)
+    eps.clamp_(-3.0, 3.0)
+    t = torch.linspace(0, 1, horizon, dtype=torch.float64)
+    u = torch.stack([0.05 * torch.sin(6.0 * t), 0.3 * torch.cos(4.0 * t)], 1).contiguous().pin_memory()
+    return u, eps
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_rollout(ns, horizon, seed, threads):
+    """The reference-equivalent CPU torch path (oracle: full GP re-fit per step) on a bounded sample."""
+    import torch
+    from oracle.rollout_ref import reference_rollout
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.envs import make_env_spec
+    torch.set_num_threads(threads)
+    params = configs.car_residual_fs(ns, horizon, with_derivatives=True)
+    u, eps = synthetic_inputs(ns, horizon, 3, seed)
+    t0 = time.perf_counter()
+    reference_rollout(params, make_env_spec(params), u, eps, condition=True)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: times the reference's CPU implementation of the path (gpytorch is not installable,
+    so this is the oracle's op-sequence-faithful restatement incl. the full re-fit per conditioning step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ns = args.cpu_samples
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rollout(min(ns, 8), 10, 1, threads)
+    times = [cpu_reference_rollout(ns, HORIZON, 100 + i, threads) for i in range(args.steps)]
+    dt = sum(times) / len(times)
+    value = ns * HORIZON / dt
+    sample = f"{ns} samples x {HORIZON} steps per bench step (same shapes, same per-sample work as the GPU arm)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.ns_per_gpu, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def extras(torch, device):
+    """Side measurements reported next to the headline (not the bench value): the script as shipped
+    (value-only model, no conditioning) and ms per SQP GP linearisation at the pendulum1D shape."""
+    import numpy as np
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.agent import Agent
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    out = {}
+    ns = 1_000_000
+    fr = ForwardRollout(configs.car_residual_fs(ns, HORIZON, with_derivatives=False), condition=False, device=device)
+    u, eps = synthetic_inputs(ns, HORIZON, 1, 3)
+    u, eps = u.to(device), eps.to(device)
+    for _ in range(2):
+        fr.run(u, eps)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        fr.run(u, eps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["as_shipped_value_only"] = {"sample_steps_per_sec": ns * HORIZON / (ms * 1e-3), "ms_per_rollout": ms, "ns": ns,
+                                    "note": "simulate_forward_sampling_car.py as shipped: T=1, model on real data only"}
+    del fr, eps
+    torch.cuda.empty_cache()
+
+    params = configs.pendulum1D_sqp()
+    agent = Agent(params, generate_base_samples=False, device=device)
+    g = torch.Generator().manual_seed(0)
+    agent.epistimic_random_vector = torch.randn(8, 1, 70, 1, 17, 3, generator=g, dtype=torch.float64).clamp(-2.5, 2.5).to(device)
+    H = 17
+    rng = np.random.default_rng(0)
+    x_h = np.tile(np.stack([np.linspace(2.2, 3.1, H), np.linspace(2.0, 0.1, H)], 1), (1, 70)) + 0.01 * rng.standard_normal((H, 140))
+    u_h = np.linspace(-3, 3, H).reshape(H, 1)
+    times = []
+    for i in range(8):
+        agent.mpc_iteration(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        agent.train_hallucinated_dynGP(0)
+        agent.dyn_fg_jacobians(agent.get_batch_x_hat(x_h, u_h), 0)
+        times.append((time.perf_counter() - t0) * 1e3)
+        x_h = x_h + 0.005 * rng.standard_normal(x_h.shape)
+    out["sqp_linearisation_ms"] = {"host_observed_ms_incl_d2h": float(np.median(times[2:])),
+                                   "shape": "pendulum1D: ns=70, H=17, T=3 (q=51), n_obs=87",
+                                   "calls": "train_hallucinated_dynGP + dyn_fg_jacobians (solver.py:84-94)"}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ns = args.ns_per_gpu
+    params = configs.car_residual_fs(ns * world, HORIZON, with_derivatives=True)
+    fr = ForwardRollout(params, condition=True, rank=rank, world_size=world, device=device)
+    eng = fr.engine
+    u_host, eps_host = synthetic_inputs(ns, HORIZON, 3, 1000 + rank)
+    u_dev, eps_dev = u_host.to(device), eps_host.to(device)
+    traj = torch.empty((ns, 4, HORIZON + 1), dtype=torch.float64, device=device)
+    traj_host = torch.empty(traj.shape, dtype=torch.float64).pin_memory()
+
+    # ---- device-resident timing ("value") ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        fr.run(u_dev, eps_dev, traj)
+    barrier()
+    eng.set_timing(True)
+    launches0 = eng.launch_count
+    kern_ms = kern_launches = 0
+    work_bytes = work_flops = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            fr.run(u_dev, eps_dev, traj)
+            # summed after the loop would need per-step event sets; reading them waits only for this rollout
+            ms, nl = eng.rollout_kernel_ms()
+            kern_ms += ms
+            kern_launches += nl
+            b, f = eng.last_launch_work()
+            work_bytes += b
+            work_flops += f
+        e1.record()
+        barrier()
+    eng.set_timing(False)
+    gpu_launches = eng.launch_count - launches0
+    t_dev = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_total = float(t_dev.item())
+    ms_per_step = ms_total / args.steps
+    value = world * ns * HORIZON / (ms_per_step * 1e-3)
+    status = eng.status()
+
+    # ---- end-to-end through the public call with HOST buffers ("e2e") ----------------------------------
+    def e2e_step():
+        eps_d = eps_host.to(device, non_blocking=True)     # this step's base samples, pinned host -> device
+        u_d = u_host.to(device, non_blocking=True)
+        fr.run(u_d, eps_d, traj)
+        traj_host.copy_(traj, non_blocking=True)            # the step's result, device -> pinned host
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * ns * HORIZON / (float(t_e2e.item()) / args.steps * 1e-3)
+    h2d = eps_host.numel() * 8 + u_host.numel() * 8
+    d2h = traj_host.numel() * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = work_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_step<2,3> (fused rollout step)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+                "peak_source": peak_src, "kernel_ms_per_launch": kern_ms / max(kern_launches, 1),
+                "launches_timed": kern_launches,
+                "algorithmic_bytes_per_launch": work_bytes / max(kern_launches, 1),
+                "algorithmic_gflop_per_launch": work_flops / max(kern_launches, 1) / 1e9,
+                "kernel_share_of_step": kern_ms / ms_total}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ns, world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(gpu_launches), "roofline": roofline, "engine_status": status,
+            "state_bytes_per_gpu": int(eng.state_bytes)}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_reference_rollout(4, 5, 1, threads)  # warm the CPU path
+        dt = cpu_reference_rollout(args.cpu_samples, HORIZON, 7, threads)
+        line["cpu_baseline"] = {"value": args.cpu_samples * HORIZON / dt, "unit": UNIT, "cores": threads,
+                                "kind": "port",
+                                "sample": f"{args.cpu_samples} samples x {HORIZON} steps ({dt:.1f} s), oracle = reference-"
+                                          "equivalent CPU torch path with full re-fit per step (gpytorch not installable)"}
+    if world == 1 and not args.no_extras:
+        del fr, eng, eps_dev, traj
+        torch.cuda.empty_cache()
+        try:
+            line["extra"] = extras(torch, device)
+        except Exception as exc:  # side measurements must never take the headline down
+            line["extra"] = {"error": repr(exc)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -177,6 +177,11 @@ int64_t gpmpc_state_bytes(const gpmpc_handle* h);
 int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops);
 /* Number of kernels this library launched since create (bench.py's gpu_launches). */
 int64_t gpmpc_launch_count(const gpmpc_handle* h);
+/* Per-launch timing of the fused step kernel inside gpmpc_rollout: when on, a CUDA event pair brackets every
+ * step-kernel launch on the rollout's stream; gpmpc_rollout_kernel_ms waits for the last one and returns the
+ * summed device time and the number of launches of the last rollout (bench.py's roofline.achieved). */
+int gpmpc_set_timing(gpmpc_handle* h, int32_t on);
+int gpmpc_rollout_kernel_ms(gpmpc_handle* h, double* total_ms, int32_t* launches);
 const char* gpmpc_version(void);
 
 #ifdef __cplusplus

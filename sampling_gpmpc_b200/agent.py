@@ -124,6 +124,7 @@ class Agent:
 
         self.engine = GPEngine(self.ns, self.g_ny, self.in_dim_x, self.in_dim_y, n_real, cap_points=0,
                                device=self.torch_device)
+        self.engine.set_condition_on_hallucinated(self.in_dim_y > 1)  # value-only model never conditions (agent.py:221-226)
         ls, os_, noise = gp_hypers_from_params(params, self.g_ny, self.in_dim_x, use_grad=self.in_dim_y > 1)
         self.engine.set_hypers(ls, os_, noise, ag["Dyn_gp_jitter"])
         self.engine.set_real_data(self.Dyn_gp_X_train, self.Dyn_gp_Y_train.contiguous())

@@ -38,6 +38,10 @@ struct gpmpc_handle {
   unsigned char* d_active = nullptr;
   int d_active_cap = 0;
   int max_dyn_smem = 0;
+  // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  int ev_used = 0;
 };
 
 #define CUDA_TRY(h, expr)                                                                      \
@@ -74,7 +78,8 @@ static void free_factor_state(gpmpc_handle* h) {
 static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stream) {
   DevState old = h->st;
   DevState& st = h->st;
-  const int c_cap = cap_points * st.T;
+  // the factor rows exist only while conditioning is on; a record-only handle keeps just the data set
+  const int c_cap = h->condition ? cap_points * st.T : 0;
   const int ldL = ((st.m + c_cap + 3) / 4) * 4;
   double *Xh, *Yh, *Lh, *beta_h;
   int *hp, *ht;
@@ -187,6 +192,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree(st.Loo); cudaFree(st.LooT); cudaFree(st.beta_o); cudaFree(st.status);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return GPMPC_OK;
 }
@@ -292,7 +298,13 @@ int gpmpc_reserve(gpmpc_handle* h, int32_t cap_points, void* stream) {
 
 int gpmpc_set_condition_on_hallucinated(gpmpc_handle* h, int32_t on) {
   if (!h) return GPMPC_ERR_ARG;
+  const bool was = h->condition;
   h->condition = on != 0;
+  if (h->condition && !was && h->have_real) {
+    if (h->st.c != 0 || h->st.np != 0)
+      return fail(h, GPMPC_ERR_STATE, "switch conditioning on only with an empty hallucinated set");
+    if (h->st.c_cap < h->st.cap_points * h->st.T) return alloc_factor_state(h, h->st.cap_points, 0);
+  }
   return GPMPC_OK;
 }
 
@@ -502,9 +514,22 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
   k_rollout_state<<<blocks, threads, 0, stream>>>(*env, ns, hst.T, 0, n_steps, 0, x0, u_ff, h->r_y, h->r_xu,
                                                    h->r_xstar, traj);
   h->launches++;
+  if (h->timing) {
+    while ((int)h->ev.size() < 2 * n_steps) {
+      cudaEvent_t e;
+      CUDA_TRY(h, cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+    h->ev_used = 0;
+  }
   for (int t = 0; t < n_steps; ++t) {
+    if (h->timing) CUDA_TRY(h, cudaEventRecord(h->ev[2 * t], stream));
     rc = gpmpc_step(h, h->r_xstar, eps + (size_t)t * eps_stride, opts, nullptr, nullptr, h->r_y, nullptr, stream);
     if (rc) return rc;
+    if (h->timing) {
+      CUDA_TRY(h, cudaEventRecord(h->ev[2 * t + 1], stream));
+      h->ev_used = 2 * (t + 1);
+    }
     bytes += h->last_bytes;
     flops += h->last_flops;
     k_rollout_state<<<blocks, threads, 0, stream>>>(*env, ns, hst.T, t + 1, n_steps, 1, x0, u_ff, h->r_y,
@@ -557,5 +582,25 @@ int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops) 
 }
 
 int64_t gpmpc_launch_count(const gpmpc_handle* h) { return h ? h->launches : -1; }
+
+int gpmpc_set_timing(gpmpc_handle* h, int32_t on) {
+  if (!h) return GPMPC_ERR_ARG;
+  h->timing = on != 0;
+  return GPMPC_OK;
+}
+
+int gpmpc_rollout_kernel_ms(gpmpc_handle* h, double* total_ms, int32_t* launches) {
+  if (!h || !total_ms || !launches) return fail(h, GPMPC_ERR_ARG, "null argument");
+  *total_ms = 0.0;
+  *launches = h->ev_used / 2;
+  if (h->ev_used == 0) return GPMPC_OK;
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[h->ev_used - 1]));
+  for (int i = 0; i < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    *total_ms += ms;
+  }
+  return GPMPC_OK;
+}
 
 }  // extern "C"

@@ -64,6 +64,8 @@ ABI = {
     "gpmpc_state_bytes": (C.c_int64, [_P]),
     "gpmpc_last_launch_work": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gpmpc_launch_count": (C.c_int64, [_P]),
+    "gpmpc_set_timing": (C.c_int, [_P, _I]),
+    "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
 }
 
@@ -308,6 +310,14 @@ class GPEngine:
         b, f = C.c_double(0), C.c_double(0)
         self.lib.gpmpc_last_launch_work(self.h, C.byref(b), C.byref(f))
         return b.value, f.value
+
+    def set_timing(self, on: bool):
+        self._check(self.lib.gpmpc_set_timing(self.h, int(on)), "gpmpc_set_timing")
+
+    def rollout_kernel_ms(self):
+        ms, n = C.c_double(0), C.c_int32(0)
+        self._check(self.lib.gpmpc_rollout_kernel_ms(self.h, C.byref(ms), C.byref(n)), "gpmpc_rollout_kernel_ms")
+        return ms.value, n.value
 
     @property
     def launch_count(self) -> int:

@@ -49,10 +49,10 @@ class ForwardRollout:
         Y_real = Y_real[:, :, : self.T] if self.T == 1 else Y_real
         self.engine = GPEngine(self.ns, self.spec.g_ny, self.spec.d, self.T, X_real.shape[0],
                                cap_points=self.steps, device=self.device)
+        self.engine.set_condition_on_hallucinated(condition)  # before any allocation: no factor rows if off
         ls, os_, noise = gp_hypers_from_params(params, self.spec.g_ny, self.spec.d, use_grad=self.T > 1)
         self.engine.set_hypers(ls, os_, noise, ag["Dyn_gp_jitter"])
         self.engine.set_real_data(X_real, Y_real.contiguous())
-        self.engine.set_condition_on_hallucinated(condition)
         self.condition = condition
         fb = ag.get("feedback", {}).get("use", False)
         K = np.asarray(params["optimizer"]["terminal_tightening"]["K"]) if fb else None
