@@ -403,11 +403,13 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
                        cudaStream_t stream) {
   const int m = st.m, n = st.m + st.c;
   const int n_pad = ((n + 1) & ~1) + 2;
-  const size_t tri = (size_t)m * (m + 1) / 2;
-  size_t shared_tab = ((size_t)m * D + m) * 8 + (size_t)((m + 1) & ~1) * 4;
-  size_t per_warp = (size_t)T * n_pad * 8;
+  constexpr int NV = StepRB<T>::value * T;
+  const size_t tri_pad = (((size_t)m * (m + 1) / 2) + 1) & ~(size_t)1;
+  const size_t m_pad = (m + 1) & ~1;
+  const size_t shared_tab = (m_pad * D + m_pad) * 8 + 2 * m_pad * 4;
+  const size_t per_warp = ((size_t)T * n_pad + NV * STEP_RED_LD + 32 + ((NV * STEP_RED_LD) & 1)) * 8;
   int loo_in_smem = 1;
-  size_t smem = tri * 8 + shared_tab + STEP_WARPS * per_warp;
+  size_t smem = tri_pad * 8 + shared_tab + STEP_WARPS * per_warp;
   if (smem > 100 * 1024) {  // keep >= 2 CTAs per SM; the shared factor then comes from L2
     loo_in_smem = 0;
     smem = shared_tab + STEP_WARPS * per_warp;

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
   double* LT = st.LooT + (size_t)j * ((size_t)m * (m + 1) / 2);
   for (int idx = tid; idx < m * m; idx += nt) {
     int i = idx / m, cc = idx % m;
-    if (cc <= i) LT[packed_col(cc, m) + (i - cc)] = A[idx];
+    if (cc <= i) LT[packed_col(cc, m) + (i - cc)] = (cc == i) ? 1.0 / A[idx] : A[idx];  // diagonal stored as 1/L_jj
   }
   // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
   if (tid < 32) {
@@ -132,7 +132,8 @@ __device__ void block_posterior(const DevState& st, int b, const double* __restr
         const double* Lrow = factor_row(st, b, j, i0 + a);
         double v = W[(size_t)(i0 + a) * q + r];
         for (int bb = 0; bb < a; ++bb) v -= Lrow[i0 + bb] * W[(size_t)(i0 + bb) * q + r];
-        W[(size_t)(i0 + a) * q + r] = v / Lrow[i0 + a];
+        // own rows keep 1/L_kk in the diagonal slot, the shared block keeps L_kk
+        W[(size_t)(i0 + a) * q + r] = (i0 + a >= st.m) ? v * Lrow[i0 + a] : v / Lrow[i0 + a];
       }
     }
     __syncthreads();
@@ -314,7 +315,7 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   }
   for (int idx = tid; idx < qa * qa; idx += nt) {
     int rr = idx / qa, ss = idx % qa;
-    if (ss <= rr) Lnew[(size_t)rr * st.ldL + n + ss] = C[idx];
+    if (ss <= rr) Lnew[(size_t)rr * st.ldL + n + ss] = (ss == rr) ? 1.0 / C[idx] : C[idx];
   }
   // beta_new = L_nn^{-1} (y - mu)
   if (tid < 32) {

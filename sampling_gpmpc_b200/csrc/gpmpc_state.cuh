@@ -26,14 +26,14 @@ struct DevState {
   const double* os;     // [g_ny]
   const double* noise;  // [g_ny][T]
   double* Loo;          // [g_ny][m][m] row-major lower Cholesky factor of K_oo + Sigma
-  double* LooT;         // [g_ny][m(m+1)/2] same factor, packed column-major (column j contiguous)
+  double* LooT;         // [g_ny][m(m+1)/2] same factor, packed column-major (column j contiguous), diagonal = 1/L_jj
   double* beta_o;       // [g_ny][m]  L_oo^{-1} y_o
   // per batch element --------------------------------------------------------------------
   double* Xh;           // [B][cap_points][d]
   double* Yh;           // [B][cap_points][T]  labels as appended (NaN kept, for export)
   int* hobs_pt;         // [c_cap] hallucinated point of factor row k   (uniform over b)
   int* hobs_task;       // [c_cap] its task
-  double* Lh;           // [B][c_cap][ldL]  bordered rows: row k has m+k+1 entries
+  double* Lh;           // [B][c_cap][ldL]  bordered rows: row k has m+k+1 entries, the last one is 1/L_kk
   double* beta_h;       // [B][c_cap]
   unsigned* status;     // device status word (GPMPC_ST_*)
   // workspace of the block kernels ---------------------------------------------------------

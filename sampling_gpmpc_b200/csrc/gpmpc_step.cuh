@@ -5,8 +5,9 @@
 //   A  kernel vector k(x*, X) against real + hallucinated scalars (one exp per lane-owned scalar)
 //   B  forward substitution against the shared factor (column sweep in shared memory)
 //   C  forward substitution against the element's own bordered rows, streamed ONCE from HBM with
-//      coalesced 16-byte loads, 4 rows in flight per warp, warp-shuffle reduction of the 4*T dot products
-//   D  Sigma* = K** - w^T w and mean = w^T beta accumulated on the fly (registers, redundantly per lane)
+//      coalesced 16-byte loads, RB rows in flight per warp; the RB*T partial dot products are transposed
+//      through shared memory (lane v finishes dot product v), lanes r < T resolve the RB x RB corner
+//   D  Sigma* = K** - w^T w and mean = w^T beta: one pass over w + warp-shuffle all-reduce
 //   E  T x T Cholesky with GPyTorch's jitter ladder, y = mean + L eps, zero-variance / truncation
 //   F  rank-T append: new rows [w^T | chol(Sigma* + noise)] written back coalesced, beta_h, data set
 //
@@ -16,7 +17,10 @@
 #include "gpmpc_state.cuh"
 
 #define STEP_WARPS 4
-#define STEP_RB 4  // own rows in flight per warp
+
+// own rows streamed per block (all in flight at once); RB*T partial dot products must fit one per lane
+template <int T> struct StepRB { static constexpr int value = T == 1 ? 8 : T == 2 ? 8 : T == 3 ? 6 : T == 4 ? 4 : T == 5 ? 5 : T == 6 ? 5 : 4; };
+#define STEP_RED_LD 33  // row stride of the per-warp reduction scratch (conflict-free column reads)
 
 template <int T>
 struct TriT {  // lower-triangular T x T in registers
@@ -52,19 +56,23 @@ __global__ void __launch_bounds__(STEP_WARPS * 32)
 k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
        int* __restrict__ jitter_level, int grow_factor, int n_pad, int loo_in_smem) {
-  extern __shared__ double smem[];
+  constexpr int RB = StepRB<T>::value;
+  constexpr int NV = RB * T;
+  extern __shared__ __align__(16) double smem[];
   const int j = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s_idx = blockIdx.x * STEP_WARPS + warp;
   const int m = st.m, c = st.c, n = m + c;
   const size_t tri = (size_t)m * (m + 1) / 2;
+  const size_t tri_pad = (tri + 1) & ~(size_t)1;
+  const int m_pad = (m + 1) & ~1;
 
-  // ---- CTA-shared tables ---------------------------------------------------------------------
-  double* sLT = smem;                               // [tri] (only if loo_in_smem)
-  double* sXo = sLT + (loo_in_smem ? tri : 0);      // [m][D] input of observed real scalar i
-  double* sBo = sXo + (size_t)m * D;                // [m]
-  int* sTo = (int*)(sBo + m);                       // [m] task of observed real scalar i
-  double* wbase = (double*)(sTo + ((m + 1) & ~1));  // per-warp w: [T][n_pad]
+  // ---- CTA-shared tables (every table starts 16-byte aligned) ------------------------------------
+  double* sLT = smem;                                  // [tri_pad] (only if loo_in_smem); diagonal = 1/L_jj
+  double* sXo = sLT + (loo_in_smem ? tri_pad : 0);     // [m_pad*D] input of observed real scalar i
+  double* sBo = sXo + (size_t)m_pad * D;               // [m_pad]
+  int* sTo = (int*)(sBo + m_pad);                      // [2*m_pad] ints: task of observed real scalar i
+  double* wbase = (double*)(sTo + 2 * m_pad);          // per-warp: w [T][n_pad], red [NV][33], tot [32]
   const double* gLT = st.LooT + (size_t)j * tri;
   if (loo_in_smem)
     for (size_t i = threadIdx.x; i < tri; i += blockDim.x) sLT[i] = gLT[i];
@@ -79,7 +87,10 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   if (s_idx >= st.ns) return;  // no block-level sync below this line
   const double* LT = loo_in_smem ? sLT : gLT;
   const int b = s_idx * st.g_ny + j;
-  double* w = wbase + (size_t)warp * T * n_pad;
+  const int per_warp = T * n_pad + NV * STEP_RED_LD + 32 + ((NV * STEP_RED_LD) & 1);
+  double* w = wbase + (size_t)warp * per_warp;
+  double* red = w + T * n_pad;
+  double* tot = red + NV * STEP_RED_LD + ((NV * STEP_RED_LD) & 1);
 
   double ls[D], xs[D];
 #pragma unroll
@@ -125,113 +136,132 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
       }
     }
   }
+  __syncwarp();
 
-  TriT<T> Sacc;
-  double macc[T];
-#pragma unroll
-  for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = 0.0;
-#pragma unroll
-  for (int r = 0; r < T; ++r) macc[r] = 0.0;
-
-  // ---- B: shared block, column sweep -------------------------------------------------------------
-  for (int jj = 0; jj < m; ++jj) {
+  // ---- B: shared block, column sweep; entry jj is finalised (scaled by 1/L_jj) by the lane that
+  //         applies column jj-1 to it, so each column costs one warp sync --------------------------------
+  if (lane < T) w[lane * n_pad] *= LT[0];
+  for (int jj = 0; jj + 1 < m; ++jj) {
     __syncwarp();
     const double* col = LT + packed_col(jj, m);
-    const double dj = col[0];
     double wj[T];
 #pragma unroll
-    for (int r = 0; r < T; ++r) wj[r] = w[r * n_pad + jj] / dj;
-    const double bo = sBo[jj];
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      macc[r] += wj[r] * bo;
-#pragma unroll
-      for (int s = 0; s <= r; ++s) Sacc.at(r, s) += wj[r] * wj[s];
-    }
-    __syncwarp();
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < T; ++r) w[r * n_pad + jj] = wj[r];
-    }
+    for (int r = 0; r < T; ++r) wj[r] = w[r * n_pad + jj];
+    const double rd_next = col[m - jj];  // = LT[packed_col(jj + 1, m)]: reciprocal diagonal of column jj+1
     for (int i = jj + 1 + lane; i < m; i += 32) {
       const double l = col[i - jj];
+      const double sc = (i == jj + 1) ? rd_next : 1.0;
 #pragma unroll
-      for (int r = 0; r < T; ++r) w[r * n_pad + i] -= l * wj[r];
+      for (int r = 0; r < T; ++r) w[r * n_pad + i] = (w[r * n_pad + i] - l * wj[r]) * sc;
     }
   }
   __syncwarp();
 
   // ---- C: own bordered rows, streamed from HBM ---------------------------------------------------
   const double* Lb = st.Lh + (size_t)b * st.c_cap * st.ldL;
-  const double* bh = st.beta_h + (size_t)b * st.c_cap;
-  for (int i0 = 0; i0 < c; i0 += STEP_RB) {
-    const int nrow = min(STEP_RB, c - i0);
+  const size_t ldL = st.ldL;
+  int i0 = 0;
+  for (; i0 + RB <= c; i0 += RB) {
     const int len = m + i0;  // prefix whose w is final
-    double acc[STEP_RB][T];
+    const double* rows = Lb + (size_t)i0 * ldL;
+    double acc[RB][T];
 #pragma unroll
-    for (int a = 0; a < STEP_RB; ++a)
+    for (int a = 0; a < RB; ++a)
 #pragma unroll
       for (int r = 0; r < T; ++r) acc[a][r] = 0.0;
     for (int k = 2 * lane; k < len; k += 64) {
-      const bool two = (k + 1 < len);
-      double2 l2[STEP_RB];
-#pragma unroll
-      for (int a = 0; a < STEP_RB; ++a)
-        if (a < nrow) l2[a] = *reinterpret_cast<const double2*>(Lb + (size_t)(i0 + a) * st.ldL + k);
-        else l2[a] = make_double2(0.0, 0.0);
+      double2 wv[T];
 #pragma unroll
       for (int r = 0; r < T; ++r) {
-        const double w0 = w[r * n_pad + k];
-        const double w1 = two ? w[r * n_pad + k + 1] : 0.0;
+        wv[r] = *reinterpret_cast<const double2*>(w + r * n_pad + k);
+        if (k + 1 >= len) wv[r].y = 0.0;  // entry `len` is not final yet
+      }
 #pragma unroll
-        for (int a = 0; a < STEP_RB; ++a) acc[a][r] += l2[a].x * w0 + l2[a].y * w1;
+      for (int a = 0; a < RB; ++a) {
+        const double2 l2 = *reinterpret_cast<const double2*>(rows + a * ldL + k);
+#pragma unroll
+        for (int r = 0; r < T; ++r) acc[a][r] = fma(l2.x, wv[r].x, fma(l2.y, wv[r].y, acc[a][r]));
       }
     }
+    // transpose-reduce through shared memory: lane v sums partial dot product v over the 32 lanes
 #pragma unroll
-    for (int a = 0; a < STEP_RB; ++a)
+    for (int a = 0; a < RB; ++a)
 #pragma unroll
-      for (int r = 0; r < T; ++r) acc[a][r] = warp_sum(acc[a][r]);
-    // resolve the nrow x nrow triangular corner (uniform over lanes)
-    double wn[STEP_RB][T];
+      for (int r = 0; r < T; ++r) red[(a * T + r) * STEP_RED_LD + lane] = acc[a][r];
+    __syncwarp();
+    if (lane < NV) {
+      const double* rr = red + lane * STEP_RED_LD;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int a = 0; a < STEP_RB; ++a) {
-      if (a < nrow) {
-        const double* row = Lb + (size_t)(i0 + a) * st.ldL + len;
-        double v[T];
+      for (int i = 0; i < 32; i += 4) {
+        s0 += rr[i];
+        s1 += rr[i + 1];
+        s2 += rr[i + 2];
+        s3 += rr[i + 3];
+      }
+      tot[lane] = (s0 + s1) + (s2 + s3);
+    }
+    __syncwarp();
+    if (lane < T) {  // lane r resolves the RB x RB triangular corner for right-hand side r
+      double wn[RB];
+      double* wr = w + lane * n_pad + len;
 #pragma unroll
-        for (int r = 0; r < T; ++r) v[r] = w[r * n_pad + len + a] - acc[a][r];
+      for (int a = 0; a < RB; ++a) {
+        const double* row = rows + a * ldL + len;
+        double v = wr[a] - tot[a * T + lane];
 #pragma unroll
-        for (int bb = 0; bb < a; ++bb) {
-          const double l = row[bb];
-#pragma unroll
-          for (int r = 0; r < T; ++r) v[r] -= l * wn[bb][r];
-        }
-        const double dg = row[a];
-        const double be = bh[i0 + a];
-#pragma unroll
-        for (int r = 0; r < T; ++r) {
-          wn[a][r] = v[r] / dg;
-          macc[r] += wn[a][r] * be;
-        }
-#pragma unroll
-        for (int r = 0; r < T; ++r)
-#pragma unroll
-          for (int s = 0; s <= r; ++s) Sacc.at(r, s) += wn[a][r] * wn[a][s];
+        for (int bb = 0; bb < a; ++bb) v -= row[bb] * wn[bb];
+        wn[a] = v * row[a];  // diagonal slot holds 1/L_kk
+        wr[a] = wn[a];
       }
     }
     __syncwarp();
+  }
+  for (; i0 < c; ++i0) {  // tail rows (c not a multiple of RB)
+    const int len = m + i0;
+    const double* row = Lb + (size_t)i0 * ldL;
+    double acc[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) acc[r] = 0.0;
+    for (int k = lane; k < len; k += 32) {
+      const double l = row[k];
+#pragma unroll
+      for (int r = 0; r < T; ++r) acc[r] = fma(l, w[r * n_pad + k], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < T; ++r) acc[r] = warp_sum(acc[r]);
+    const double rd = row[len];
     if (lane == 0) {
 #pragma unroll
-      for (int a = 0; a < STEP_RB; ++a)
-        if (a < nrow) {
-#pragma unroll
-          for (int r = 0; r < T; ++r) w[r * n_pad + len + a] = wn[a][r];
-        }
+      for (int r = 0; r < T; ++r) w[r * n_pad + len] = (w[r * n_pad + len] - acc[r]) * rd;
     }
     __syncwarp();
   }
 
-  // ---- D: posterior moments ----------------------------------------------------------------------
+  // ---- D: posterior moments: S = K** - sum_i w_i w_i^T, mean = sum_i w_i beta_i -------------------------
+  TriT<T> Sacc;
+  double macc[T];
+#pragma unroll
+  for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = 0.0;
+#pragma unroll
+  for (int r = 0; r < T; ++r) macc[r] = 0.0;
+  const double* bh = st.beta_h + (size_t)b * st.c_cap;
+  for (int i = lane; i < n; i += 32) {
+    const double be = i < m ? sBo[i] : bh[i - m];
+    double wi[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) wi[r] = w[r * n_pad + i];
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      macc[r] = fma(wi[r], be, macc[r]);
+#pragma unroll
+      for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(wi[r], wi[s], Sacc.at(r, s));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = warp_sum(Sacc.v[i]);
+#pragma unroll
+  for (int r = 0; r < T; ++r) macc[r] = warp_sum(macc[r]);
   TriT<T> S;
 #pragma unroll
   for (int r = 0; r < T; ++r)
@@ -308,11 +338,11 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   if (!chol_T<T>(Sn, 0.0, Ln)) {
     if (lane == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
   }
-  double* Lnew = st.Lh + ((size_t)b * st.c_cap + c) * st.ldL;
+  double* Lnew = st.Lh + ((size_t)b * st.c_cap + c) * ldL;
   double bn[T];
 #pragma unroll
   for (int r = 0; r < T; ++r) {
-    for (int k = lane; k < n; k += 32) Lnew[(size_t)r * st.ldL + k] = w[r * n_pad + k];
+    for (int k = lane; k < n; k += 32) Lnew[(size_t)r * ldL + k] = w[r * n_pad + k];
     double t = yv[r] - macc[r];
 #pragma unroll
     for (int s = 0; s < r; ++s) t -= Ln.at(r, s) * bn[s];
@@ -322,7 +352,8 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
     for (int r = 0; r < T; ++r) {
 #pragma unroll
-      for (int s = 0; s <= r; ++s) Lnew[(size_t)r * st.ldL + n + s] = Ln.at(r, s);
+      for (int s = 0; s < r; ++s) Lnew[(size_t)r * ldL + n + s] = Ln.at(r, s);
+      Lnew[(size_t)r * ldL + n + r] = 1.0 / Ln.at(r, r);  // reciprocal diagonal (see gpmpc_state.cuh)
       st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
     }
     if (b == 0) {
