@@ -416,10 +416,12 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   }
   if ((int)smem > h->max_dyn_smem) return fail(h, GPMPC_ERR_CAPACITY, "factor too large for the fused step kernel");
   auto kern = k_step<D, T>;
-  static size_t configured = 0;  // per instantiation
-  if (smem > 48 * 1024 && smem > configured) {
+  static bool configured = false;  // per instantiation
+  if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-    configured = h->max_dyn_smem;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    configured = true;
   }
   dim3 grid((st.ns + STEP_WARPS - 1) / STEP_WARPS, st.g_ny);
   kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, n_pad, loo_in_smem);

@@ -92,10 +92,11 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   double* red = w + T * n_pad;
   double* tot = red + NV * STEP_RED_LD + ((NV * STEP_RED_LD) & 1);
 
-  double ls[D], xs[D];
+  double ls[D], il[D], xs[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) {
     ls[a] = st.ls[j * D + a];
+    il[a] = 1.0 / ls[a];
     xs[a] = x[(size_t)b * D + a];
   }
   const double os = st.os[j];
@@ -112,14 +113,14 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
       xa = st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * D;
       ta = st.hobs_task[k];
     }
-    double g[D], sq = 0.0, ga = 0.0, la2 = 1.0;
+    double g[D], sq = 0.0, ga = 0.0, il2 = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       double r = xa[a] - xs[a];
-      double t = r / ls[a];
-      sq += t * t;
-      g[a] = t / ls[a];  // r_a / l_a^2
-      if (a == ta - 1) { ga = g[a]; la2 = ls[a] * ls[a]; }
+      double t = r * il[a];
+      sq = fma(t, t, sq);
+      g[a] = t * il[a];  // r_a / l_a^2
+      if (a == ta - 1) { ga = g[a]; il2 = il[a] * il[a]; }
     }
     double k0 = os * exp(-0.5 * sq);
     if (ta == 0) {
@@ -131,7 +132,7 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
       for (int tb = 1; tb < T; ++tb) {
         double h = -ga * g[tb - 1];
-        if (tb == ta) h += 1.0 / la2;
+        if (tb == ta) h += il2;
         w[tb * n_pad + i] = k0 * h;
       }
     }
@@ -268,7 +269,7 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
     for (int s = 0; s <= r; ++s) {
       double kss = 0.0;
-      if (r == s) kss = (r == 0) ? os : os / (ls[r > 0 ? r - 1 : 0] * ls[r > 0 ? r - 1 : 0]);
+      if (r == s) kss = (r == 0) ? os : os * (il[r > 0 ? r - 1 : 0] * il[r > 0 ? r - 1 : 0]);
       S.at(r, s) = kss - Sacc.at(r, s);
     }
   double vr[T];
