@@ -69,41 +69,57 @@ static cudaError_t dev_alloc(Tp** p, size_t count) {
 static void free_factor_state(gpmpc_handle* h) {
   DevState& st = h->st;
   cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task);
-  cudaFree(st.Lh); cudaFree(st.beta_h);
-  st.Xh = st.Yh = st.Lh = st.beta_h = nullptr;
+  cudaFree(st.LhT); cudaFree(st.rdiag); cudaFree(st.beta_h);
+  st.Xh = st.Yh = st.LhT = st.rdiag = st.beta_h = nullptr;
   st.hobs_pt = st.hobs_task = nullptr;
+}
+
+// copies element b's factor entries, reciprocal diagonals and beta between two layouts (capacity growth)
+__global__ void k_relayout(DevState from, DevState to) {
+  const int b = blockIdx.x;
+  const int cols = from.m + from.c, rows = from.c;
+  for (int idx = threadIdx.x; idx < cols * rows; idx += blockDim.x) {
+    const int col = idx / rows, k = idx % rows;
+    *own_entry(to, b, k, col) = *own_entry(from, b, k, col);
+  }
+  for (int k = threadIdx.x; k < rows; k += blockDim.x) {
+    to.rdiag[(size_t)b * to.c_cap + k] = from.rdiag[(size_t)b * from.c_cap + k];
+    to.beta_h[(size_t)b * to.c_cap + k] = from.beta_h[(size_t)b * from.c_cap + k];
+  }
 }
 
 // (re)allocates the per-element state for `cap_points`, keeping what is already stored
 static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stream) {
   DevState old = h->st;
   DevState& st = h->st;
-  // the factor rows exist only while conditioning is on; a record-only handle keeps just the data set
+  // the factor exists only while conditioning is on; a record-only handle keeps just the data set
   const int c_cap = h->condition ? cap_points * st.T : 0;
-  const int ldL = ((st.m + c_cap + 3) / 4) * 4;
-  double *Xh, *Yh, *Lh, *beta_h;
+  const int ldC = std::max(4, ((c_cap + 3) / 4) * 4);
+  double *Xh, *Yh, *LhT, *rdiag, *beta_h;
   int *hp, *ht;
   const size_t B = (size_t)st.B;
+  const size_t lh_count = c_cap ? B * (size_t)(st.m + c_cap) * ldC : 1;
   CUDA_TRY(h, dev_alloc(&Xh, B * cap_points * st.d));
   CUDA_TRY(h, dev_alloc(&Yh, B * cap_points * st.T));
-  CUDA_TRY(h, dev_alloc(&Lh, B * c_cap * (size_t)ldL));
+  CUDA_TRY(h, dev_alloc(&LhT, lh_count));
+  CUDA_TRY(h, dev_alloc(&rdiag, B * c_cap));
   CUDA_TRY(h, dev_alloc(&beta_h, B * c_cap));
   CUDA_TRY(h, dev_alloc(&hp, (size_t)c_cap));
   CUDA_TRY(h, dev_alloc(&ht, (size_t)c_cap));
+  // entries on and above the diagonal are never written and must read as 0 (gpmpc_state.cuh)
+  CUDA_TRY(h, cudaMemsetAsync(LhT, 0, lh_count * sizeof(double), stream));
   if (old.Xh && old.np > 0) {
     CUDA_TRY(h, cudaMemcpy2DAsync(Xh, (size_t)cap_points * st.d * 8, old.Xh, (size_t)old.cap_points * st.d * 8,
                                   (size_t)old.np * st.d * 8, B, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpy2DAsync(Yh, (size_t)cap_points * st.T * 8, old.Yh, (size_t)old.cap_points * st.T * 8,
                                   (size_t)old.np * st.T * 8, B, cudaMemcpyDeviceToDevice, stream));
   }
-  if (old.Lh && old.c > 0) {
-    // rows keep their content; only the row stride and the per-element stride change
-    for (size_t b = 0; b < B; ++b)
-      CUDA_TRY(h, cudaMemcpy2DAsync(Lh + b * c_cap * (size_t)ldL, (size_t)ldL * 8,
-                                    old.Lh + b * old.c_cap * (size_t)old.ldL, (size_t)old.ldL * 8,
-                                    (size_t)(st.m + old.c) * 8, old.c, cudaMemcpyDeviceToDevice, stream));
-    CUDA_TRY(h, cudaMemcpy2DAsync(beta_h, (size_t)c_cap * 8, old.beta_h, (size_t)old.c_cap * 8,
-                                  (size_t)old.c * 8, B, cudaMemcpyDeviceToDevice, stream));
+  if (old.LhT && old.c > 0 && c_cap >= old.c) {
+    DevState to = st;
+    to.LhT = LhT; to.rdiag = rdiag; to.beta_h = beta_h; to.c_cap = c_cap; to.ldC = ldC;
+    k_relayout<<<(unsigned)B, 256, 0, stream>>>(old, to);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaMemcpyAsync(hp, old.hobs_pt, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpyAsync(ht, old.hobs_task, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
   }
@@ -111,8 +127,8 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
     CUDA_TRY(h, cudaStreamSynchronize(stream));
     free_factor_state(h);
   }
-  st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
-  st.cap_points = cap_points; st.c_cap = c_cap; st.ldL = ldL;
+  st.Xh = Xh; st.Yh = Yh; st.LhT = LhT; st.rdiag = rdiag; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
+  st.cap_points = cap_points; st.c_cap = c_cap; st.ldC = ldC;
   h->dims.cap_points = cap_points;
   return GPMPC_OK;
 }
@@ -265,8 +281,8 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   const bool m_changed = (m != st.m);
   st.m = m;
   st.c = 0; st.np = 0;
-  if (m_changed || !st.Lh) {
-    // ldL depends on m: (re)allocate the per-element state from scratch
+  if (m_changed || !st.LhT) {
+    // the slab height depends on m: (re)allocate the per-element state from scratch
     free_factor_state(h);
     int rc = alloc_factor_state(h, st.cap_points, stream);
     if (rc) return rc;
@@ -397,25 +413,23 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 
 }  // extern "C"
 
-template <int D, int T>
+template <int D, int T, int RSR, int RSO>
 static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                        const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                        cudaStream_t stream) {
-  const int m = st.m, n = st.m + st.c;
-  const int n_pad = ((n + 1) & ~1) + 2;
-  constexpr int NV = StepRB<T>::value * T;
+  const int m = st.m;
   const size_t tri_pad = (((size_t)m * (m + 1) / 2) + 1) & ~(size_t)1;
   const size_t m_pad = (m + 1) & ~1;
   const size_t shared_tab = (m_pad * D + m_pad) * 8 + 2 * m_pad * 4;
-  const size_t per_warp = ((size_t)T * n_pad + NV * STEP_RED_LD + 32 + ((NV * STEP_RED_LD) & 1)) * 8;
+  const size_t per_warp = (size_t)T * m_pad * 8;
   int loo_in_smem = 1;
   size_t smem = tri_pad * 8 + shared_tab + STEP_WARPS * per_warp;
-  if (smem > 100 * 1024) {  // keep >= 2 CTAs per SM; the shared factor then comes from L2
+  if (smem > 64 * 1024) {  // keep several CTAs per SM; the shared factor then comes from L2
     loo_in_smem = 0;
     smem = shared_tab + STEP_WARPS * per_warp;
   }
-  if ((int)smem > h->max_dyn_smem) return fail(h, GPMPC_ERR_CAPACITY, "factor too large for the fused step kernel");
-  auto kern = k_step<D, T>;
+  if ((int)smem > h->max_dyn_smem) return fail(h, GPMPC_ERR_CAPACITY, "real-data block too large for the fused step kernel");
+  auto kern = k_step<D, T, RSR, RSO>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
@@ -424,19 +438,38 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
     configured = true;
   }
   dim3 grid((st.ns + STEP_WARPS - 1) / STEP_WARPS, st.g_ny);
-  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, n_pad, loo_in_smem);
+  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
 }
 
+// register-slot variants: RSR*32 >= m shared rows, RSO*32 >= c own rows (picked per launch as c grows)
+template <int D, int T>
+static int dispatch_slots(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                          const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                          cudaStream_t stream, bool* handled) {
+  const int m = st.m, c = st.c;
+  *handled = true;
+#define STEP_VARIANT(RSR_, RSO_)                                                         \
+  if (m <= 32 * RSR_ && c <= 32 * RSO_)                                                  \
+    return launch_step<D, T, RSR_, RSO_>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
+  STEP_VARIANT(2, 2)
+  STEP_VARIANT(2, 5)
+  STEP_VARIANT(6, 4)
+  if (T <= 4) { STEP_VARIANT(8, 8) }
+#undef STEP_VARIANT
+  *handled = false;
+  return GPMPC_OK;
+}
+
 static int dispatch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                          const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
-                         cudaStream_t stream) {
-#define STEP_CASE(D_)                                                                            \
-  case D_:                                                                                       \
-    return st.T == 1 ? launch_step<D_, 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream)      \
-                     : launch_step<D_, D_ + 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
+                         cudaStream_t stream, bool* handled) {
+#define STEP_CASE(D_)                                                                                  \
+  case D_:                                                                                             \
+    return st.T == 1 ? dispatch_slots<D_, 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled) \
+                     : dispatch_slots<D_, D_ + 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
   switch (st.d) {
     STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6)
   }
@@ -461,8 +494,19 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
   const int grow = (eps && h->condition) ? 1 : 0;
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
   count_work(h, 1, grow);
-  rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream);
+  bool handled = false;
+  rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream, &handled);
   if (rc) return rc;
+  if (!handled) {
+    // factor too tall for the register-resident sweep: same recursion through the general block kernels
+    const double w_bytes = h->last_bytes, w_flops = h->last_flops;
+    rc = gpmpc_posterior(h, x, 1, mean, var, eps, opts, y, jitter_level, stream_);
+    if (rc) return rc;
+    if (eps) rc = gpmpc_append(h, x, y, nullptr, 1, stream_);
+    h->last_bytes = w_bytes;
+    h->last_flops = w_flops;
+    return rc;
+  }
   if (eps) {
     hst.np += 1;
     if (grow) {
@@ -574,7 +618,8 @@ int64_t gpmpc_state_bytes(const gpmpc_handle* h) {
   if (!h) return -1;
   const DevState& st = h->st;
   const int64_t B = st.B;
-  return 8 * (B * st.c_cap * (int64_t)st.ldL + B * st.c_cap + B * st.cap_points * (int64_t)(st.d + st.T)) +
+  return 8 * (B * (st.c_cap ? (int64_t)(st.m + st.c_cap) * st.ldC : 0) + 2 * B * st.c_cap +
+              B * st.cap_points * (int64_t)(st.d + st.T)) +
          8 * (int64_t)st.g_ny * ((int64_t)st.m * st.m + (int64_t)st.m * (st.m + 1) / 2 + st.m);
 }
 

@@ -121,19 +121,19 @@ __device__ void block_posterior(const DevState& st, int b, const double* __restr
     const int rb = min(FS_ROWS, n - i0);
     for (int idx = tid; idx < rb * q; idx += nt) {
       int a = idx / q, r = idx % q;
-      const double* Lrow = factor_row(st, b, j, i0 + a);
       double acc = 0.0;
-      for (int k = 0; k < i0; ++k) acc += Lrow[k] * W[(size_t)k * q + r];
+      for (int k = 0; k < i0; ++k) acc += factor_entry(st, b, j, i0 + a, k) * W[(size_t)k * q + r];
       W[(size_t)(i0 + a) * q + r] -= acc;
     }
     __syncthreads();
     for (int r = tid; r < q; r += nt) {  // a thread owns column r: no sync needed inside the block
       for (int a = 0; a < rb; ++a) {
-        const double* Lrow = factor_row(st, b, j, i0 + a);
-        double v = W[(size_t)(i0 + a) * q + r];
-        for (int bb = 0; bb < a; ++bb) v -= Lrow[i0 + bb] * W[(size_t)(i0 + bb) * q + r];
-        // own rows keep 1/L_kk in the diagonal slot, the shared block keeps L_kk
-        W[(size_t)(i0 + a) * q + r] = (i0 + a >= st.m) ? v * Lrow[i0 + a] : v / Lrow[i0 + a];
+        const int i = i0 + a;
+        double v = W[(size_t)i * q + r];
+        for (int bb = 0; bb < a; ++bb) v -= factor_entry(st, b, j, i, i0 + bb) * W[(size_t)(i0 + bb) * q + r];
+        // own rows keep 1/L_kk in rdiag, the shared block keeps L_kk on its diagonal
+        W[(size_t)i * q + r] = (i >= st.m) ? v * st.rdiag[(size_t)b * st.c_cap + (i - st.m)]
+                                           : v / st.Loo[((size_t)j * st.m + i) * st.m + i];
       }
     }
     __syncthreads();
@@ -251,7 +251,7 @@ k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts o
 // Conditioning: append the active points' T scalars each to element b's factor.
 //   reuse != 0 : the workspace may hold W, S, mu for exactly these x (checked per element on device)
 //   active     : DEVICE uint8[H] or NULL; pt_base = index of the first new point in Xh/Yh
-// New rows k = c + r':  Lh[k][0..n) = W[:, act(r')],  Lh[k][n + s'] = chol(S_act + noise)[r'][s'].
+// New rows k = c + r':  L[m+k][0..n) = W[:, act(r')],  L[m+k][n + s'] = chol(S_act + noise)[r'][s'].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK_THREADS)
 k_append(DevState st, const double* __restrict__ x, const double* __restrict__ ylab,
@@ -308,14 +308,15 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     if (tid == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
     return;
   }
-  double* Lnew = st.Lh + ((size_t)b * st.c_cap + st.c) * st.ldL;
+  // new rows k = c + rr, written column by column (rr fastest: contiguous within a column)
   for (int idx = tid; idx < qa * n; idx += nt) {
-    int rr = idx / n, k = idx % n;
-    Lnew[(size_t)rr * st.ldL + k] = W[(size_t)k * q + sh_act[rr]];
+    int k = idx / qa, rr = idx % qa;
+    *own_entry(st, b, st.c + rr, k) = W[(size_t)k * q + sh_act[rr]];
   }
   for (int idx = tid; idx < qa * qa; idx += nt) {
-    int rr = idx / qa, ss = idx % qa;
-    if (ss <= rr) Lnew[(size_t)rr * st.ldL + n + ss] = (ss == rr) ? 1.0 / C[idx] : C[idx];
+    int ss = idx / qa, rr = idx % qa;
+    if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = C[(size_t)rr * qa + ss];
+    else if (ss == rr) st.rdiag[(size_t)b * st.c_cap + st.c + rr] = 1.0 / C[(size_t)rr * qa + rr];
   }
   // beta_new = L_nn^{-1} (y - mu)
   if (tid < 32) {

@@ -15,7 +15,7 @@ struct DevState {
   int np;          // hallucinated points recorded per batch element
   int cap_points;  // capacity in points
   int c_cap;       // capacity in factor rows = cap_points * T
-  int ldL;         // row stride of Lh (doubles), multiple of 4, >= m + c_cap
+  int ldC;         // column stride of LhT (doubles), multiple of 4, >= c_cap
   double jitter;
   // shared (per GP output) ---------------------------------------------------------------
   const double* Xr;     // [n_real][d]
@@ -33,7 +33,12 @@ struct DevState {
   double* Yh;           // [B][cap_points][T]  labels as appended (NaN kept, for export)
   int* hobs_pt;         // [c_cap] hallucinated point of factor row k   (uniform over b)
   int* hobs_task;       // [c_cap] its task
-  double* Lh;           // [B][c_cap][ldL]  bordered rows: row k has m+k+1 entries, the last one is 1/L_kk
+  // The element's bordered rows  L[m+k][0..m+k]  are stored COLUMN-major: LhT[b][j][k] = L[m+k][j] for
+  // j < m+k (strictly below the diagonal); everything else in the (m+c_cap) x ldC slab stays 0 from the
+  // allocation memset.  Forward substitution then sweeps columns: a lane owns rows, reads of one column are
+  // contiguous over rows, and no cross-lane reduction is needed.  Diagonals live in rdiag as 1/L_kk.
+  double* LhT;          // [B][m + c_cap][ldC]
+  double* rdiag;        // [B][c_cap]  1 / L[m+k][m+k]
   double* beta_h;       // [B][c_cap]
   unsigned* status;     // device status word (GPMPC_ST_*)
   // workspace of the block kernels ---------------------------------------------------------
@@ -83,10 +88,15 @@ __device__ __forceinline__ const double* train_scalar(const DevState& st, int b,
   return st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * st.d;
 }
 
-// row i of the full bordered factor L = [[L_oo, 0], [Lh rows]] for batch element b (output j)
-__device__ __forceinline__ const double* factor_row(const DevState& st, int b, int j, int i) {
-  if (i < st.m) return st.Loo + ((size_t)j * st.m + i) * st.m;
-  return st.Lh + ((size_t)b * st.c_cap + (i - st.m)) * st.ldL;
+// address of L[m+k][col] (col < m+k) of batch element b's own rows
+__device__ __forceinline__ double* own_entry(const DevState& st, int b, int k, int col) {
+  return st.LhT + ((size_t)b * (st.m + st.c_cap) + col) * st.ldC + k;
+}
+
+// strictly-lower entry L[i][col] (col < i) of the full bordered factor [[L_oo, 0], [own rows]] (output j)
+__device__ __forceinline__ double factor_entry(const DevState& st, int b, int j, int i, int col) {
+  if (i < st.m) return st.Loo[((size_t)j * st.m + i) * st.m + col];
+  return *own_entry(st, b, i - st.m, col);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
