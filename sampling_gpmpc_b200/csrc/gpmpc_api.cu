@@ -421,7 +421,8 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   const size_t tri_pad = (((size_t)m * (m + 1) / 2) + 1) & ~(size_t)1;
   const size_t m_pad = (m + 1) & ~1;
   const size_t shared_tab = (m_pad * D + m_pad) * 8 + 2 * m_pad * 4;
-  const size_t per_warp = (size_t)T * m_pad * 8;
+  const int cs = ((st.c + 1) & ~1) + 2;  // stage column stride (doubles), even
+  const size_t per_warp = (size_t)T * m_pad * 8 + (size_t)STEP_P * STEP_G * cs * 8 + STEP_P * 8;
   int loo_in_smem = 1;
   size_t smem = tri_pad * 8 + shared_tab + STEP_WARPS * per_warp;
   if (smem > 64 * 1024) {  // keep several CTAs per SM; the shared factor then comes from L2
@@ -438,7 +439,7 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
     configured = true;
   }
   dim3 grid((st.ns + STEP_WARPS - 1) / STEP_WARPS, st.g_ny);
-  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem);
+  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem, cs);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;

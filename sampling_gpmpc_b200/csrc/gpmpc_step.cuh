@@ -12,8 +12,10 @@
 //
 //   A  kernel vector k(x*, X): each lane evaluates the entries of the rows it owns (one exp per row)
 //   B  shared columns j < m against L_oo (shared memory), final w_j also parked in shared memory
-//   V  the element's own rows against the shared columns (rows stream from HBM, fully independent loads)
-//   T  the element's own triangular block (streams from HBM; chain of c shuffles)
+//   V  the element's own rows against the shared columns   } the element's factor columns stream from HBM
+//   T  the element's own triangular block (c shuffles)      } through a per-warp ring of TMA bulk copies
+//      (cp.async.bulk + mbarrier complete_tx, STEP_P stages of STEP_G columns): one elected lane issues
+//      one copy per column, STEP_P-1 stages ahead of the stage being consumed
 //   D  Sigma* = K** - sum_i w_i w_i^T and mean = sum_i w_i beta_i from registers + warp-shuffle all-reduce
 //   E  T x T Cholesky with GPyTorch's jitter ladder, y = mean + L eps, zero-variance / truncation
 //   F  rank-T append: w_i goes to column i of the T new rows (T contiguous doubles per column)
@@ -25,6 +27,30 @@
 
 #define STEP_WARPS 4
 #define FULL_MASK 0xffffffffu
+#define STEP_G 2  // factor columns per TMA stage
+#define STEP_P 4  // stages in the per-warp ring (STEP_P - 1 stages in flight while one is consumed)
+
+// ---- TMA bulk copy + mbarrier (one ring per warp; the warp is its own producer and consumer) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 template <int T>
 struct TriT {  // lower-triangular T x T in registers
@@ -88,7 +114,7 @@ template <int D, int T, int RSR, int RSO>
 __global__ void __launch_bounds__(STEP_WARPS * 32)
 k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-       int* __restrict__ jitter_level, int grow_factor, int loo_in_smem) {
+       int* __restrict__ jitter_level, int grow_factor, int loo_in_smem, int cs) {
   extern __shared__ __align__(16) double smem[];
   const int j_out = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,6 +130,10 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   double* sBo = sXo + (size_t)m_pad * D;               // [m_pad]
   int* sTo = (int*)(sBo + m_pad);                      // [2*m_pad] ints: task of observed real scalar i
   double* wo_base = (double*)(sTo + 2 * m_pad);        // per warp: final w of the shared rows, [T][m_pad]
+  double* ring_base = wo_base + (size_t)STEP_WARPS * T * m_pad;  // per warp: [STEP_P][STEP_G][cs]
+  uint64_t* bar_base = (uint64_t*)(ring_base + (size_t)STEP_WARPS * STEP_P * STEP_G * cs);  // [warps][STEP_P]
+  if (threadIdx.x < STEP_WARPS * STEP_P) mbar_init(bar_base + threadIdx.x, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   const double* gLT = st.LooT + (size_t)j_out * tri;
   if (loo_in_smem)
     for (size_t i = threadIdx.x; i < tri; i += blockDim.x) sLT[i] = gLT[i];
@@ -119,6 +149,8 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   const double* LT = loo_in_smem ? sLT : gLT;
   const int b = s_idx * st.g_ny + j_out;
   double* wo = wo_base + (size_t)warp * T * m_pad;
+  double* ring = ring_base + (size_t)warp * STEP_P * STEP_G * cs;
+  uint64_t* bars = bar_base + warp * STEP_P;
   const size_t ldC = st.ldC;
   double* LhTb = st.LhT + (size_t)b * (m + st.c_cap) * ldC;
 
@@ -188,48 +220,104 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   }
   __syncwarp();
 
-  // ---- V: own rows against the shared columns (independent loads, streamed from HBM) ----------------------
-  if (c > 0) {
-#pragma unroll 4
-    for (int j = 0; j < m; ++j) {
-      const double* col = LhTb + (size_t)j * ldC;
-      double wj[T];
+  // ---- V + T: the element's own factor columns, streamed through the TMA ring ------------------------------
+  // group g = STEP_G consecutive columns; groups 0..nV-1 cover the shared columns 0..m-1 (all c own rows),
+  // groups nV.. cover the triangular columns k = 0..c-2 (rows k+1..c-1).  Column copies start at an even row
+  // and have even length so that source, destination and size are 16-byte aligned.
+  const int c_even = (c + 1) & ~1;
+  const int nV = c > 0 ? (m + STEP_G - 1) / STEP_G : 0;
+  const int nT = c > 1 ? (c - 1 + STEP_G - 1) / STEP_G : 0;
+  const int ngroups = nV + nT;
+  auto issue_group = [&](int g) {  // lane 0 only
+    const int sidx = g % STEP_P;
+    double* dst0 = ring + (size_t)sidx * STEP_G * cs;
+    uint32_t total = 0;
+    int col0, ncol, r0[STEP_G];
+    if (g < nV) {
+      col0 = g * STEP_G;
+      ncol = min(STEP_G, m - col0);
 #pragma unroll
-      for (int r = 0; r < T; ++r) wj[r] = wo[r * m_pad + j];
+      for (int u = 0; u < STEP_G; ++u) r0[u] = 0;
+    } else {
+      const int k0 = (g - nV) * STEP_G;
+      col0 = m + k0;
+      ncol = min(STEP_G, c - 1 - k0);
 #pragma unroll
-      for (int rs = 0; rs < RSO; ++rs) {
-        const int i = lane + 32 * rs;
-        if (i < c) {
-          const double l = col[i];
+      for (int u = 0; u < STEP_G; ++u) r0[u] = (k0 + u + 1) & ~1;
+    }
 #pragma unroll
-          for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
+    for (int u = 0; u < STEP_G; ++u)
+      if (u < ncol) total += (uint32_t)(c_even - r0[u]) * 8u;
+    mbar_expect_tx(bars + sidx, total);
+#pragma unroll
+    for (int u = 0; u < STEP_G; ++u)
+      if (u < ncol)
+        tma_bulk_g2s(dst0 + (size_t)u * cs + r0[u], LhTb + (size_t)(col0 + u) * ldC + r0[u],
+                     (uint32_t)(c_even - r0[u]) * 8u, bars + sidx);
+  };
+  if (lane == 0)
+    for (int g = 0; g < min(STEP_P - 1, ngroups); ++g) issue_group(g);
+
+  for (int g = 0; g < nV; ++g) {
+    // the stage freed by group g-1 is refilled before this group is consumed
+    __syncwarp();
+    if (lane == 0 && g + STEP_P - 1 < ngroups) issue_group(g + STEP_P - 1);
+    mbar_wait(bars + g % STEP_P, (g / STEP_P) & 1);
+    const double* stg = ring + (size_t)(g % STEP_P) * STEP_G * cs;
+#pragma unroll
+    for (int u = 0; u < STEP_G; ++u) {
+      const int j = g * STEP_G + u;
+      if (j < m) {
+        double wj[T];
+#pragma unroll
+        for (int r = 0; r < T; ++r) wj[r] = wo[r * m_pad + j];
+#pragma unroll
+        for (int rs = 0; rs < RSO; ++rs) {
+          const int i = lane + 32 * rs;
+          if (i < c) {
+            const double l = stg[u * cs + i];
+#pragma unroll
+            for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
+          }
         }
       }
     }
   }
 
-  // ---- T: own triangular block ----------------------------------------------------------------------------
 #pragma unroll
   for (int jb = 0; jb < RSO; ++jb) {
-    const int kend = min(32, c - 32 * jb);
-#pragma unroll 4
-    for (int jl = 0; jl < kend; ++jl) {
-      const int k = 32 * jb + jl;
-      const double* col = LhTb + (size_t)(m + k) * ldC;
-      double wj[T];
-#pragma unroll
-      for (int r = 0; r < T; ++r) wj[r] = __shfl_sync(FULL_MASK, ko[jb][r] * rdl[jb], jl);
-      if (lane == jl) {
-#pragma unroll
-        for (int r = 0; r < T; ++r) ko[jb][r] = wj[r];
+    for (int gi = 0; gi < 32 / STEP_G; ++gi) {
+      const int k0 = 32 * jb + STEP_G * gi;
+      if (k0 >= c) break;
+      const int g = nV + k0 / STEP_G;
+      const bool has_data = k0 < c - 1;
+      if (has_data) {
+        __syncwarp();
+        if (lane == 0 && g + STEP_P - 1 < ngroups) issue_group(g + STEP_P - 1);
+        mbar_wait(bars + g % STEP_P, (g / STEP_P) & 1);
       }
+      const double* stg = ring + (size_t)(g % STEP_P) * STEP_G * cs;
 #pragma unroll
-      for (int rs = jb; rs < RSO; ++rs) {
-        const int i = lane + 32 * rs;
-        if (i > k && i < c) {
-          const double l = col[i];
+      for (int u = 0; u < STEP_G; ++u) {
+        const int k = k0 + u;
+        if (k < c) {
+          const int jl = STEP_G * gi + u;
+          double wj[T];
 #pragma unroll
-          for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
+          for (int r = 0; r < T; ++r) wj[r] = __shfl_sync(FULL_MASK, ko[jb][r] * rdl[jb], jl);
+          if (lane == jl) {
+#pragma unroll
+            for (int r = 0; r < T; ++r) ko[jb][r] = wj[r];
+          }
+#pragma unroll
+          for (int rs = jb; rs < RSO; ++rs) {
+            const int i = lane + 32 * rs;
+            if (i > k && i < c) {
+              const double l = stg[u * cs + i];
+#pragma unroll
+              for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
+            }
+          }
         }
       }
     }
