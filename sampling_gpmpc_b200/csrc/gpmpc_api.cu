@@ -37,7 +37,7 @@ struct gpmpc_handle {
   int r_ns = 0;
   unsigned char* d_active = nullptr;
   int d_active_cap = 0;
-  int max_dyn_smem = 0;
+  int max_dyn_smem = 0, num_sms = 148;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -69,23 +69,9 @@ static cudaError_t dev_alloc(Tp** p, size_t count) {
 static void free_factor_state(gpmpc_handle* h) {
   DevState& st = h->st;
   cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task);
-  cudaFree(st.LhT); cudaFree(st.rdiag); cudaFree(st.beta_h);
-  st.Xh = st.Yh = st.LhT = st.rdiag = st.beta_h = nullptr;
+  cudaFree(st.Lh); cudaFree(st.beta_h);
+  st.Xh = st.Yh = st.Lh = st.beta_h = nullptr;
   st.hobs_pt = st.hobs_task = nullptr;
-}
-
-// copies element b's factor entries, reciprocal diagonals and beta between two layouts (capacity growth)
-__global__ void k_relayout(DevState from, DevState to) {
-  const int b = blockIdx.x;
-  const int cols = from.m + from.c, rows = from.c;
-  for (int idx = threadIdx.x; idx < cols * rows; idx += blockDim.x) {
-    const int col = idx / rows, k = idx % rows;
-    *own_entry(to, b, k, col) = *own_entry(from, b, k, col);
-  }
-  for (int k = threadIdx.x; k < rows; k += blockDim.x) {
-    to.rdiag[(size_t)b * to.c_cap + k] = from.rdiag[(size_t)b * from.c_cap + k];
-    to.beta_h[(size_t)b * to.c_cap + k] = from.beta_h[(size_t)b * from.c_cap + k];
-  }
 }
 
 // (re)allocates the per-element state for `cap_points`, keeping what is already stored
@@ -94,32 +80,33 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
   DevState& st = h->st;
   // the factor exists only while conditioning is on; a record-only handle keeps just the data set
   const int c_cap = h->condition ? cap_points * st.T : 0;
-  const int ldC = std::max(4, ((c_cap + 3) / 4) * 4);
-  double *Xh, *Yh, *LhT, *rdiag, *beta_h;
+  // sub-panel layout (gpmpc_state.cuh): an element's rows are one contiguous stream whose prefix does not
+  // depend on the capacity, so growing is a strided copy of the used prefixes
+  const long long stride = c_cap ? (long long)subpanel_off((c_cap + 7) / 8, st.mo) : 0;
+  double *Xh, *Yh, *Lh, *beta_h;
   int *hp, *ht;
   const size_t B = (size_t)st.B;
-  const size_t lh_count = c_cap ? B * (size_t)(st.m + c_cap) * ldC : 1;
+  const size_t lh_count = c_cap ? B * (size_t)stride : 1;
   CUDA_TRY(h, dev_alloc(&Xh, B * cap_points * st.d));
   CUDA_TRY(h, dev_alloc(&Yh, B * cap_points * st.T));
-  CUDA_TRY(h, dev_alloc(&LhT, lh_count));
-  CUDA_TRY(h, dev_alloc(&rdiag, B * c_cap));
+  CUDA_TRY(h, dev_alloc(&Lh, lh_count));
   CUDA_TRY(h, dev_alloc(&beta_h, B * c_cap));
   CUDA_TRY(h, dev_alloc(&hp, (size_t)c_cap));
   CUDA_TRY(h, dev_alloc(&ht, (size_t)c_cap));
-  // entries on and above the diagonal are never written and must read as 0 (gpmpc_state.cuh)
-  CUDA_TRY(h, cudaMemsetAsync(LhT, 0, lh_count * sizeof(double), stream));
+  // padding columns [m, mo) must read as 0; rows not yet appended are never used but kept finite
+  CUDA_TRY(h, cudaMemsetAsync(Lh, 0, lh_count * sizeof(double), stream));
   if (old.Xh && old.np > 0) {
     CUDA_TRY(h, cudaMemcpy2DAsync(Xh, (size_t)cap_points * st.d * 8, old.Xh, (size_t)old.cap_points * st.d * 8,
                                   (size_t)old.np * st.d * 8, B, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpy2DAsync(Yh, (size_t)cap_points * st.T * 8, old.Yh, (size_t)old.cap_points * st.T * 8,
                                   (size_t)old.np * st.T * 8, B, cudaMemcpyDeviceToDevice, stream));
   }
-  if (old.LhT && old.c > 0 && c_cap >= old.c) {
-    DevState to = st;
-    to.LhT = LhT; to.rdiag = rdiag; to.beta_h = beta_h; to.c_cap = c_cap; to.ldC = ldC;
-    k_relayout<<<(unsigned)B, 256, 0, stream>>>(old, to);
-    h->launches++;
-    CUDA_TRY(h, cudaGetLastError());
+  if (old.Lh && old.c > 0 && c_cap >= old.c) {
+    const size_t used = subpanel_off((old.c + 7) / 8, st.mo) * 8;  // bytes of the sub-panels in use
+    CUDA_TRY(h, cudaMemcpy2DAsync(Lh, (size_t)stride * 8, old.Lh, (size_t)old.elem_stride * 8, used, B,
+                                  cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpy2DAsync(beta_h, (size_t)c_cap * 8, old.beta_h, (size_t)old.c_cap * 8, (size_t)old.c * 8, B,
+                                  cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpyAsync(hp, old.hobs_pt, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpyAsync(ht, old.hobs_task, (size_t)old.c * 4, cudaMemcpyDeviceToDevice, stream));
   }
@@ -127,8 +114,8 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
     CUDA_TRY(h, cudaStreamSynchronize(stream));
     free_factor_state(h);
   }
-  st.Xh = Xh; st.Yh = Yh; st.LhT = LhT; st.rdiag = rdiag; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
-  st.cap_points = cap_points; st.c_cap = c_cap; st.ldC = ldC;
+  st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
+  st.cap_points = cap_points; st.c_cap = c_cap; st.elem_stride = stride;
   h->dims.cap_points = cap_points;
   return GPMPC_OK;
 }
@@ -184,6 +171,7 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   h->dims = *dims;
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->max_dyn_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   DevState& st = h->st;
   st.ns = dims->ns; st.g_ny = dims->g_ny; st.d = dims->d; st.T = dims->T; st.n_real = dims->n_real;
   st.B = dims->ns * dims->g_ny;
@@ -205,7 +193,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   free_factor_state(h);
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
-  cudaFree(st.Loo); cudaFree(st.LooT); cudaFree(st.beta_o); cudaFree(st.status);
+  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -264,14 +252,14 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     for (int i = 0; i < m; ++i) yobs[(size_t)j * m + i] = hy[((size_t)j * n + pt[i]) * T + task[i]];
 
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
-  cudaFree(st.Loo); cudaFree(st.LooT); cudaFree(st.beta_o);
+  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o);
   double *Xr, *yo; int *op, *ot;
   CUDA_TRY(h, dev_alloc(&Xr, (size_t)n * d));
   CUDA_TRY(h, dev_alloc(&op, (size_t)m));
   CUDA_TRY(h, dev_alloc(&ot, (size_t)m));
   CUDA_TRY(h, dev_alloc(&yo, (size_t)g_ny * m));
   CUDA_TRY(h, dev_alloc(&st.Loo, (size_t)g_ny * m * m));
-  CUDA_TRY(h, dev_alloc(&st.LooT, (size_t)g_ny * ((size_t)m * (m + 1) / 2)));
+  CUDA_TRY(h, dev_alloc(&st.LooP, (size_t)g_ny * subpanel_off((m + 7) / 8, 0)));
   CUDA_TRY(h, dev_alloc(&st.beta_o, (size_t)g_ny * m));
   CUDA_TRY(h, cudaMemcpyAsync(Xr, X, (size_t)n * d * 8, cudaMemcpyDeviceToDevice, stream));
   CUDA_TRY(h, cudaMemcpyAsync(op, pt.data(), (size_t)m * 4, cudaMemcpyHostToDevice, stream));
@@ -280,8 +268,9 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   st.Xr = Xr; st.obs_pt = op; st.obs_task = ot; st.y_obs = yo;
   const bool m_changed = (m != st.m);
   st.m = m;
+  st.mo = (m + 7) & ~7;
   st.c = 0; st.np = 0;
-  if (m_changed || !st.LhT) {
+  if (m_changed || !st.Lh) {
     // the slab height depends on m: (re)allocate the per-element state from scratch
     free_factor_state(h);
     int rc = alloc_factor_state(h, st.cap_points, stream);
@@ -413,24 +402,26 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 
 }  // extern "C"
 
-template <int D, int T, int RSR, int RSO>
+template <int D, int T>
 static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                        const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
-                       cudaStream_t stream) {
-  const int m = st.m;
-  const size_t tri_pad = (((size_t)m * (m + 1) / 2) + 1) & ~(size_t)1;
-  const size_t m_pad = (m + 1) & ~1;
-  const size_t shared_tab = (m_pad * D + m_pad) * 8 + 2 * m_pad * 4;
-  const int cs = ((st.c + 1) & ~1) + 2;  // stage column stride (doubles), even
-  const size_t per_warp = (size_t)T * m_pad * 8 + (size_t)STEP_P * STEP_G * cs * 8 + STEP_P * 8;
+                       cudaStream_t stream, bool* handled) {
+  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
+  const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
+  const size_t loop_sz = subpanel_off(Pm, 0);
+  const size_t m_even = (m + 1) & ~1;
+  const size_t shared_tab = (m_even * D + m_even) * 8 + 2 * m_even * 4 + 128;
+  const size_t wv_sz = ((size_t)(st.mo + 8 * P8) * TP + 15) & ~(size_t)15;
+  const size_t per_warp = (wv_sz + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
   int loo_in_smem = 1;
-  size_t smem = tri_pad * 8 + shared_tab + STEP_WARPS * per_warp;
-  if (smem > 64 * 1024) {  // keep several CTAs per SM; the shared factor then comes from L2
+  size_t smem = loop_sz * 8 + shared_tab + STEP_WARPS * per_warp;
+  if (loop_sz * 8 > 40 * 1024) {  // large real-data block: L_oo is read through L1/L2 instead
     loo_in_smem = 0;
     smem = shared_tab + STEP_WARPS * per_warp;
   }
-  if ((int)smem > h->max_dyn_smem) return fail(h, GPMPC_ERR_CAPACITY, "real-data block too large for the fused step kernel");
-  auto kern = k_step<D, T, RSR, RSO>;
+  *handled = (int)smem <= h->max_dyn_smem;
+  if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over
+  auto kern = k_step<D, T>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
@@ -438,29 +429,16 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
                                      cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  dim3 grid((st.ns + STEP_WARPS - 1) / STEP_WARPS, st.g_ny);
-  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem, cs);
+  // persistent CTAs: as many as are co-resident, split over the g_ny outputs; each warp loops over samples
+  int occ = 1;
+  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STEP_WARPS * 32, smem));
+  occ = std::max(occ, 1);
+  const int want = (st.ns + STEP_WARPS - 1) / STEP_WARPS;
+  const int resident = std::max(1, h->num_sms * occ / st.g_ny);
+  dim3 grid(std::min(want, resident), st.g_ny);
+  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  return GPMPC_OK;
-}
-
-// register-slot variants: RSR*32 >= m shared rows, RSO*32 >= c own rows (picked per launch as c grows)
-template <int D, int T>
-static int dispatch_slots(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
-                          const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
-                          cudaStream_t stream, bool* handled) {
-  const int m = st.m, c = st.c;
-  *handled = true;
-#define STEP_VARIANT(RSR_, RSO_)                                                         \
-  if (m <= 32 * RSR_ && c <= 32 * RSO_)                                                  \
-    return launch_step<D, T, RSR_, RSO_>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
-  STEP_VARIANT(2, 2)
-  STEP_VARIANT(2, 5)
-  STEP_VARIANT(6, 4)
-  if (T <= 4) { STEP_VARIANT(8, 8) }
-#undef STEP_VARIANT
-  *handled = false;
   return GPMPC_OK;
 }
 
@@ -469,8 +447,8 @@ static int dispatch_step(gpmpc_handle* h, const DevState& st, const double* x, c
                          cudaStream_t stream, bool* handled) {
 #define STEP_CASE(D_)                                                                                  \
   case D_:                                                                                             \
-    return st.T == 1 ? dispatch_slots<D_, 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled) \
-                     : dispatch_slots<D_, D_ + 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
+    return st.T == 1 ? launch_step<D_, 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled) \
+                     : launch_step<D_, D_ + 1>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
   switch (st.d) {
     STEP_CASE(1) STEP_CASE(2) STEP_CASE(3) STEP_CASE(4) STEP_CASE(5) STEP_CASE(6)
   }
@@ -619,9 +597,8 @@ int64_t gpmpc_state_bytes(const gpmpc_handle* h) {
   if (!h) return -1;
   const DevState& st = h->st;
   const int64_t B = st.B;
-  return 8 * (B * (st.c_cap ? (int64_t)(st.m + st.c_cap) * st.ldC : 0) + 2 * B * st.c_cap +
-              B * st.cap_points * (int64_t)(st.d + st.T)) +
-         8 * (int64_t)st.g_ny * ((int64_t)st.m * st.m + (int64_t)st.m * (st.m + 1) / 2 + st.m);
+  return 8 * (B * (int64_t)st.elem_stride + B * st.c_cap + B * st.cap_points * (int64_t)(st.d + st.T)) +
+         8 * (int64_t)st.g_ny * ((int64_t)st.m * st.m + (int64_t)subpanel_off((st.m + 7) / 8, 0) + st.m);
 }
 
 int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops) {

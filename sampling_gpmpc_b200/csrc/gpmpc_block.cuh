@@ -70,11 +70,15 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
     __syncthreads();
   }
   if (level > 0 && tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_JITTER | ((unsigned)level << 8));
-  // packed column-major copy for the fused rollout kernel
-  double* LT = st.LooT + (size_t)j * ((size_t)m * (m + 1) / 2);
+  // sub-panel copy for the fused rollout kernel (gpmpc_state.cuh): diagonal stored as 1/L_jj, rest of the
+  // upper triangle and the padding rows zero
+  const int Pm = (m + 7) >> 3;
+  double* LP = st.LooP + (size_t)j * subpanel_off(Pm, 0);
+  for (int idx = tid; idx < (int)subpanel_off(Pm, 0); idx += nt) LP[idx] = 0.0;
+  __syncthreads();
   for (int idx = tid; idx < m * m; idx += nt) {
     int i = idx / m, cc = idx % m;
-    if (cc <= i) LT[packed_col(cc, m) + (i - cc)] = (cc == i) ? 1.0 / A[idx] : A[idx];  // diagonal stored as 1/L_jj
+    if (cc <= i) LP[subpanel_off(i >> 3, 0) + (size_t)cc * 8 + (i & 7)] = (cc == i) ? 1.0 / A[idx] : A[idx];
   }
   // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
   if (tid < 32) {
@@ -131,8 +135,8 @@ __device__ void block_posterior(const DevState& st, int b, const double* __restr
         const int i = i0 + a;
         double v = W[(size_t)i * q + r];
         for (int bb = 0; bb < a; ++bb) v -= factor_entry(st, b, j, i, i0 + bb) * W[(size_t)(i0 + bb) * q + r];
-        // own rows keep 1/L_kk in rdiag, the shared block keeps L_kk on its diagonal
-        W[(size_t)i * q + r] = (i >= st.m) ? v * st.rdiag[(size_t)b * st.c_cap + (i - st.m)]
+        // own rows keep 1/L_kk in their diagonal slot, the shared block keeps L_kk on its diagonal
+        W[(size_t)i * q + r] = (i >= st.m) ? v * *own_entry(st, b, i - st.m, i)
                                            : v / st.Loo[((size_t)j * st.m + i) * st.m + i];
       }
     }
@@ -316,7 +320,7 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   for (int idx = tid; idx < qa * qa; idx += nt) {
     int ss = idx / qa, rr = idx % qa;
     if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = C[(size_t)rr * qa + ss];
-    else if (ss == rr) st.rdiag[(size_t)b * st.c_cap + st.c + rr] = 1.0 / C[(size_t)rr * qa + rr];
+    else if (ss == rr) *own_entry(st, b, st.c + rr, n + rr) = 1.0 / C[(size_t)rr * qa + rr];
   }
   // beta_new = L_nn^{-1} (y - mu)
   if (tid < 32) {

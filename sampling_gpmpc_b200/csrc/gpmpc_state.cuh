@@ -8,14 +8,30 @@
 #define GP_MIN_VARIANCE 1e-10  // gpytorch.settings.min_variance for double
 #define GP_MAX_TRIES 3         // gpytorch.settings.cholesky_max_tries
 
+// ---- sub-panel layout of a lower-triangular factor -------------------------------------------------------
+// Rows are grouped in SUB-PANELS of 8.  Sub-panel p holds, for every storage column t < off + 8p + 8, the 8
+// consecutive doubles  L[8p .. 8p+7][t]  ("column group", 64 bytes); groups are stored one after the other in
+// column order and sub-panels one after the other in row order, so an element's factor is ONE contiguous
+// stream that the fused step kernel pulls through shared memory with TMA bulk copies in consumption order.
+//   off = 0 for the shared real-data factor L_oo (storage column = column);
+//   off = mo = roundup8(m) for an element's own rows: storage columns [0, m) are the shared columns, [m, mo)
+//   are zero padding (so that every column range the kernel iterates over in steps of 4 is aligned), and
+//   storage column mo + k is own column k.
+// Inside the 8 x 8 diagonal block only the strictly lower part is meaningful; the diagonal slot holds 1/L_kk.
+__host__ __device__ __forceinline__ size_t subpanel_off(int p, int off) {
+  // doubles before sub-panel p:  8 * sum_{q<p} (off + 8q + 8)
+  return (size_t)8 * ((size_t)p * (off + 8) + (size_t)4 * p * (p - 1));
+}
+
 struct DevState {
   int ns, g_ny, d, T, n_real, B;
   int m;           // observed real scalars (shared by every batch element)
-  int c;           // hallucinated scalars currently in the factor (rows of Lh in use)
+  int mo;          // storage-column offset of the own columns = roundup8(m)
+  int c;           // hallucinated scalars currently in the factor (own rows in use)
   int np;          // hallucinated points recorded per batch element
   int cap_points;  // capacity in points
   int c_cap;       // capacity in factor rows = cap_points * T
-  int ldC;         // column stride of LhT (doubles), multiple of 4, >= c_cap
+  long long elem_stride;  // doubles between consecutive elements' factors = subpanel_off(ceil(c_cap/8), mo)
   double jitter;
   // shared (per GP output) ---------------------------------------------------------------
   const double* Xr;     // [n_real][d]
@@ -26,19 +42,14 @@ struct DevState {
   const double* os;     // [g_ny]
   const double* noise;  // [g_ny][T]
   double* Loo;          // [g_ny][m][m] row-major lower Cholesky factor of K_oo + Sigma
-  double* LooT;         // [g_ny][m(m+1)/2] same factor, packed column-major (column j contiguous), diagonal = 1/L_jj
+  double* LooP;         // [g_ny][subpanel_off(ceil(m/8), 0)] the same factor in sub-panel layout, diagonal = 1/L_jj
   double* beta_o;       // [g_ny][m]  L_oo^{-1} y_o
   // per batch element --------------------------------------------------------------------
   double* Xh;           // [B][cap_points][d]
   double* Yh;           // [B][cap_points][T]  labels as appended (NaN kept, for export)
   int* hobs_pt;         // [c_cap] hallucinated point of factor row k   (uniform over b)
   int* hobs_task;       // [c_cap] its task
-  // The element's bordered rows  L[m+k][0..m+k]  are stored COLUMN-major: LhT[b][j][k] = L[m+k][j] for
-  // j < m+k (strictly below the diagonal); everything else in the (m+c_cap) x ldC slab stays 0 from the
-  // allocation memset.  Forward substitution then sweeps columns: a lane owns rows, reads of one column are
-  // contiguous over rows, and no cross-lane reduction is needed.  Diagonals live in rdiag as 1/L_kk.
-  double* LhT;          // [B][m + c_cap][ldC]
-  double* rdiag;        // [B][c_cap]  1 / L[m+k][m+k]
+  double* Lh;           // [B][elem_stride] own rows L[m+k][0 .. m+k] in sub-panel layout (off = mo)
   double* beta_h;       // [B][c_cap]
   unsigned* status;     // device status word (GPMPC_ST_*)
   // workspace of the block kernels ---------------------------------------------------------
@@ -49,11 +60,6 @@ struct DevState {
   double* mu;           // [B][q]
   double* xc;           // [B][H][d]  test points the cache was built for
 };
-
-__device__ __forceinline__ size_t packed_col(int j, int m) {
-  // start of column j in the packed column-major lower triangle (element (i,j), i>=j, at +i-j)
-  return (size_t)j * m - ((size_t)j * (j - 1)) / 2;
-}
 
 // cov( task ta of f at xa , task tb of f at xb ) for the scaled SE kernel with derivative tasks
 // (gpytorch RBFKernelGrad / RBFKernel under ScaleKernel).  r = xa - xb.
@@ -88,9 +94,11 @@ __device__ __forceinline__ const double* train_scalar(const DevState& st, int b,
   return st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * st.d;
 }
 
-// address of L[m+k][col] (col < m+k) of batch element b's own rows
+// address of L[m+k][col] (logical column col <= m+k) of batch element b's own rows; col == m+k is the
+// diagonal slot, which holds 1 / L[m+k][m+k]
 __device__ __forceinline__ double* own_entry(const DevState& st, int b, int k, int col) {
-  return st.LhT + ((size_t)b * (st.m + st.c_cap) + col) * st.ldC + k;
+  const int t = col < st.m ? col : col - st.m + st.mo;
+  return st.Lh + (size_t)b * st.elem_stride + subpanel_off(k >> 3, st.mo) + (size_t)t * 8 + (k & 7);
 }
 
 // strictly-lower entry L[i][col] (col < i) of the full bordered factor [[L_oo, 0], [own rows]] (output j)

@@ -1,34 +1,36 @@
-// K1: fused rollout step (H = 1).  One WARP per batch element (sample s, output j); the warps of a CTA
-// share output j, so the shared real-data factor L_oo (packed column-major, diagonal stored as 1/L_jj),
-// the observed real inputs and beta_o are staged once per CTA in shared memory.
+// K1: fused rollout step (H = 1): posterior + draw + post-processing + rank-T append in one launch.
 //
-// The whole step is a COLUMN SWEEP of the bordered factor with lanes owning rows:
-//   lane l holds, in registers, the T right-hand sides of rows l, l+32, ... (RSR slots for the m shared
-//   rows, RSO slots for the element's own c rows).  Processing column j means: the owner lane finalises
-//   w_j = k_j / L_jj and broadcasts it (T warp shuffles); every lane updates its rows i > j with
-//   k_i -= L[i][j] w_j.  Reads of one column are contiguous over rows (coalesced), there is no cross-lane
-//   reduction and no shared-memory scratch, and every load address is known up front, so the loads of
-//   later columns are issued while the shuffle/FMA chain of earlier columns is still running.
+// One WARP owns one batch element (sample s, output j) at a time and loops over samples (persistent CTAs:
+// blockIdx.y = output j, so the warps of a CTA share L_oo, the observed real inputs and beta_o in shared
+// memory).  The step is a forward substitution  w = L^{-1} k(X, x*)  against the bordered factor
+// [[L_oo, 0], [V, L_hh]], done LEFT-LOOKING over SUB-PANELS of 8 rows (layout: gpmpc_state.cuh):
 //
-//   A  kernel vector k(x*, X): each lane evaluates the entries of the rows it owns (one exp per row)
-//   B  shared columns j < m against L_oo (shared memory), final w_j also parked in shared memory
-//   V  the element's own rows against the shared columns   } the element's factor columns stream from HBM
-//   T  the element's own triangular block (c shuffles)      } through a per-warp ring of TMA bulk copies
-//      (cp.async.bulk + mbarrier complete_tx, STEP_P stages of STEP_G columns): one elected lane issues
-//      one copy per column, STEP_P-1 stages ahead of the stage being consumed
-//   D  Sigma* = K** - sum_i w_i w_i^T and mean = sum_i w_i beta_i from registers + warp-shuffle all-reduce
+//   A  kernel vector k(X, x*): lanes over training scalars, T right-hand sides each, written to the per-warp
+//      shared array wv[storage column][T]  (in place: wv holds k first, w = L^{-1} k afterwards)
+//   B  the m shared rows against L_oo (shared memory, sub-panel layout)
+//   C  the element's own c rows, streamed from HBM exactly once:  the element's factor is one contiguous
+//      stream of sub-panels, cut into chunks of STEP_SEG column groups (2 KB) that one elected lane pulls into
+//      a per-warp ring of STEP_NST shared-memory slots with TMA bulk copies (cp.async.bulk + mbarrier
+//      complete_tx).  The ring runs STEP_NST-1 chunks ahead of the consumer and ACROSS elements: while an
+//      element's epilogue runs, the first chunks of the warp's next element are already in flight.
+//      Per sub-panel, lane (i, g) = (lane & 7, lane >> 3) owns row i and every 4th column:
+//        off-diagonal columns: 4 columns per iteration, acc_r += L[i][t] * w[t][r]  (one conflict-free 256-byte
+//        shared load of L per warp and iteration, w broadcast per lane group), then a transpose-reduce over the
+//        4 lane groups (3 shuffles) leaves lane (i, g) with row i's total for task g;
+//        8 x 8 diagonal block: column sweep with one shuffle per column, lane group g solving task g.
+//   D  Sigma* = K** - sum_t w_t w_t^T and mean = sum_t w_t beta_t from wv, warp-shuffle all-reduce
 //   E  T x T Cholesky with GPyTorch's jitter ladder, y = mean + L eps, zero-variance / truncation
-//   F  rank-T append: w_i goes to column i of the T new rows (T contiguous doubles per column)
+//   F  rank-T append: w goes to the T new rows' column groups (T contiguous doubles per column group)
 //
-// HBM traffic per element-step = its own factor entries read once + T new rows written once + O(T) I/O:
-// HBM-bound by design (DESIGN.md "Roofline"); the host counts the algorithmic bytes per launch.
+// HBM traffic per element-step = its own factor read once (8-row granularity) + T new rows written once + O(c)
+// inputs: HBM-bound by design (DESIGN.md "Roofline"); the host counts the algorithmic bytes per launch.
 #pragma once
 #include "gpmpc_state.cuh"
 
 #define STEP_WARPS 4
 #define FULL_MASK 0xffffffffu
-#define STEP_G 2  // factor columns per TMA stage
-#define STEP_P 4  // stages in the per-warp ring (STEP_P - 1 stages in flight while one is consumed)
+#define STEP_SEG 32  // 8-row column groups per TMA chunk / ring slot (32 * 64 B = 2 KB); multiple of 8
+#define STEP_NST 4   // ring slots per warp (power of 2): one being consumed, three in flight
 
 // ---- TMA bulk copy + mbarrier (one ring per warp; the warp is its own producer and consumer) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,367 +112,375 @@ __device__ __forceinline__ void kernel_row(const double* __restrict__ xa, int ta
   }
 }
 
-template <int D, int T, int RSR, int RSO>
+// T right-hand-side values of one storage column from wv (row stride TP doubles, 16-byte aligned when TP is even)
+template <int T>
+__device__ __forceinline__ void load_w(const double* __restrict__ p, double (&w)[T]) {
+  if constexpr (T == 1) {
+    w[0] = p[0];
+  } else {
+#pragma unroll
+    for (int r = 0; r + 1 < T; r += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(p + r);
+      w[r] = v.x;
+      w[r + 1] = v.y;
+    }
+    if constexpr (T & 1) w[T - 1] = p[T - 1];
+  }
+}
+
+// acc_r += sum over this lane's columns of L[i][t] * w[t][r]: `n4` iterations of 4 storage columns whose
+// column groups lie contiguously at `lbase` (lane pointer already offset by g*8 + i), w at `wbase` (offset g*TP)
+template <int T, int TP>
+__device__ __forceinline__ void accumulate(double (&acc)[T], const double* __restrict__ lbase,
+                                           const double* __restrict__ wbase, int n4) {
+#pragma unroll 4
+  for (int it = 0; it < n4; ++it) {
+    const double l = lbase[it * 32];
+    double w[T];
+    load_w<T>(wbase + it * 4 * TP, w);
+#pragma unroll
+    for (int r = 0; r < T; ++r) acc[r] = fma(l, w[r], acc[r]);
+  }
+}
+
+// lane (i, g) ends with the sum over the 4 lane groups of task 4*tg + g (tasks >= T read as 0)
+template <int T, int TG>
+__device__ __forceinline__ void transpose_reduce(const double (&acc)[T], int g, double (&tot)[TG]) {
+  const bool hi = g & 2, odd = g & 1;
+#pragma unroll
+  for (int tg = 0; tg < TG; ++tg) {
+    const double a0 = acc[4 * tg];
+    const double a1 = 4 * tg + 1 < T ? acc[4 * tg + 1 < T ? 4 * tg + 1 : 0] : 0.0;
+    const double a2 = 4 * tg + 2 < T ? acc[4 * tg + 2 < T ? 4 * tg + 2 : 0] : 0.0;
+    const double a3 = 4 * tg + 3 < T ? acc[4 * tg + 3 < T ? 4 * tg + 3 : 0] : 0.0;
+    double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
+    k0 += __shfl_xor_sync(FULL_MASK, hi ? a0 : a2, 16);
+    if (4 * tg + 1 < T) k1 += __shfl_xor_sync(FULL_MASK, hi ? a1 : a3, 16);
+    const double k = (odd ? k1 : k0) + __shfl_xor_sync(FULL_MASK, odd ? k0 : k1, 8);
+    tot[tg] = k;
+  }
+}
+
+// 8 x 8 diagonal block of a sub-panel: rows n_off .. n_off+7 of wv hold the kernel entries, `tot` the
+// off-diagonal dot products; on return wv holds w for the `nvalid` valid rows.  dblk = column group of the
+// block's first column (8 groups contiguous).  Lane (i, g) solves row i for task(s) g (+4).
+template <int T, int TP, int TG>
+__device__ __forceinline__ void diag_solve(const double* __restrict__ dblk, double* __restrict__ wv_blk, int nvalid,
+                                           const double (&tot)[TG], int lane) {
+  const int i = lane & 7, g = lane >> 3;
+  double rhs[TG], mine[TG], dcol[8];
+#pragma unroll
+  for (int tg = 0; tg < TG; ++tg) {
+    const int r = 4 * tg + g;
+    rhs[tg] = (r < T ? wv_blk[i * TP + (r < T ? r : 0)] : 0.0) - tot[tg];
+    mine[tg] = 0.0;
+  }
+#pragma unroll
+  for (int jl = 0; jl < 8; ++jl) dcol[jl] = dblk[jl * 8 + i];
+  const double rd = dblk[i * 8 + i];
+#pragma unroll
+  for (int jl = 0; jl < 8; ++jl) {
+    if (jl < nvalid) {
+#pragma unroll
+      for (int tg = 0; tg < TG; ++tg) {
+        const double wj = __shfl_sync(FULL_MASK, rhs[tg] * rd, (lane & 24) | jl);
+        if (i == jl) mine[tg] = wj;
+        if (i > jl) rhs[tg] = fma(-dcol[jl], wj, rhs[tg]);
+      }
+    }
+  }
+#pragma unroll
+  for (int tg = 0; tg < TG; ++tg) {
+    const int r = 4 * tg + g;
+    if (r < T && i < nvalid) wv_blk[i * TP + r] = mine[tg];
+  }
+  __syncwarp();
+}
+
+template <int D, int T>
 __global__ void __launch_bounds__(STEP_WARPS * 32)
 k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-       int* __restrict__ jitter_level, int grow_factor, int loo_in_smem, int cs) {
-  extern __shared__ __align__(16) double smem[];
+       int* __restrict__ jitter_level, int grow_factor, int loo_in_smem) {
+  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
+  constexpr int TG = (T + 3) / 4;
+  extern __shared__ __align__(128) double smem[];
   const int j_out = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s_idx = blockIdx.x * STEP_WARPS + warp;
-  const int m = st.m, c = st.c;
-  const size_t tri = (size_t)m * (m + 1) / 2;
-  const size_t tri_pad = (tri + 1) & ~(size_t)1;
-  const int m_pad = (m + 1) & ~1;
+  const int li = lane & 7, lg = lane >> 3;
+  const int m = st.m, mo = st.mo, c = st.c;
+  const int Pm = (m + 7) >> 3, P8 = (c + 7) >> 3;
+  const int loop_sz = (int)subpanel_off(Pm, 0);
+  const int m_even = (m + 1) & ~1;
 
-  // ---- CTA-shared tables ---------------------------------------------------------------------------
-  double* sLT = smem;                                  // [tri_pad] (only if loo_in_smem); diagonal = 1/L_jj
-  double* sXo = sLT + (loo_in_smem ? tri_pad : 0);     // [m_pad*D] input of observed real scalar i
-  double* sBo = sXo + (size_t)m_pad * D;               // [m_pad]
-  int* sTo = (int*)(sBo + m_pad);                      // [2*m_pad] ints: task of observed real scalar i
-  double* wo_base = (double*)(sTo + 2 * m_pad);        // per warp: final w of the shared rows, [T][m_pad]
-  double* ring_base = wo_base + (size_t)STEP_WARPS * T * m_pad;  // per warp: [STEP_P][STEP_G][cs]
-  uint64_t* bar_base = (uint64_t*)(ring_base + (size_t)STEP_WARPS * STEP_P * STEP_G * cs);  // [warps][STEP_P]
-  if (threadIdx.x < STEP_WARPS * STEP_P) mbar_init(bar_base + threadIdx.x, 1);
+  // ---- shared-memory carve-up ------------------------------------------------------------------------
+  double* sL = smem;                                         // [loop_sz] L_oo sub-panels (only if loo_in_smem)
+  double* sXo = sL + (loo_in_smem ? loop_sz : 0);            // [m_even*D] input of observed real scalar i
+  double* sBo = sXo + (size_t)m_even * D;                    // [m_even]
+  int* sTo = (int*)(sBo + m_even);                           // [2*m_even] ints: task of observed real scalar i
+  const int wv_rows = mo + 8 * P8;
+  const int wv_sz = ((wv_rows * TP + 15) & ~15);             // per warp, doubles (keeps the ring 128-byte aligned)
+  double* warp_base = (double*)(sTo + 2 * m_even);
+  warp_base = (double*)(((uintptr_t)warp_base + 127) & ~(uintptr_t)127);
+  double* wv = warp_base + (size_t)warp * (wv_sz + STEP_NST * STEP_SEG * 8);
+  double* ring = wv + wv_sz;                                 // [STEP_NST][STEP_SEG*8]
+  uint64_t* bars = (uint64_t*)(warp_base + (size_t)STEP_WARPS * (wv_sz + STEP_NST * STEP_SEG * 8)) + warp * STEP_NST;
+
+  if (threadIdx.x < STEP_WARPS * STEP_NST) mbar_init(bars - warp * STEP_NST + threadIdx.x, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  const double* gLT = st.LooT + (size_t)j_out * tri;
+  const double* gL = st.LooP + (size_t)j_out * loop_sz;
   if (loo_in_smem)
-    for (size_t i = threadIdx.x; i < tri; i += blockDim.x) sLT[i] = gLT[i];
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const double* xp = st.Xr + (size_t)st.obs_pt[i] * D;
+    for (int idx = threadIdx.x; idx < loop_sz; idx += blockDim.x) sL[idx] = gL[idx];
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
+    const double* xp = st.Xr + (size_t)st.obs_pt[idx] * D;
 #pragma unroll
-    for (int a = 0; a < D; ++a) sXo[i * D + a] = xp[a];
-    sBo[i] = st.beta_o[(size_t)j_out * m + i];
-    sTo[i] = st.obs_task[i];
+    for (int a = 0; a < D; ++a) sXo[idx * D + a] = xp[a];
+    sBo[idx] = st.beta_o[(size_t)j_out * m + idx];
+    sTo[idx] = st.obs_task[idx];
   }
+  for (int idx = lane; idx < wv_rows * TP; idx += 32) wv[idx] = 0.0;  // padding rows [m, mo) stay 0 for good
   __syncthreads();
-  if (s_idx >= st.ns) return;  // no block-level sync below this line
-  const double* LT = loo_in_smem ? sLT : gLT;
-  const int b = s_idx * st.g_ny + j_out;
-  double* wo = wo_base + (size_t)warp * T * m_pad;
-  double* ring = ring_base + (size_t)warp * STEP_P * STEP_G * cs;
-  uint64_t* bars = bar_base + warp * STEP_P;
-  const size_t ldC = st.ldC;
-  double* LhTb = st.LhT + (size_t)b * (m + st.c_cap) * ldC;
+  // no block-level synchronisation below this line: every warp runs its own element loop
 
-  double il[D], xs[D];
+  const double* Lp = loo_in_smem ? sL : gL;
+  const int nwarps_total = gridDim.x * STEP_WARPS;
+  const int s_first = blockIdx.x * STEP_WARPS + warp;
+  double il[D];
 #pragma unroll
-  for (int a = 0; a < D; ++a) {
-    il[a] = 1.0 / st.ls[j_out * D + a];
-    xs[a] = x[(size_t)b * D + a];
-  }
+  for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
   const double os = st.os[j_out];
 
-  // ---- A: kernel vector, each lane for the rows it owns ------------------------------------------------
-  double kr[RSR][T], ko[RSO][T], rdl[RSO];
-#pragma unroll
-  for (int rs = 0; rs < RSR; ++rs) {
-    const int i = lane + 32 * rs;
-    if (i < m) {
-      kernel_row<D, T>(sXo + i * D, sTo[i], xs, il, os, kr[rs]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < T; ++r) kr[rs][r] = 0.0;
-    }
-  }
-  const double* rdg = st.rdiag + (size_t)b * st.c_cap;
-#pragma unroll
-  for (int rs = 0; rs < RSO; ++rs) {
-    const int i = lane + 32 * rs;
-    if (i < c) {
-      const double* xa = st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[i]) * D;
-      kernel_row<D, T>(xa, st.hobs_task[i], xs, il, os, ko[rs]);
-      rdl[rs] = rdg[i];
-    } else {
-#pragma unroll
-      for (int r = 0; r < T; ++r) ko[rs][r] = 0.0;
-      rdl[rs] = 0.0;
-    }
-  }
-
-  // ---- B: shared columns against L_oo ------------------------------------------------------------------
-#pragma unroll
-  for (int jb = 0; jb < RSR; ++jb) {
-    const int jend = min(32, m - 32 * jb);
-    for (int jl = 0; jl < jend; ++jl) {
-      const int j = 32 * jb + jl;
-      const double* col = LT + packed_col(j, m);
-      const double rd = col[0];
-      double wj[T];
-#pragma unroll
-      for (int r = 0; r < T; ++r) wj[r] = __shfl_sync(FULL_MASK, kr[jb][r] * rd, jl);
-      if (lane == jl) {
-#pragma unroll
-        for (int r = 0; r < T; ++r) {
-          kr[jb][r] = wj[r];
-          wo[r * m_pad + j] = wj[r];
-        }
+  // ---- producer state (warp-uniform; lane 0 issues): chunks of the own factor in consumption order ----
+  int prod_s = s_first, prod_p8 = 0, prod_ch = 0;
+  unsigned issued = 0, consumed = 0;
+  auto produce = [&]() {  // issues chunks until STEP_NST are outstanding or nothing is left
+    while (issued < consumed + STEP_NST && prod_s < st.ns && P8 > 0) {
+      const int ncols = mo + 8 * prod_p8 + 8;
+      const int g0 = prod_ch * STEP_SEG;
+      const int ng = min(STEP_SEG, ncols - g0);
+      if (lane == 0) {
+        const double* src = st.Lh + (size_t)(prod_s * st.g_ny + j_out) * st.elem_stride +
+                            subpanel_off(prod_p8, mo) + (size_t)g0 * 8;
+        uint64_t* bar = bars + (issued & (STEP_NST - 1));
+        mbar_expect_tx(bar, (uint32_t)ng * 64u);
+        tma_bulk_g2s(ring + (size_t)(issued & (STEP_NST - 1)) * STEP_SEG * 8, src, (uint32_t)ng * 64u, bar);
       }
-#pragma unroll
-      for (int rs = jb; rs < RSR; ++rs) {
-        const int i = lane + 32 * rs;
-        if (i > j && i < m) {
-          const double l = col[i - j];
-#pragma unroll
-          for (int r = 0; r < T; ++r) kr[rs][r] = fma(-l, wj[r], kr[rs][r]);
-        }
+      ++issued;
+      if (g0 + ng >= ncols) {
+        prod_ch = 0;
+        if (++prod_p8 == P8) { prod_p8 = 0; prod_s += nwarps_total; }
+      } else {
+        ++prod_ch;
       }
     }
-  }
-  __syncwarp();
-
-  // ---- V + T: the element's own factor columns, streamed through the TMA ring ------------------------------
-  // group g = STEP_G consecutive columns; groups 0..nV-1 cover the shared columns 0..m-1 (all c own rows),
-  // groups nV.. cover the triangular columns k = 0..c-2 (rows k+1..c-1).  Column copies start at an even row
-  // and have even length so that source, destination and size are 16-byte aligned.
-  const int c_even = (c + 1) & ~1;
-  const int nV = c > 0 ? (m + STEP_G - 1) / STEP_G : 0;
-  const int nT = c > 1 ? (c - 1 + STEP_G - 1) / STEP_G : 0;
-  const int ngroups = nV + nT;
-  auto issue_group = [&](int g) {  // lane 0 only
-    const int sidx = g % STEP_P;
-    double* dst0 = ring + (size_t)sidx * STEP_G * cs;
-    uint32_t total = 0;
-    int col0, ncol, r0[STEP_G];
-    if (g < nV) {
-      col0 = g * STEP_G;
-      ncol = min(STEP_G, m - col0);
-#pragma unroll
-      for (int u = 0; u < STEP_G; ++u) r0[u] = 0;
-    } else {
-      const int k0 = (g - nV) * STEP_G;
-      col0 = m + k0;
-      ncol = min(STEP_G, c - 1 - k0);
-#pragma unroll
-      for (int u = 0; u < STEP_G; ++u) r0[u] = (k0 + u + 1) & ~1;
-    }
-#pragma unroll
-    for (int u = 0; u < STEP_G; ++u)
-      if (u < ncol) total += (uint32_t)(c_even - r0[u]) * 8u;
-    mbar_expect_tx(bars + sidx, total);
-#pragma unroll
-    for (int u = 0; u < STEP_G; ++u)
-      if (u < ncol)
-        tma_bulk_g2s(dst0 + (size_t)u * cs + r0[u], LhTb + (size_t)(col0 + u) * ldC + r0[u],
-                     (uint32_t)(c_even - r0[u]) * 8u, bars + sidx);
   };
-  if (lane == 0)
-    for (int g = 0; g < min(STEP_P - 1, ngroups); ++g) issue_group(g);
+  produce();
 
-  for (int g = 0; g < nV; ++g) {
-    // the stage freed by group g-1 is refilled before this group is consumed
+  for (int s_idx = s_first; s_idx < st.ns; s_idx += nwarps_total) {
+    const int b = s_idx * st.g_ny + j_out;
+    __syncwarp();  // wv is about to be rewritten: every lane is done with the previous element
+    double xs[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) xs[a] = x[(size_t)b * D + a];
+
+    // ---- A: kernel vector ---------------------------------------------------------------------------------
+    for (int i = lane; i < m; i += 32) {
+      double kv[T];
+      kernel_row<D, T>(sXo + i * D, sTo[i], xs, il, os, kv);
+#pragma unroll
+      for (int r = 0; r < T; ++r) wv[i * TP + r] = kv[r];
+    }
+    for (int k = lane; k < c; k += 32) {
+      double kv[T];
+      const double* xa = st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * D;
+      kernel_row<D, T>(xa, st.hobs_task[k], xs, il, os, kv);
+#pragma unroll
+      for (int r = 0; r < T; ++r) wv[(mo + k) * TP + r] = kv[r];
+    }
     __syncwarp();
-    if (lane == 0 && g + STEP_P - 1 < ngroups) issue_group(g + STEP_P - 1);
-    mbar_wait(bars + g % STEP_P, (g / STEP_P) & 1);
-    const double* stg = ring + (size_t)(g % STEP_P) * STEP_G * cs;
+
+    // ---- B: shared rows against L_oo --------------------------------------------------------------------------
+    for (int p8 = 0; p8 < Pm; ++p8) {
+      const int n_off = 8 * p8;
+      const double* base = Lp + subpanel_off(p8, 0);
+      double acc[T], tot[TG];
 #pragma unroll
-    for (int u = 0; u < STEP_G; ++u) {
-      const int j = g * STEP_G + u;
-      if (j < m) {
-        double wj[T];
+      for (int r = 0; r < T; ++r) acc[r] = 0.0;
+      accumulate<T, TP>(acc, base + lg * 8 + li, wv + lg * TP, n_off >> 2);
+      transpose_reduce<T, TG>(acc, lg, tot);
+      diag_solve<T, TP, TG>(base + n_off * 8, wv + n_off * TP, min(8, m - n_off), tot, lane);
+    }
+
+    // ---- C: own rows, streamed through the TMA ring -------------------------------------------------------------
+    for (int p8 = 0; p8 < P8; ++p8) {
+      const int n_off = mo + 8 * p8;
+      const int nch = (n_off + 8 + STEP_SEG - 1) / STEP_SEG;
+      double acc[T], tot[TG];
 #pragma unroll
-        for (int r = 0; r < T; ++r) wj[r] = wo[r * m_pad + j];
-#pragma unroll
-        for (int rs = 0; rs < RSO; ++rs) {
-          const int i = lane + 32 * rs;
-          if (i < c) {
-            const double l = stg[u * cs + i];
-#pragma unroll
-            for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
-          }
+      for (int r = 0; r < T; ++r) acc[r] = 0.0;
+      const double* slot_base = ring;
+      for (int ch = 0; ch < nch; ++ch) {
+        const unsigned slot = consumed & (STEP_NST - 1);
+        mbar_wait(bars + slot, (consumed / STEP_NST) & 1);
+        slot_base = ring + (size_t)slot * STEP_SEG * 8;
+        const int t0 = ch * STEP_SEG;
+        const int t1 = min(t0 + STEP_SEG, n_off);
+        if (t1 > t0) accumulate<T, TP>(acc, slot_base + lg * 8 + li, wv + (t0 + lg) * TP, (t1 - t0) >> 2);
+        if (ch < nch - 1) {  // fully consumed (the diagonal block lives in the last chunk): refill the slot
+          __syncwarp();
+          ++consumed;
+          produce();
         }
       }
+      transpose_reduce<T, TG>(acc, lg, tot);
+      diag_solve<T, TP, TG>(slot_base + (size_t)(n_off - (nch - 1) * STEP_SEG) * 8, wv + n_off * TP,
+                            min(8, c - 8 * p8), tot, lane);
+      ++consumed;
+      produce();
     }
-  }
 
+    // ---- D: posterior moments --------------------------------------------------------------------------------
+    TriT<T> Sacc;
+    double macc[T];
 #pragma unroll
-  for (int jb = 0; jb < RSO; ++jb) {
-    for (int gi = 0; gi < 32 / STEP_G; ++gi) {
-      const int k0 = 32 * jb + STEP_G * gi;
-      if (k0 >= c) break;
-      const int g = nV + k0 / STEP_G;
-      const bool has_data = k0 < c - 1;
-      if (has_data) {
-        __syncwarp();
-        if (lane == 0 && g + STEP_P - 1 < ngroups) issue_group(g + STEP_P - 1);
-        mbar_wait(bars + g % STEP_P, (g / STEP_P) & 1);
-      }
-      const double* stg = ring + (size_t)(g % STEP_P) * STEP_G * cs;
+    for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = 0.0;
 #pragma unroll
-      for (int u = 0; u < STEP_G; ++u) {
-        const int k = k0 + u;
-        if (k < c) {
-          const int jl = STEP_G * gi + u;
-          double wj[T];
-#pragma unroll
-          for (int r = 0; r < T; ++r) wj[r] = __shfl_sync(FULL_MASK, ko[jb][r] * rdl[jb], jl);
-          if (lane == jl) {
-#pragma unroll
-            for (int r = 0; r < T; ++r) ko[jb][r] = wj[r];
-          }
-#pragma unroll
-          for (int rs = jb; rs < RSO; ++rs) {
-            const int i = lane + 32 * rs;
-            if (i > k && i < c) {
-              const double l = stg[u * cs + i];
-#pragma unroll
-              for (int r = 0; r < T; ++r) ko[rs][r] = fma(-l, wj[r], ko[rs][r]);
-            }
-          }
-        }
-      }
-    }
-  }
-
-  // ---- D: posterior moments --------------------------------------------------------------------------------
-  TriT<T> Sacc;
-  double macc[T];
-#pragma unroll
-  for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = 0.0;
-#pragma unroll
-  for (int r = 0; r < T; ++r) macc[r] = 0.0;
-  const double* bh = st.beta_h + (size_t)b * st.c_cap;
-#pragma unroll
-  for (int rs = 0; rs < RSR; ++rs) {
-    const int i = lane + 32 * rs;
-    const double be = i < m ? sBo[i] : 0.0;
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      macc[r] = fma(kr[rs][r], be, macc[r]);
-#pragma unroll
-      for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(kr[rs][r], kr[rs][s], Sacc.at(r, s));
-    }
-  }
-#pragma unroll
-  for (int rs = 0; rs < RSO; ++rs) {
-    const int i = lane + 32 * rs;
-    const double be = i < c ? bh[i] : 0.0;
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      macc[r] = fma(ko[rs][r], be, macc[r]);
-#pragma unroll
-      for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(ko[rs][r], ko[rs][s], Sacc.at(r, s));
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = warp_sum(Sacc.v[i]);
-#pragma unroll
-  for (int r = 0; r < T; ++r) macc[r] = warp_sum(macc[r]);
-  TriT<T> S;
-#pragma unroll
-  for (int r = 0; r < T; ++r)
-#pragma unroll
-    for (int s = 0; s <= r; ++s) {
-      double kss = 0.0;
-      if (r == s) kss = (r == 0) ? os : os * (il[r > 0 ? r - 1 : 0] * il[r > 0 ? r - 1 : 0]);
-      S.at(r, s) = kss - Sacc.at(r, s);
-    }
-  double vr[T];
-#pragma unroll
-  for (int r = 0; r < T; ++r) vr[r] = fmax(S.at(r, r), GP_MIN_VARIANCE);
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      if (mean) mean[(size_t)b * T + r] = macc[r];
-      if (var) var[(size_t)b * T + r] = vr[r];
-    }
-  }
-  if (!eps) return;
-
-  // ---- E: draw ------------------------------------------------------------------------------------
-  TriT<T> Lc;
-  int level = 0;
-  if (T == 1) {
-    Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
-  } else {
-    bool ok = chol_T<T>(S, 0.0, Lc);
-    double jit = st.jitter;
-    while (!ok && level < GP_MAX_TRIES) {
-      ++level;
-      ok = chol_T<T>(S, jit, Lc);
-      jit *= 10.0;
-    }
-    if (!ok) level = 4;
-  }
-  double yv[T];
-#pragma unroll
-  for (int r = 0; r < T; ++r) {
-    double acc = macc[r];
-#pragma unroll
-    for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
-    yv[r] = level < 4 ? acc : nan("");
-  }
-  bool zero = opts.variance_is_zero >= 0.0;
-#pragma unroll
-  for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
-#pragma unroll
-  for (int r = 0; r < T; ++r) {
-    if (zero) yv[r] = macc[r];
-    if (opts.beta >= 0.0) {
-      const double sd = sqrt(vr[r]);
-      yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < T; ++r) y[(size_t)b * T + r] = yv[r];
-    if (jitter_level) jitter_level[b] = level;
-    if (level == 4) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
-  }
-
-  // ---- F: condition on (x*, y) --------------------------------------------------------------------
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < D; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * D + a] = xs[a];
-#pragma unroll
-    for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
-  }
-  if (!grow_factor) return;
-  TriT<T> Sn = S, Ln;
-#pragma unroll
-  for (int r = 0; r < T; ++r) Sn.at(r, r) += st.noise[j_out * T + r];
-  if (!chol_T<T>(Sn, 0.0, Ln)) {
-    if (lane == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
-  }
-  // new rows c .. c+T-1: entry of column i is w_i (T contiguous doubles per column)
-#pragma unroll
-  for (int rs = 0; rs < RSR; ++rs) {
-    const int i = lane + 32 * rs;
-    if (i < m) {
-      double* dst = LhTb + (size_t)i * ldC + c;
-#pragma unroll
-      for (int r = 0; r < T; ++r) dst[r] = kr[rs][r];
-    }
-  }
-#pragma unroll
-  for (int rs = 0; rs < RSO; ++rs) {
-    const int i = lane + 32 * rs;
-    if (i < c) {
-      double* dst = LhTb + (size_t)(m + i) * ldC + c;
-#pragma unroll
-      for (int r = 0; r < T; ++r) dst[r] = ko[rs][r];
-    }
-  }
-  if (lane == 0) {
-    double bn[T];
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      double t = yv[r] - macc[r];
-#pragma unroll
-      for (int s = 0; s < r; ++s) {
-        t -= Ln.at(r, s) * bn[s];
-        LhTb[(size_t)(m + c + s) * ldC + c + r] = Ln.at(r, s);
-      }
-      bn[r] = t / Ln.at(r, r);
-      st.rdiag[(size_t)b * st.c_cap + c + r] = 1.0 / Ln.at(r, r);
-      st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
-    }
-    if (b == 0) {
+    for (int r = 0; r < T; ++r) macc[r] = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      double w[T];
+      load_w<T>(wv + i * TP, w);
+      const double be = sBo[i];
 #pragma unroll
       for (int r = 0; r < T; ++r) {
-        st.hobs_pt[c + r] = st.np;
-        st.hobs_task[c + r] = r;
+        macc[r] = fma(w[r], be, macc[r]);
+#pragma unroll
+        for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(w[r], w[s], Sacc.at(r, s));
+      }
+    }
+    const double* bh = st.beta_h + (size_t)b * st.c_cap;
+    for (int k = lane; k < c; k += 32) {
+      double w[T];
+      load_w<T>(wv + (mo + k) * TP, w);
+      const double be = bh[k];
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        macc[r] = fma(w[r], be, macc[r]);
+#pragma unroll
+        for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(w[r], w[s], Sacc.at(r, s));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = warp_sum(Sacc.v[i]);
+#pragma unroll
+    for (int r = 0; r < T; ++r) macc[r] = warp_sum(macc[r]);
+    TriT<T> S;
+#pragma unroll
+    for (int r = 0; r < T; ++r)
+#pragma unroll
+      for (int s = 0; s <= r; ++s) {
+        double kss = 0.0;
+        if (r == s) kss = (r == 0) ? os : os * (il[r > 0 ? r - 1 : 0] * il[r > 0 ? r - 1 : 0]);
+        S.at(r, s) = kss - Sacc.at(r, s);
+      }
+    double vr[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) vr[r] = fmax(S.at(r, r), GP_MIN_VARIANCE);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        if (mean) mean[(size_t)b * T + r] = macc[r];
+        if (var) var[(size_t)b * T + r] = vr[r];
+      }
+    }
+    if (!eps) continue;
+
+    // ---- E: draw ------------------------------------------------------------------------------------
+    TriT<T> Lc;
+    int level = 0;
+    if (T == 1) {
+      Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
+    } else {
+      bool ok = chol_T<T>(S, 0.0, Lc);
+      double jit = st.jitter;
+      while (!ok && level < GP_MAX_TRIES) {
+        ++level;
+        ok = chol_T<T>(S, jit, Lc);
+        jit *= 10.0;
+      }
+      if (!ok) level = 4;
+    }
+    double yv[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      double acc = macc[r];
+#pragma unroll
+      for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
+      yv[r] = level < 4 ? acc : nan("");
+    }
+    bool zero = opts.variance_is_zero >= 0.0;
+#pragma unroll
+    for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      if (zero) yv[r] = macc[r];
+      if (opts.beta >= 0.0) {
+        const double sd = sqrt(vr[r]);
+        yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < T; ++r) y[(size_t)b * T + r] = yv[r];
+      if (jitter_level) jitter_level[b] = level;
+      if (level == 4) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+    }
+
+    // ---- F: condition on (x*, y) --------------------------------------------------------------------
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * D + a] = xs[a];
+#pragma unroll
+      for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
+    }
+    if (!grow_factor) continue;
+    TriT<T> Sn = S, Ln;
+#pragma unroll
+    for (int r = 0; r < T; ++r) Sn.at(r, r) += st.noise[j_out * T + r];
+    if (!chol_T<T>(Sn, 0.0, Ln)) {
+      if (lane == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
+    }
+    // new rows c .. c+T-1: entry of storage column t is w[t][r]; row c+r lives in sub-panel (c+r)/8
+    double* Le = st.Lh + (size_t)b * st.elem_stride;
+    double* rowp[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) rowp[r] = Le + subpanel_off((c + r) >> 3, mo) + ((c + r) & 7);
+    for (int t = lane; t < mo + c; t += 32) {
+      if (t >= m && t < mo) continue;  // padding columns stay 0
+      double w[T];
+      load_w<T>(wv + t * TP, w);
+#pragma unroll
+      for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = w[r];
+    }
+    if (lane == 0) {
+      double bn[T];
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        double t = yv[r] - macc[r];
+#pragma unroll
+        for (int s = 0; s < r; ++s) {
+          t -= Ln.at(r, s) * bn[s];
+          rowp[r][(size_t)(mo + c + s) * 8] = Ln.at(r, s);
+        }
+        bn[r] = t / Ln.at(r, r);
+        rowp[r][(size_t)(mo + c + r) * 8] = 1.0 / Ln.at(r, r);
+        st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
+      }
+      if (b == 0) {
+#pragma unroll
+        for (int r = 0; r < T; ++r) {
+          st.hobs_pt[c + r] = st.np;
+          st.hobs_task[c + r] = r;
+        }
       }
     }
   }
