@@ -402,26 +402,11 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 
 }  // extern "C"
 
-template <int D, int T>
-static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
-                       const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
-                       cudaStream_t stream, bool* handled) {
-  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
-  const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
-  const size_t loop_sz = subpanel_off(Pm, 0);
-  const size_t m_even = (m + 1) & ~1;
-  const size_t shared_tab = (m_even * D + m_even) * 8 + 2 * m_even * 4 + 128;
-  const size_t wv_sz = ((size_t)(st.mo + 8 * P8) * TP + 15) & ~(size_t)15;
-  const size_t per_warp = (wv_sz + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
-  int loo_in_smem = 1;
-  size_t smem = loop_sz * 8 + shared_tab + STEP_WARPS * per_warp;
-  if (loop_sz * 8 > 40 * 1024) {  // large real-data block: L_oo is read through L1/L2 instead
-    loo_in_smem = 0;
-    smem = shared_tab + STEP_WARPS * per_warp;
-  }
-  *handled = (int)smem <= h->max_dyn_smem;
-  if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over
-  auto kern = k_step<D, T>;
+template <int D, int T, bool LOO_SMEM>
+static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                            const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                            size_t smem, cudaStream_t stream) {
+  auto kern = k_step<D, T, LOO_SMEM>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
@@ -436,10 +421,34 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   const int want = (st.ns + STEP_WARPS - 1) / STEP_WARPS;
   const int resident = std::max(1, h->num_sms * occ / st.g_ny);
   dim3 grid(std::min(want, resident), st.g_ny);
-  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow, loo_in_smem);
+  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
+}
+
+template <int D, int T>
+static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                       const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                       cudaStream_t stream, bool* handled) {
+  // shared-memory budget, mirroring the carve-up at the top of k_step
+  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
+  const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
+  const size_t loop_sz = subpanel_off(Pm, 0);
+  const size_t m_even = (m + 1) & ~1;
+  const size_t shared_tab = (m_even * D + m_even) * 8 + 2 * m_even * 4 + 128;
+  const size_t wv_rows = st.mo + 8 * P8;
+  const size_t wv_sz = (wv_rows * TP + 8 + 15) & ~(size_t)15, wb_sz = (wv_rows + 15) & ~(size_t)15;
+  const size_t per_warp = (wv_sz + wb_sz + 64 + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
+  const size_t smem_with = loop_sz * 8 + shared_tab + STEP_WARPS * per_warp;
+  const size_t smem_without = shared_tab + STEP_WARPS * per_warp;
+  // keep L_oo in shared memory while at least two CTAs still fit per SM; otherwise read it through L1/L2
+  const bool loo_smem = smem_with <= (size_t)h->max_dyn_smem / 2;
+  const size_t smem = loo_smem ? smem_with : smem_without;
+  *handled = smem <= (size_t)h->max_dyn_smem;
+  if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over
+  return loo_smem ? launch_step_impl<D, T, true>(h, st, x, eps, o, mean, var, y, jl, grow, smem, stream)
+                  : launch_step_impl<D, T, false>(h, st, x, eps, o, mean, var, y, jl, grow, smem, stream);
 }
 
 static int dispatch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,

@@ -80,6 +80,21 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
     int i = idx / m, cc = idx % m;
     if (cc <= i) LP[subpanel_off(i >> 3, 0) + (size_t)cc * 8 + (i & 7)] = (cc == i) ? 1.0 / A[idx] : A[idx];
   }
+  __syncthreads();
+  // transposed inverses of the 8 x 8 diagonal blocks in their strictly upper slots (gpmpc_state.cuh)
+  if (tid < 32) {
+    for (int k = 0; k < m; ++k) {
+      const int i = k & 7, kb = k - i;
+      if (tid < i) {
+        const int jj = tid;
+        double acc = 0.0;
+        for (int t = jj; t < i; ++t)
+          acc = fma(A[(size_t)k * m + kb + t], __ldcg(LP + subpanel_off(kb >> 3, 0) + (size_t)(kb + t) * 8 + jj), acc);
+        __stcg(LP + subpanel_off(kb >> 3, 0) + (size_t)k * 8 + jj, -acc / A[(size_t)k * m + k]);
+      }
+      __syncwarp();
+    }
+  }
   // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
   if (tid < 32) {
     const double* y = st.y_obs + (size_t)j * m;
@@ -334,6 +349,8 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
       __syncwarp();
     }
   }
+  __syncthreads();
+  if (tid < 32) warp_update_dinv(st, b, st.c, st.c + qa, tid);
   if (b == 0)
     for (int rr = tid; rr < qa; rr += nt) {
       st.hobs_pt[st.c + rr] = pt_base + sh_act[rr] / T;

@@ -17,7 +17,11 @@
 //   off = mo = roundup8(m) for an element's own rows: storage columns [0, m) are the shared columns, [m, mo)
 //   are zero padding (so that every column range the kernel iterates over in steps of 4 is aligned), and
 //   storage column mo + k is own column k.
-// Inside the 8 x 8 diagonal block only the strictly lower part is meaningful; the diagonal slot holds 1/L_kk.
+// Inside an 8 x 8 diagonal block D the strictly lower slots hold L, the diagonal slots hold 1/L_kk and the strictly
+// UPPER slot (row j, column i), j < i, holds inv(D)[i][j] -- the transposed inverse of the block, maintained by
+// whoever appends rows (warp_update_dinv) -- so that the fused kernel can apply a whole block solve as two FP64
+// tensor-core MMAs (w_blk = inv(D) rhs) instead of an 8-step substitution chain.  Substitution-based readers
+// (gpmpc_block.cuh) use the lower part only.
 __host__ __device__ __forceinline__ size_t subpanel_off(int p, int off) {
   // doubles before sub-panel p:  8 * sum_{q<p} (off + 8q + 8)
   return (size_t)8 * ((size_t)p * (off + 8) + (size_t)4 * p * (p - 1));
@@ -105,6 +109,24 @@ __device__ __forceinline__ double* own_entry(const DevState& st, int b, int k, i
 __device__ __forceinline__ double factor_entry(const DevState& st, int b, int j, int i, int col) {
   if (i < st.m) return st.Loo[((size_t)j * st.m + i) * st.m + col];
   return *own_entry(st, b, i - st.m, col);
+}
+
+// Completes the diagonal blocks of own rows [k0, k1) of element b (already written: L entries and 1/L_kk) with
+// the transposed inverse in the strictly upper slots.  Called by ONE full warp; rows in increasing order:
+//   inv(D)[i][j] = -(1/L_ii) * sum_{t=j}^{i-1} D[i][t] inv(D)[t][j],   j < i (indices within the block)
+__device__ __forceinline__ void warp_update_dinv(const DevState& st, int b, int k0, int k1, int lane) {
+  for (int k = k0; k < k1; ++k) {
+    const int i = k & 7, kb = k - i;
+    if (lane < i) {
+      const int j = lane;
+      const double rd = __ldcg(own_entry(st, b, k, st.m + k));
+      double acc = 0.0;
+      for (int t = j; t < i; ++t)
+        acc = fma(__ldcg(own_entry(st, b, k, st.m + kb + t)), __ldcg(own_entry(st, b, kb + j, st.m + kb + t)), acc);
+      __stcg(own_entry(st, b, kb + j, st.m + k), -rd * acc);
+    }
+    __syncwarp();
+  }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

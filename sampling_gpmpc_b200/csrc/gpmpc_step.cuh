@@ -3,7 +3,10 @@
 // One WARP owns one batch element (sample s, output j) at a time and loops over samples (persistent CTAs:
 // blockIdx.y = output j, so the warps of a CTA share L_oo, the observed real inputs and beta_o in shared
 // memory).  The step is a forward substitution  w = L^{-1} k(X, x*)  against the bordered factor
-// [[L_oo, 0], [V, L_hh]], done LEFT-LOOKING over SUB-PANELS of 8 rows (layout: gpmpc_state.cuh):
+// [[L_oo, 0], [V, L_hh]], done LEFT-LOOKING over SUB-PANELS of 8 rows (layout: gpmpc_state.cuh) on the FP64
+// tensor cores: one mma.sync.m8n8k4.f64 multiplies an 8-row x 4-column tile of L with the 4 x T tile of w
+// (T <= 7 right-hand sides = the N dimension; unused columns are don't-care), so the inner loop is two shared
+// loads and one DMMA per 4 factor columns and needs no cross-lane reduction.
 //
 //   A  kernel vector k(X, x*): lanes over training scalars, T right-hand sides each, written to the per-warp
 //      shared array wv[storage column][T]  (in place: wv holds k first, w = L^{-1} k afterwards)
@@ -13,21 +16,21 @@
 //      a per-warp ring of STEP_NST shared-memory slots with TMA bulk copies (cp.async.bulk + mbarrier
 //      complete_tx).  The ring runs STEP_NST-1 chunks ahead of the consumer and ACROSS elements: while an
 //      element's epilogue runs, the first chunks of the warp's next element are already in flight.
-//      Per sub-panel, lane (i, g) = (lane & 7, lane >> 3) owns row i and every 4th column:
-//        off-diagonal columns: 4 columns per iteration, acc_r += L[i][t] * w[t][r]  (one conflict-free 256-byte
-//        shared load of L per warp and iteration, w broadcast per lane group), then a transpose-reduce over the
-//        4 lane groups (3 shuffles) leaves lane (i, g) with row i's total for task g;
-//        8 x 8 diagonal block: column sweep with one shuffle per column, lane group g solving task g.
-//   D  Sigma* = K** - sum_t w_t w_t^T and mean = sum_t w_t beta_t from wv, warp-shuffle all-reduce
+//      Per sub-panel: dot = L[rows][cols < n_off] w  (DMMA chain, two accumulator sets), rhs = k - dot, then the
+//      8 x 8 diagonal block is applied as w_blk = inv(D) rhs with two more DMMAs (inv(D) is kept transposed in
+//      the block's upper triangle) -- no substitution chain anywhere.
+//   D  W^T [W | beta] with the same DMMA loop: Sigma* = K** - W^T W, mean = W^T beta
 //   E  T x T Cholesky with GPyTorch's jitter ladder, y = mean + L eps, zero-variance / truncation
-//   F  rank-T append: w goes to the T new rows' column groups (T contiguous doubles per column group)
+//   F  rank-T append: w goes to the T new rows' column groups, then the touched diagonal blocks' inverses
 //
 // HBM traffic per element-step = its own factor read once (8-row granularity) + T new rows written once + O(c)
 // inputs: HBM-bound by design (DESIGN.md "Roofline"); the host counts the algorithmic bytes per launch.
 #pragma once
 #include "gpmpc_state.cuh"
 
+#ifndef STEP_WARPS
 #define STEP_WARPS 4
+#endif
 #define FULL_MASK 0xffffffffu
 #define STEP_SEG 32  // 8-row column groups per TMA chunk / ring slot (32 * 64 B = 2 KB); multiple of 8
 #define STEP_NST 4   // ring slots per warp (power of 2): one being consumed, three in flight
@@ -128,108 +131,88 @@ __device__ __forceinline__ void load_w(const double* __restrict__ p, double (&w)
   }
 }
 
-// acc_r += sum over this lane's columns of L[i][t] * w[t][r]: `n4` iterations of 4 storage columns whose
-// column groups lie contiguously at `lbase` (lane pointer already offset by g*8 + i), w at `wbase` (offset g*TP)
+// D(8x8) += A(8x4) B(4x8) in fp64 on the tensor cores.  Fragments (lane = 4*gid + tig): a = A[gid][tig],
+// b = B[tig][gid], c0/c1 = C[gid][2*tig], C[gid][2*tig+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// c += L[8 rows][4*n4 columns] * w[4*n4 columns][.]: column groups contiguous at `lp` (lane pointer already at
+// + tig*8 + gid), w rows at `wp` (lane pointer already at + tig*TP + gid).  n4 is even; two accumulator sets.
+template <int TP>
+__device__ __forceinline__ void mma_accumulate(double (&c)[4], const double* __restrict__ lp,
+                                               const double* __restrict__ wp, int n4) {
+#pragma unroll 2
+  for (int it = 0; it < n4; it += 2) {
+    const double a0 = lp[it * 32], b0 = wp[it * 4 * TP];
+    const double a1 = lp[it * 32 + 32], b1 = wp[it * 4 * TP + 4 * TP];
+    dmma(c[0], c[1], a0, b0);
+    dmma(c[2], c[3], a1, b1);
+  }
+}
+
+// Finishes one sub-panel: rows n_off .. n_off+7 of wv (wv_blk) hold the kernel entries, c the off-diagonal dot
+// products (C layout).  rhs = k - dot goes back to wv, w_blk = inv(D) rhs comes out of two DMMAs and replaces it.
+// Rows >= nvalid (padding / not yet appended) are forced to 0.
 template <int T, int TP>
-__device__ __forceinline__ void accumulate(double (&acc)[T], const double* __restrict__ lbase,
-                                           const double* __restrict__ wbase, int n4) {
-#pragma unroll 4
-  for (int it = 0; it < n4; ++it) {
-    const double l = lbase[it * 32];
-    double w[T];
-    load_w<T>(wbase + it * 4 * TP, w);
-#pragma unroll
-    for (int r = 0; r < T; ++r) acc[r] = fma(l, w[r], acc[r]);
-  }
-}
-
-// lane (i, g) ends with the sum over the 4 lane groups of task 4*tg + g (tasks >= T read as 0)
-template <int T, int TG>
-__device__ __forceinline__ void transpose_reduce(const double (&acc)[T], int g, double (&tot)[TG]) {
-  const bool hi = g & 2, odd = g & 1;
-#pragma unroll
-  for (int tg = 0; tg < TG; ++tg) {
-    const double a0 = acc[4 * tg];
-    const double a1 = 4 * tg + 1 < T ? acc[4 * tg + 1 < T ? 4 * tg + 1 : 0] : 0.0;
-    const double a2 = 4 * tg + 2 < T ? acc[4 * tg + 2 < T ? 4 * tg + 2 : 0] : 0.0;
-    const double a3 = 4 * tg + 3 < T ? acc[4 * tg + 3 < T ? 4 * tg + 3 : 0] : 0.0;
-    double k0 = hi ? a2 : a0, k1 = hi ? a3 : a1;
-    k0 += __shfl_xor_sync(FULL_MASK, hi ? a0 : a2, 16);
-    if (4 * tg + 1 < T) k1 += __shfl_xor_sync(FULL_MASK, hi ? a1 : a3, 16);
-    const double k = (odd ? k1 : k0) + __shfl_xor_sync(FULL_MASK, odd ? k0 : k1, 8);
-    tot[tg] = k;
-  }
-}
-
-// 8 x 8 diagonal block of a sub-panel: rows n_off .. n_off+7 of wv hold the kernel entries, `tot` the
-// off-diagonal dot products; on return wv holds w for the `nvalid` valid rows.  dblk = column group of the
-// block's first column (8 groups contiguous).  Lane (i, g) solves row i for task(s) g (+4).
-template <int T, int TP, int TG>
-__device__ __forceinline__ void diag_solve(const double* __restrict__ dblk, double* __restrict__ wv_blk, int nvalid,
-                                           const double (&tot)[TG], int lane) {
-  const int i = lane & 7, g = lane >> 3;
-  double rhs[TG], mine[TG], dcol[8];
-#pragma unroll
-  for (int tg = 0; tg < TG; ++tg) {
-    const int r = 4 * tg + g;
-    rhs[tg] = (r < T ? wv_blk[i * TP + (r < T ? r : 0)] : 0.0) - tot[tg];
-    mine[tg] = 0.0;
-  }
-#pragma unroll
-  for (int jl = 0; jl < 8; ++jl) dcol[jl] = dblk[jl * 8 + i];
-  const double rd = dblk[i * 8 + i];
-#pragma unroll
-  for (int jl = 0; jl < 8; ++jl) {
-    if (jl < nvalid) {
-#pragma unroll
-      for (int tg = 0; tg < TG; ++tg) {
-        const double wj = __shfl_sync(FULL_MASK, rhs[tg] * rd, (lane & 24) | jl);
-        if (i == jl) mine[tg] = wj;
-        if (i > jl) rhs[tg] = fma(-dcol[jl], wj, rhs[tg]);
-      }
-    }
-  }
-#pragma unroll
-  for (int tg = 0; tg < TG; ++tg) {
-    const int r = 4 * tg + g;
-    if (r < T && i < nvalid) wv_blk[i * TP + r] = mine[tg];
-  }
+__device__ __forceinline__ void subpanel_finish(const double (&c)[4], const double* __restrict__ dblk,
+                                                double* __restrict__ wv_blk, int nvalid, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const bool v0 = 2 * tig < T, v1 = 2 * tig + 1 < T, live = gid < nvalid;
+  double* mine = wv_blk + gid * TP + 2 * tig;
+  if (v0) mine[0] = live ? mine[0] - (c[0] + c[2]) : 0.0;
+  if (v1) mine[1] = live ? mine[1] - (c[1] + c[3]) : 0.0;
+  // inv(D)[gid][k], k = tig and tig + 4: slot (row k, column gid) of the block, zero above the diagonal
+  const double a0 = tig <= gid ? dblk[gid * 8 + tig] : 0.0;
+  const double a1 = tig + 4 <= gid ? dblk[gid * 8 + tig + 4] : 0.0;
+  __syncwarp();
+  const double b0 = wv_blk[tig * TP + gid], b1 = wv_blk[(tig + 4) * TP + gid];
+  double d0 = 0.0, d1 = 0.0;
+  dmma(d0, d1, a0, b0);
+  dmma(d0, d1, a1, b1);
+  __syncwarp();
+  if (v0) mine[0] = live ? d0 : 0.0;
+  if (v1) mine[1] = live ? d1 : 0.0;
   __syncwarp();
 }
 
-template <int D, int T>
+template <int D, int T, bool LOO_SMEM>
 __global__ void __launch_bounds__(STEP_WARPS * 32)
 k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-       int* __restrict__ jitter_level, int grow_factor, int loo_in_smem) {
+       int* __restrict__ jitter_level, int grow_factor) {
   constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
-  constexpr int TG = (T + 3) / 4;
   extern __shared__ __align__(128) double smem[];
   const int j_out = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int li = lane & 7, lg = lane >> 3;
+  const int gid = lane >> 2, tig = lane & 3;
   const int m = st.m, mo = st.mo, c = st.c;
   const int Pm = (m + 7) >> 3, P8 = (c + 7) >> 3;
   const int loop_sz = (int)subpanel_off(Pm, 0);
   const int m_even = (m + 1) & ~1;
 
-  // ---- shared-memory carve-up ------------------------------------------------------------------------
-  double* sL = smem;                                         // [loop_sz] L_oo sub-panels (only if loo_in_smem)
-  double* sXo = sL + (loo_in_smem ? loop_sz : 0);            // [m_even*D] input of observed real scalar i
+  // ---- shared-memory carve-up (sizes mirrored by launch_step in gpmpc_api.cu) -----------------------------
+  double* sL = smem;                                         // [loop_sz] L_oo sub-panels (only if LOO_SMEM)
+  double* sXo = sL + (LOO_SMEM ? loop_sz : 0);               // [m_even*D] input of observed real scalar i
   double* sBo = sXo + (size_t)m_even * D;                    // [m_even]
   int* sTo = (int*)(sBo + m_even);                           // [2*m_even] ints: task of observed real scalar i
   const int wv_rows = mo + 8 * P8;
-  const int wv_sz = ((wv_rows * TP + 15) & ~15);             // per warp, doubles (keeps the ring 128-byte aligned)
+  const int wv_sz = (wv_rows * TP + 8 + 15) & ~15;           // per warp, doubles (+8: don't-care reads of idle lanes)
+  const int wb_sz = (wv_rows + 15) & ~15;
+  const int per_warp = wv_sz + wb_sz + 64 + STEP_NST * STEP_SEG * 8;
   double* warp_base = (double*)(sTo + 2 * m_even);
   warp_base = (double*)(((uintptr_t)warp_base + 127) & ~(uintptr_t)127);
-  double* wv = warp_base + (size_t)warp * (wv_sz + STEP_NST * STEP_SEG * 8);
-  double* ring = wv + wv_sz;                                 // [STEP_NST][STEP_SEG*8]
-  uint64_t* bars = (uint64_t*)(warp_base + (size_t)STEP_WARPS * (wv_sz + STEP_NST * STEP_SEG * 8)) + warp * STEP_NST;
+  double* wv = warp_base + (size_t)warp * per_warp;          // [wv_rows][TP]  k, then w
+  double* wb = wv + wv_sz;                                   // [wv_rows]      beta by storage column
+  double* sc = wb + wb_sz;                                   // [8][8]         W^T [W | beta]
+  double* ring = sc + 64;                                    // [STEP_NST][STEP_SEG*8]
+  uint64_t* bars = (uint64_t*)(warp_base + (size_t)STEP_WARPS * per_warp) + warp * STEP_NST;
 
   if (threadIdx.x < STEP_WARPS * STEP_NST) mbar_init(bars - warp * STEP_NST + threadIdx.x, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   const double* gL = st.LooP + (size_t)j_out * loop_sz;
-  if (loo_in_smem)
+  if (LOO_SMEM)
     for (int idx = threadIdx.x; idx < loop_sz; idx += blockDim.x) sL[idx] = gL[idx];
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
     const double* xp = st.Xr + (size_t)st.obs_pt[idx] * D;
@@ -238,11 +221,14 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
     sBo[idx] = st.beta_o[(size_t)j_out * m + idx];
     sTo[idx] = st.obs_task[idx];
   }
-  for (int idx = lane; idx < wv_rows * TP; idx += 32) wv[idx] = 0.0;  // padding rows [m, mo) stay 0 for good
+  // padding rows [m, mo) and rows >= c of wv / wb are zero for the whole launch
+  for (int idx = lane; idx < wv_sz + wb_sz; idx += 32) wv[idx] = 0.0;
   __syncthreads();
+  for (int idx = lane; idx < m; idx += 32) wb[idx] = sBo[idx];
+  __syncwarp();
   // no block-level synchronisation below this line: every warp runs its own element loop
 
-  const double* Lp = loo_in_smem ? sL : gL;
+  const double* Lp = LOO_SMEM ? sL : gL;
   const int nwarps_total = gridDim.x * STEP_WARPS;
   const int s_first = blockIdx.x * STEP_WARPS + warp;
   double il[D];
@@ -250,27 +236,30 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
   const double os = st.os[j_out];
 
-  // ---- producer state (warp-uniform; lane 0 issues): chunks of the own factor in consumption order ----
-  int prod_s = s_first, prod_p8 = 0, prod_ch = 0;
+  // ---- producer (warp-uniform state; lane 0 issues): the own factors of this warp's elements, in
+  //      consumption order, as one sequence of chunks that never cross a sub-panel boundary --------------------
+  int prod_s = P8 > 0 ? s_first : st.ns;
+  int prod_p8 = 0, prod_left = mo + 8;
+  const double* prod_src = st.Lh + (size_t)(prod_s < st.ns ? prod_s * st.g_ny + j_out : 0) * st.elem_stride;
   unsigned issued = 0, consumed = 0;
-  auto produce = [&]() {  // issues chunks until STEP_NST are outstanding or nothing is left
-    while (issued < consumed + STEP_NST && prod_s < st.ns && P8 > 0) {
-      const int ncols = mo + 8 * prod_p8 + 8;
-      const int g0 = prod_ch * STEP_SEG;
-      const int ng = min(STEP_SEG, ncols - g0);
+  auto produce = [&]() {  // keeps STEP_NST chunks outstanding while anything is left
+    while (issued < consumed + STEP_NST && prod_s < st.ns) {
+      const int ng = min(STEP_SEG, prod_left);
       if (lane == 0) {
-        const double* src = st.Lh + (size_t)(prod_s * st.g_ny + j_out) * st.elem_stride +
-                            subpanel_off(prod_p8, mo) + (size_t)g0 * 8;
-        uint64_t* bar = bars + (issued & (STEP_NST - 1));
-        mbar_expect_tx(bar, (uint32_t)ng * 64u);
-        tma_bulk_g2s(ring + (size_t)(issued & (STEP_NST - 1)) * STEP_SEG * 8, src, (uint32_t)ng * 64u, bar);
+        const unsigned slot = issued & (STEP_NST - 1);
+        mbar_expect_tx(bars + slot, (uint32_t)ng * 64u);
+        tma_bulk_g2s(ring + (size_t)slot * STEP_SEG * 8, prod_src, (uint32_t)ng * 64u, bars + slot);
       }
       ++issued;
-      if (g0 + ng >= ncols) {
-        prod_ch = 0;
-        if (++prod_p8 == P8) { prod_p8 = 0; prod_s += nwarps_total; }
-      } else {
-        ++prod_ch;
+      prod_src += ng * 8;
+      prod_left -= ng;
+      if (prod_left == 0) {
+        if (++prod_p8 == P8) {
+          prod_p8 = 0;
+          prod_s += nwarps_total;
+          if (prod_s < st.ns) prod_src = st.Lh + (size_t)(prod_s * st.g_ny + j_out) * st.elem_stride;
+        }
+        prod_left = mo + 8 * prod_p8 + 8;
       }
     }
   };
@@ -283,19 +272,22 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
     for (int a = 0; a < D; ++a) xs[a] = x[(size_t)b * D + a];
 
-    // ---- A: kernel vector ---------------------------------------------------------------------------------
+    // ---- A: kernel vector (and the element's beta) ----------------------------------------------------------
     for (int i = lane; i < m; i += 32) {
       double kv[T];
       kernel_row<D, T>(sXo + i * D, sTo[i], xs, il, os, kv);
 #pragma unroll
       for (int r = 0; r < T; ++r) wv[i * TP + r] = kv[r];
     }
+    const double* bh = st.beta_h + (size_t)b * st.c_cap;
     for (int k = lane; k < c; k += 32) {
       double kv[T];
       const double* xa = st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * D;
+      const double be = bh[k];
       kernel_row<D, T>(xa, st.hobs_task[k], xs, il, os, kv);
 #pragma unroll
       for (int r = 0; r < T; ++r) wv[(mo + k) * TP + r] = kv[r];
+      wb[mo + k] = be;
     }
     __syncwarp();
 
@@ -303,21 +295,16 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
     for (int p8 = 0; p8 < Pm; ++p8) {
       const int n_off = 8 * p8;
       const double* base = Lp + subpanel_off(p8, 0);
-      double acc[T], tot[TG];
-#pragma unroll
-      for (int r = 0; r < T; ++r) acc[r] = 0.0;
-      accumulate<T, TP>(acc, base + lg * 8 + li, wv + lg * TP, n_off >> 2);
-      transpose_reduce<T, TG>(acc, lg, tot);
-      diag_solve<T, TP, TG>(base + n_off * 8, wv + n_off * TP, min(8, m - n_off), tot, lane);
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      mma_accumulate<TP>(acc, base + tig * 8 + gid, wv + tig * TP + gid, n_off >> 2);
+      subpanel_finish<T, TP>(acc, base + n_off * 8, wv + n_off * TP, min(8, m - n_off), lane);
     }
 
     // ---- C: own rows, streamed through the TMA ring -------------------------------------------------------------
     for (int p8 = 0; p8 < P8; ++p8) {
       const int n_off = mo + 8 * p8;
       const int nch = (n_off + 8 + STEP_SEG - 1) / STEP_SEG;
-      double acc[T], tot[TG];
-#pragma unroll
-      for (int r = 0; r < T; ++r) acc[r] = 0.0;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
       const double* slot_base = ring;
       for (int ch = 0; ch < nch; ++ch) {
         const unsigned slot = consumed & (STEP_NST - 1);
@@ -325,63 +312,47 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
         slot_base = ring + (size_t)slot * STEP_SEG * 8;
         const int t0 = ch * STEP_SEG;
         const int t1 = min(t0 + STEP_SEG, n_off);
-        if (t1 > t0) accumulate<T, TP>(acc, slot_base + lg * 8 + li, wv + (t0 + lg) * TP, (t1 - t0) >> 2);
+        if (t1 > t0) mma_accumulate<TP>(acc, slot_base + tig * 8 + gid, wv + (t0 + tig) * TP + gid, (t1 - t0) >> 2);
         if (ch < nch - 1) {  // fully consumed (the diagonal block lives in the last chunk): refill the slot
           __syncwarp();
           ++consumed;
           produce();
         }
       }
-      transpose_reduce<T, TG>(acc, lg, tot);
-      diag_solve<T, TP, TG>(slot_base + (size_t)(n_off - (nch - 1) * STEP_SEG) * 8, wv + n_off * TP,
-                            min(8, c - 8 * p8), tot, lane);
+      subpanel_finish<T, TP>(acc, slot_base + (size_t)(n_off - (nch - 1) * STEP_SEG) * 8, wv + n_off * TP,
+                             min(8, c - 8 * p8), lane);
       ++consumed;
       produce();
     }
 
-    // ---- D: posterior moments --------------------------------------------------------------------------------
-    TriT<T> Sacc;
+    // ---- D: posterior moments: C[r][s] = sum_t w[t][r] w[t][s],  C[r][7] = sum_t w[t][r] beta[t] ------------------
+    {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      const double* wp = wv + tig * TP + gid;
+      const double* bp = wb + tig;
+      const bool is_beta = gid == 7;
+#pragma unroll 2
+      for (int t = 0; t < wv_rows; t += 8) {
+        const double a0 = wp[t * TP], a1 = wp[(t + 4) * TP];
+        const double e0 = bp[t], e1 = bp[t + 4];
+        dmma(acc[0], acc[1], a0, is_beta ? e0 : a0);
+        dmma(acc[2], acc[3], a1, is_beta ? e1 : a1);
+      }
+      *reinterpret_cast<double2*>(sc + gid * 8 + 2 * tig) = make_double2(acc[0] + acc[2], acc[1] + acc[3]);
+      __syncwarp();
+    }
+    TriT<T> S;
     double macc[T];
 #pragma unroll
-    for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = 0.0;
-#pragma unroll
-    for (int r = 0; r < T; ++r) macc[r] = 0.0;
-    for (int i = lane; i < m; i += 32) {
-      double w[T];
-      load_w<T>(wv + i * TP, w);
-      const double be = sBo[i];
-#pragma unroll
-      for (int r = 0; r < T; ++r) {
-        macc[r] = fma(w[r], be, macc[r]);
-#pragma unroll
-        for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(w[r], w[s], Sacc.at(r, s));
-      }
-    }
-    const double* bh = st.beta_h + (size_t)b * st.c_cap;
-    for (int k = lane; k < c; k += 32) {
-      double w[T];
-      load_w<T>(wv + (mo + k) * TP, w);
-      const double be = bh[k];
-#pragma unroll
-      for (int r = 0; r < T; ++r) {
-        macc[r] = fma(w[r], be, macc[r]);
-#pragma unroll
-        for (int s = 0; s <= r; ++s) Sacc.at(r, s) = fma(w[r], w[s], Sacc.at(r, s));
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < T * (T + 1) / 2; ++i) Sacc.v[i] = warp_sum(Sacc.v[i]);
-#pragma unroll
-    for (int r = 0; r < T; ++r) macc[r] = warp_sum(macc[r]);
-    TriT<T> S;
-#pragma unroll
-    for (int r = 0; r < T; ++r)
+    for (int r = 0; r < T; ++r) {
+      macc[r] = sc[r * 8 + 7];
 #pragma unroll
       for (int s = 0; s <= r; ++s) {
         double kss = 0.0;
         if (r == s) kss = (r == 0) ? os : os * (il[r > 0 ? r - 1 : 0] * il[r > 0 ? r - 1 : 0]);
-        S.at(r, s) = kss - Sacc.at(r, s);
+        S.at(r, s) = kss - sc[r * 8 + s];
       }
+    }
     double vr[T];
 #pragma unroll
     for (int r = 0; r < T; ++r) vr[r] = fmax(S.at(r, r), GP_MIN_VARIANCE);
@@ -483,5 +454,7 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
         }
       }
     }
+    __syncwarp();
+    warp_update_dinv(st, b, c, c + T, lane);
   }
 }
