@@ -68,10 +68,10 @@ static cudaError_t dev_alloc(Tp** p, size_t count) {
 
 static void free_factor_state(gpmpc_handle* h) {
   DevState& st = h->st;
-  cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task);
+  cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task); cudaFree(st.hrow0);
   cudaFree(st.Lh); cudaFree(st.beta_h);
   st.Xh = st.Yh = st.Lh = st.beta_h = nullptr;
-  st.hobs_pt = st.hobs_task = nullptr;
+  st.hobs_pt = st.hobs_task = st.hrow0 = nullptr;
 }
 
 // (re)allocates the per-element state for `cap_points`, keeping what is already stored
@@ -84,7 +84,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
   // depend on the capacity, so growing is a strided copy of the used prefixes
   const long long stride = c_cap ? (long long)subpanel_off((c_cap + 7) / 8, st.mo) : 0;
   double *Xh, *Yh, *Lh, *beta_h;
-  int *hp, *ht;
+  int *hp, *ht, *hr;
   const size_t B = (size_t)st.B;
   const size_t lh_count = c_cap ? B * (size_t)stride : 1;
   CUDA_TRY(h, dev_alloc(&Xh, B * cap_points * st.d));
@@ -93,6 +93,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
   CUDA_TRY(h, dev_alloc(&beta_h, B * c_cap));
   CUDA_TRY(h, dev_alloc(&hp, (size_t)c_cap));
   CUDA_TRY(h, dev_alloc(&ht, (size_t)c_cap));
+  CUDA_TRY(h, dev_alloc(&hr, (size_t)cap_points));
   // padding columns [m, mo) must read as 0; rows not yet appended are never used but kept finite
   CUDA_TRY(h, cudaMemsetAsync(Lh, 0, lh_count * sizeof(double), stream));
   if (old.Xh && old.np > 0) {
@@ -100,6 +101,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
                                   (size_t)old.np * st.d * 8, B, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(h, cudaMemcpy2DAsync(Yh, (size_t)cap_points * st.T * 8, old.Yh, (size_t)old.cap_points * st.T * 8,
                                   (size_t)old.np * st.T * 8, B, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hr, old.hrow0, (size_t)old.np * 4, cudaMemcpyDeviceToDevice, stream));
   }
   if (old.Lh && old.c > 0 && c_cap >= old.c) {
     const size_t used = subpanel_off((old.c + 7) / 8, st.mo) * 8;  // bytes of the sub-panels in use
@@ -114,7 +116,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
     CUDA_TRY(h, cudaStreamSynchronize(stream));
     free_factor_state(h);
   }
-  st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht;
+  st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht; st.hrow0 = hr;
   st.cap_points = cap_points; st.c_cap = c_cap; st.elem_stride = stride;
   h->dims.cap_points = cap_points;
   return GPMPC_OK;
@@ -405,7 +407,7 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 template <int D, int T, bool LOO_SMEM>
 static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                             const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
-                            size_t smem, cudaStream_t stream) {
+                            int warps, size_t smem, cudaStream_t stream) {
   auto kern = k_step<D, T, LOO_SMEM>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -414,14 +416,11 @@ static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x
                                      cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  // persistent CTAs: as many as are co-resident, split over the g_ny outputs; each warp loops over samples
-  int occ = 1;
-  CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, STEP_WARPS * 32, smem));
-  occ = std::max(occ, 1);
-  const int want = (st.ns + STEP_WARPS - 1) / STEP_WARPS;
-  const int resident = std::max(1, h->num_sms * occ / st.g_ny);
+  // persistent CTAs, one per SM, split over the g_ny outputs; each warp loops over samples
+  const int want = (st.ns + warps - 1) / warps;
+  const int resident = std::max(1, h->num_sms / st.g_ny);
   dim3 grid(std::min(want, resident), st.g_ny);
-  kern<<<grid, STEP_WARPS * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
+  kern<<<grid, warps * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
@@ -432,23 +431,27 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
                        const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                        cudaStream_t stream, bool* handled) {
   // shared-memory budget, mirroring the carve-up at the top of k_step
-  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
   const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
   const size_t loop_sz = subpanel_off(Pm, 0);
   const size_t m_even = (m + 1) & ~1;
-  const size_t shared_tab = (m_even * D + m_even) * 8 + 2 * m_even * 4 + 128;
+  const size_t nr_even = (st.n_real + 1) & ~1;
+  const size_t shared_tab = (nr_even * D + m_even) * 8 + (size_t)(((st.n_real * T + 1) & ~1) + ((st.np + 1) & ~1)) * 4 + 128;
   const size_t wv_rows = st.mo + 8 * P8;
-  const size_t wv_sz = (wv_rows * TP + 8 + 15) & ~(size_t)15, wb_sz = (wv_rows + 15) & ~(size_t)15;
-  const size_t per_warp = (wv_sz + wb_sz + 64 + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
-  const size_t smem_with = loop_sz * 8 + shared_tab + STEP_WARPS * per_warp;
-  const size_t smem_without = shared_tab + STEP_WARPS * per_warp;
-  // keep L_oo in shared memory while at least two CTAs still fit per SM; otherwise read it through L1/L2
-  const bool loo_smem = smem_with <= (size_t)h->max_dyn_smem / 2;
-  const size_t smem = loo_smem ? smem_with : smem_without;
-  *handled = smem <= (size_t)h->max_dyn_smem;
+  const size_t wv_sz = (wv_rows * T + 8 + 15) & ~(size_t)15, wb_sz = (wv_rows + 15) & ~(size_t)15;
+  const size_t per_warp = (wv_sz + wb_sz + 128 + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
+  const size_t budget = (size_t)h->max_dyn_smem;
+  // L_oo lives in shared memory if at least 8 warps still fit beside it; otherwise it is read through L1/L2
+  bool loo_smem = loop_sz * 8 + shared_tab + 8 * per_warp <= budget;
+  const size_t fixed = shared_tab + (loo_smem ? loop_sz * 8 : 0);
+  *handled = fixed + per_warp <= budget;
   if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over
-  return loo_smem ? launch_step_impl<D, T, true>(h, st, x, eps, o, mean, var, y, jl, grow, smem, stream)
-                  : launch_step_impl<D, T, false>(h, st, x, eps, o, mean, var, y, jl, grow, smem, stream);
+  int warps = (int)std::min<size_t>(STEP_MAX_WARPS, (budget - fixed) / per_warp);
+  // small launches: spread the samples over the SMs rather than filling few CTAs
+  const int per_cta_need = (st.ns * st.g_ny + h->num_sms - 1) / h->num_sms;
+  warps = std::max(1, std::min(warps, std::max(per_cta_need, 1)));
+  const size_t smem = fixed + (size_t)warps * per_warp;
+  return loo_smem ? launch_step_impl<D, T, true>(h, st, x, eps, o, mean, var, y, jl, grow, warps, smem, stream)
+                  : launch_step_impl<D, T, false>(h, st, x, eps, o, mean, var, y, jl, grow, warps, smem, stream);
 }
 
 static int dispatch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,

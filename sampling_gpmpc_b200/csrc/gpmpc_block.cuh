@@ -282,7 +282,17 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   __shared__ int sh_act[512];  // active test scalars (q' <= 512 checked by the host)
   __shared__ int sh_qa;
 
-  // record the points (labels keep their NaNs)
+  // record the points (labels keep their NaNs); a point's T factor rows are consecutive
+  if (b == 0)
+    for (int h = tid; h < H; h += nt) {
+      int row = -1;
+      if (grow_factor && (!active || active[h])) {
+        int before = 0;
+        for (int hh = 0; hh < h; ++hh) before += (!active || active[hh]) ? 1 : 0;
+        row = st.c + before * T;
+      }
+      st.hrow0[pt_base + h] = row;
+    }
   for (int idx = tid; idx < H * d; idx += nt)
     st.Xh[((size_t)b * st.cap_points + pt_base) * d + idx] = x[(size_t)b * H * d + idx];
   for (int idx = tid; idx < H * T; idx += nt)

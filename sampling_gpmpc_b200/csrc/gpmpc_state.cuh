@@ -53,6 +53,7 @@ struct DevState {
   double* Yh;           // [B][cap_points][T]  labels as appended (NaN kept, for export)
   int* hobs_pt;         // [c_cap] hallucinated point of factor row k   (uniform over b)
   int* hobs_task;       // [c_cap] its task
+  int* hrow0;           // [cap_points] first factor row of hallucinated point p (its T tasks are consecutive), -1 if not in the factor
   double* Lh;           // [B][elem_stride] own rows L[m+k][0 .. m+k] in sub-panel layout (off = mo)
   double* beta_h;       // [B][c_cap]
   unsigned* status;     // device status word (GPMPC_ST_*)

@@ -12,9 +12,9 @@
 //      shared array wv[storage column][T]  (in place: wv holds k first, w = L^{-1} k afterwards)
 //   B  the m shared rows against L_oo (shared memory, sub-panel layout)
 //   C  the element's own c rows, streamed from HBM exactly once:  the element's factor is one contiguous
-//      stream of sub-panels, cut into chunks of STEP_SEG column groups (2 KB) that one elected lane pulls into
-//      a per-warp ring of STEP_NST shared-memory slots with TMA bulk copies (cp.async.bulk + mbarrier
-//      complete_tx).  The ring runs STEP_NST-1 chunks ahead of the consumer and ACROSS elements: while an
+//      stream of sub-panels, cut into fixed chunks of STEP_SEG column groups (4 KB, sub-panel boundaries are
+//      ignored) that one elected lane pulls into a per-warp ring of STEP_NST shared-memory slots with TMA bulk
+//      copies (cp.async.bulk + mbarrier complete_tx).  The ring runs STEP_NST-1 chunks ahead of the consumer and ACROSS elements: while an
 //      element's epilogue runs, the first chunks of the warp's next element are already in flight.
 //      Per sub-panel: dot = L[rows][cols < n_off] w  (DMMA chain, two accumulator sets), rhs = k - dot, then the
 //      8 x 8 diagonal block is applied as w_blk = inv(D) rhs with two more DMMAs (inv(D) is kept transposed in
@@ -28,12 +28,15 @@
 #pragma once
 #include "gpmpc_state.cuh"
 
-#ifndef STEP_WARPS
-#define STEP_WARPS 4
-#endif
+#define STEP_MAX_WARPS 16  // warps per CTA are chosen per launch (shared-memory budget), one CTA per SM
 #define FULL_MASK 0xffffffffu
-#define STEP_SEG 32  // 8-row column groups per TMA chunk / ring slot (32 * 64 B = 2 KB); multiple of 8
-#define STEP_NST 4   // ring slots per warp (power of 2): one being consumed, three in flight
+#ifndef STEP_SEG
+#define STEP_SEG 64  // 8-row column groups per TMA chunk / ring slot (64 * 64 B = 4 KB); multiple of 8
+#endif
+#ifndef STEP_NST
+#define STEP_NST 2   // ring slots per warp: one being consumed, the other in flight
+#endif
+#define STEP_SLOT_BYTES (STEP_SEG * 64)
 
 // ---- TMA bulk copy + mbarrier (one ring per warp; the warp is its own producer and consumer) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,6 +58,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
 template <int T>
@@ -115,20 +128,45 @@ __device__ __forceinline__ void kernel_row(const double* __restrict__ xa, int ta
   }
 }
 
-// T right-hand-side values of one storage column from wv (row stride TP doubles, 16-byte aligned when TP is even)
-template <int T>
-__device__ __forceinline__ void load_w(const double* __restrict__ p, double (&w)[T]) {
-  if constexpr (T == 1) {
-    w[0] = p[0];
-  } else {
+// the T x T block cov( task ta at xa , task tb at xs ), one exp per point
+template <int D, int T>
+__device__ __forceinline__ void kernel_block(const double (&xa)[D], const double (&xs)[D], const double (&il)[D],
+                                             double os, double (&out)[T][T]) {
+  double g[D], sq = 0.0;
 #pragma unroll
-    for (int r = 0; r + 1 < T; r += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(p + r);
-      w[r] = v.x;
-      w[r + 1] = v.y;
-    }
-    if constexpr (T & 1) w[T - 1] = p[T - 1];
+  for (int a = 0; a < D; ++a) {
+    const double t = (xa[a] - xs[a]) * il[a];
+    sq = fma(t, t, sq);
+    g[a] = t * il[a];  // r_a / l_a^2
   }
+  const double k0 = os * exp(-0.5 * sq);
+  out[0][0] = k0;
+  if constexpr (T > 1) {
+#pragma unroll
+    for (int tb = 1; tb < T; ++tb) {
+      out[0][tb] = k0 * g[tb - 1];
+      out[tb][0] = -out[0][tb];
+    }
+#pragma unroll
+    for (int ta = 1; ta < T; ++ta)
+#pragma unroll
+      for (int tb = 1; tb < T; ++tb) {
+        double h = -g[ta - 1] * g[tb - 1];
+        if (ta == tb) h += il[ta - 1] * il[ta - 1];
+        out[ta][tb] = k0 * h;
+      }
+  }
+}
+
+// ---- explicit shared-space accesses (32-bit addresses, immediate offsets) for the hot loops -----------------
+template <int OFF = 0>
+__device__ __forceinline__ double lds(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
 
 // D(8x8) += A(8x4) B(4x8) in fp64 on the tensor cores.  Fragments (lane = 4*gid + tig): a = A[gid][tig],
@@ -138,53 +176,76 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// c += L[8 rows][4*n4 columns] * w[4*n4 columns][.]: column groups contiguous at `lp` (lane pointer already at
-// + tig*8 + gid), w rows at `wp` (lane pointer already at + tig*TP + gid).  n4 is even; two accumulator sets.
-template <int TP>
-__device__ __forceinline__ void mma_accumulate(double (&c)[4], const double* __restrict__ lp,
-                                               const double* __restrict__ wp, int n4) {
-#pragma unroll 2
-  for (int it = 0; it < n4; it += 2) {
-    const double a0 = lp[it * 32], b0 = wp[it * 4 * TP];
-    const double a1 = lp[it * 32 + 32], b1 = wp[it * 4 * TP + 4 * TP];
+// c += L[8 rows][4*n4 columns] * w[4*n4 columns][.]: column groups contiguous from shared address `la` (lane
+// address: + tig*64 + gid*8), w rows from `wa` (lane address: + (tig*T + gid)*8).  n4 is even; two accumulator sets.
+template <int T>
+__device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint32_t wa, int n4) {
+  constexpr int WSTEP = 4 * T * 8;  // bytes of w per 4 columns
+  int it = 0;
+  for (; it + 4 <= n4; it += 4) {
+    const double a0 = lds<0>(la), a1 = lds<256>(la), a2 = lds<512>(la), a3 = lds<768>(la);
+    const double b0 = lds<0>(wa), b1 = lds<WSTEP>(wa), b2 = lds<2 * WSTEP>(wa), b3 = lds<3 * WSTEP>(wa);
+    dmma(c[0], c[1], a0, b0);
+    dmma(c[2], c[3], a1, b1);
+    dmma(c[0], c[1], a2, b2);
+    dmma(c[2], c[3], a3, b3);
+    la += 1024;
+    wa += 4 * WSTEP;
+  }
+  if (it < n4) {
+    const double a0 = lds<0>(la), a1 = lds<256>(la);
+    const double b0 = lds<0>(wa), b1 = lds<WSTEP>(wa);
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
   }
 }
 
-// Finishes one sub-panel: rows n_off .. n_off+7 of wv (wv_blk) hold the kernel entries, c the off-diagonal dot
-// products (C layout).  rhs = k - dot goes back to wv, w_blk = inv(D) rhs comes out of two DMMAs and replaces it.
-// Rows >= nvalid (padding / not yet appended) are forced to 0.
-template <int T, int TP>
-__device__ __forceinline__ void subpanel_finish(const double (&c)[4], const double* __restrict__ dblk,
-                                                double* __restrict__ wv_blk, int nvalid, int lane) {
-  const int gid = lane >> 2, tig = lane & 3;
+// Finishes one sub-panel: rows n_off .. n_off+7 of wv (shared address wblk) hold the kernel entries, c the
+// off-diagonal dot products (C layout).  rhs = k - dot goes back to wv, w_blk = inv(D) rhs comes out of two DMMAs
+// and replaces it.  Rows >= nvalid (padding / not yet appended) are forced to 0.  dblk = shared (or generic, for
+// the L_oo-in-global variant) address of the 8 x 8 diagonal block.
+template <int T, bool DBLK_SHARED>
+__device__ __forceinline__ void subpanel_finish(const double (&c)[4], uint32_t dblk_s, const double* dblk_g,
+                                                uint32_t wblk, int nvalid, int gid, int tig) {
   const bool v0 = 2 * tig < T, v1 = 2 * tig + 1 < T, live = gid < nvalid;
-  double* mine = wv_blk + gid * TP + 2 * tig;
-  if (v0) mine[0] = live ? mine[0] - (c[0] + c[2]) : 0.0;
-  if (v1) mine[1] = live ? mine[1] - (c[1] + c[3]) : 0.0;
+  const uint32_t mine = wblk + (gid * T + 2 * tig) * 8;
+  double r0 = 0.0, r1 = 0.0;
+  if (v0) r0 = lds(mine) - (c[0] + c[2]);
+  if (v1) r1 = lds<8>(mine) - (c[1] + c[3]);
+  if (v0) sts(mine, live ? r0 : 0.0);
+  if (v1) sts(mine + 8, live ? r1 : 0.0);
   // inv(D)[gid][k], k = tig and tig + 4: slot (row k, column gid) of the block, zero above the diagonal
-  const double a0 = tig <= gid ? dblk[gid * 8 + tig] : 0.0;
-  const double a1 = tig + 4 <= gid ? dblk[gid * 8 + tig + 4] : 0.0;
+  double a0 = 0.0, a1 = 0.0;
+  if (DBLK_SHARED) {
+    if (tig <= gid) a0 = lds(dblk_s + (gid * 8 + tig) * 8);
+    if (tig + 4 <= gid) a1 = lds(dblk_s + (gid * 8 + tig + 4) * 8);
+  } else {
+    if (tig <= gid) a0 = dblk_g[gid * 8 + tig];
+    if (tig + 4 <= gid) a1 = dblk_g[gid * 8 + tig + 4];
+  }
   __syncwarp();
-  const double b0 = wv_blk[tig * TP + gid], b1 = wv_blk[(tig + 4) * TP + gid];
+  const double b0 = lds(wblk + (tig * T + gid) * 8), b1 = lds(wblk + ((tig + 4) * T + gid) * 8);
   double d0 = 0.0, d1 = 0.0;
   dmma(d0, d1, a0, b0);
-  dmma(d0, d1, a1, b1);
-  __syncwarp();
-  if (v0) mine[0] = live ? d0 : 0.0;
-  if (v1) mine[1] = live ? d1 : 0.0;
+  dmma(d0, d1, a1, b1);  // mma.sync: every lane's operand loads above have completed
+  if (v0) sts(mine, live ? d0 : 0.0);
+  if (v1) sts(mine + 8, live ? d1 : 0.0);
   __syncwarp();
 }
 
+// host + device: column groups (64 B) in the factor stream of an element with c own rows
+__host__ __device__ __forceinline__ int step_groups_per_element(int c, int mo) {
+  return (int)(subpanel_off((c + 7) / 8, mo) / 8);
+}
+
 template <int D, int T, bool LOO_SMEM>
-__global__ void __launch_bounds__(STEP_WARPS * 32)
+__global__ void __launch_bounds__(STEP_MAX_WARPS * 32, 1)
 k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
        double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
        int* __restrict__ jitter_level, int grow_factor) {
-  constexpr int TP = T == 1 ? 1 : ((T + 1) & ~1);
   extern __shared__ __align__(128) double smem[];
   const int j_out = blockIdx.y;
+  const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int m = st.m, mo = st.mo, c = st.c;
@@ -194,33 +255,35 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 
   // ---- shared-memory carve-up (sizes mirrored by launch_step in gpmpc_api.cu) -----------------------------
   double* sL = smem;                                         // [loop_sz] L_oo sub-panels (only if LOO_SMEM)
-  double* sXo = sL + (LOO_SMEM ? loop_sz : 0);               // [m_even*D] input of observed real scalar i
-  double* sBo = sXo + (size_t)m_even * D;                    // [m_even]
-  int* sTo = (int*)(sBo + m_even);                           // [2*m_even] ints: task of observed real scalar i
+  const int nr_even = (st.n_real + 1) & ~1;
+  double* sXr = sL + (LOO_SMEM ? loop_sz : 0);               // [nr_even*D] real inputs
+  double* sBo = sXr + (size_t)nr_even * D;                   // [m_even]
+  int* sRrow = (int*)(sBo + m_even);                         // [n_real*T] factor row of (real point, task), -1 = unobserved
+  int* sHrow = sRrow + ((st.n_real * T + 1) & ~1);           // [np] first own row of hallucinated point p, -1 = not in the factor
   const int wv_rows = mo + 8 * P8;
-  const int wv_sz = (wv_rows * TP + 8 + 15) & ~15;           // per warp, doubles (+8: don't-care reads of idle lanes)
+  const int wv_sz = (wv_rows * T + 8 + 15) & ~15;            // per warp, doubles (+8: don't-care reads of idle lanes)
   const int wb_sz = (wv_rows + 15) & ~15;
-  const int per_warp = wv_sz + wb_sz + 64 + STEP_NST * STEP_SEG * 8;
-  double* warp_base = (double*)(sTo + 2 * m_even);
+  const int per_warp = wv_sz + wb_sz + 128 + STEP_NST * STEP_SEG * 8;
+  double* warp_base = (double*)(sHrow + ((st.np + 1) & ~1));
   warp_base = (double*)(((uintptr_t)warp_base + 127) & ~(uintptr_t)127);
-  double* wv = warp_base + (size_t)warp * per_warp;          // [wv_rows][TP]  k, then w
-  double* wb = wv + wv_sz;                                   // [wv_rows]      beta by storage column
-  double* sc = wb + wb_sz;                                   // [8][8]         W^T [W | beta]
-  double* ring = sc + 64;                                    // [STEP_NST][STEP_SEG*8]
-  uint64_t* bars = (uint64_t*)(warp_base + (size_t)STEP_WARPS * per_warp) + warp * STEP_NST;
+  double* wv = warp_base + (size_t)warp * per_warp;          // [wv_rows][T]  k, then w
+  double* wb = wv + wv_sz;                                   // [wv_rows]     beta by storage column
+  double* sc = wb + wb_sz;                                   // [8][8]        W^T [W | beta]
+  double* sc2 = sc + 64;                                     // [8][8]        last (partly filled) diagonal block
+  double* ring = sc2 + 64;                                   // [STEP_NST][STEP_SEG*8]
+  uint64_t* bars = (uint64_t*)(warp_base + (size_t)nw * per_warp) + warp * STEP_NST;
 
-  if (threadIdx.x < STEP_WARPS * STEP_NST) mbar_init(bars - warp * STEP_NST + threadIdx.x, 1);
+  if (lane < STEP_NST) mbar_init(bars + lane, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   const double* gL = st.LooP + (size_t)j_out * loop_sz;
   if (LOO_SMEM)
     for (int idx = threadIdx.x; idx < loop_sz; idx += blockDim.x) sL[idx] = gL[idx];
-  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) {
-    const double* xp = st.Xr + (size_t)st.obs_pt[idx] * D;
-#pragma unroll
-    for (int a = 0; a < D; ++a) sXo[idx * D + a] = xp[a];
-    sBo[idx] = st.beta_o[(size_t)j_out * m + idx];
-    sTo[idx] = st.obs_task[idx];
-  }
+  for (int idx = threadIdx.x; idx < st.n_real * D; idx += blockDim.x) sXr[idx] = st.Xr[idx];
+  for (int idx = threadIdx.x; idx < st.n_real * T; idx += blockDim.x) sRrow[idx] = -1;
+  for (int idx = threadIdx.x; idx < st.np; idx += blockDim.x) sHrow[idx] = st.hrow0[idx];
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sBo[idx] = st.beta_o[(size_t)j_out * m + idx];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sRrow[st.obs_pt[idx] * T + st.obs_task[idx]] = idx;
   // padding rows [m, mo) and rows >= c of wv / wb are zero for the whole launch
   for (int idx = lane; idx < wv_sz + wb_sz; idx += 32) wv[idx] = 0.0;
   __syncthreads();
@@ -228,115 +291,208 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   __syncwarp();
   // no block-level synchronisation below this line: every warp runs its own element loop
 
-  const double* Lp = LOO_SMEM ? sL : gL;
-  const int nwarps_total = gridDim.x * STEP_WARPS;
-  const int s_first = blockIdx.x * STEP_WARPS + warp;
+  const uint32_t wv_s = smem_u32(wv), wb_s = smem_u32(wb), ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+  const uint32_t sL_s = smem_u32(sL);
+  const uint32_t a_lane = tig * 64 + gid * 8;        // lane offset into a run of column groups (A fragment)
+  const uint32_t b_lane = (tig * T + gid) * 8;       // lane offset into wv rows (B fragment)
+  const int nwarps_total = gridDim.x * nw;
+  const int s_first = blockIdx.x * nw + warp;
   double il[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
   const double os = st.os[j_out];
+  double noise[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) noise[r] = st.noise[j_out * T + r];
 
-  // ---- producer (warp-uniform state; lane 0 issues): the own factors of this warp's elements, in
-  //      consumption order, as one sequence of chunks that never cross a sub-panel boundary --------------------
-  int prod_s = P8 > 0 ? s_first : st.ns;
-  int prod_p8 = 0, prod_left = mo + 8;
-  const double* prod_src = st.Lh + (size_t)(prod_s < st.ns ? prod_s * st.g_ny + j_out : 0) * st.elem_stride;
-  unsigned issued = 0, consumed = 0;
-  auto produce = [&]() {  // keeps STEP_NST chunks outstanding while anything is left
-    while (issued < consumed + STEP_NST && prod_s < st.ns) {
-      const int ng = min(STEP_SEG, prod_left);
-      if (lane == 0) {
-        const unsigned slot = issued & (STEP_NST - 1);
-        mbar_expect_tx(bars + slot, (uint32_t)ng * 64u);
-        tma_bulk_g2s(ring + (size_t)slot * STEP_SEG * 8, prod_src, (uint32_t)ng * 64u, bars + slot);
-      }
-      ++issued;
-      prod_src += ng * 8;
-      prod_left -= ng;
-      if (prod_left == 0) {
-        if (++prod_p8 == P8) {
-          prod_p8 = 0;
-          prod_s += nwarps_total;
-          if (prod_s < st.ns) prod_src = st.Lh + (size_t)(prod_s * st.g_ny + j_out) * st.elem_stride;
-        }
-        prod_left = mo + 8 * prod_p8 + 8;
-      }
+  // ---- producer (warp-uniform state; lane 0 issues): the factor streams of this warp's elements, one after
+  //      the other, in chunks of STEP_SLOT_BYTES (the last chunk of an element is shorter) ----------------------
+  const unsigned elem_bytes = (unsigned)step_groups_per_element(c, mo) * 64u;
+  const size_t elem_step = (size_t)st.elem_stride * st.g_ny * nwarps_total * 8;  // bytes to this warp's next element
+  const char* prod_base = (const char*)(st.Lh + (size_t)(s_first * st.g_ny + j_out) * st.elem_stride);
+  int prod_left = (elem_bytes > 0 && s_first < st.ns) ? (st.ns - s_first + nwarps_total - 1) / nwarps_total : 0;  // elements
+  unsigned prod_off = 0, prod_slot = 0;
+  auto produce_one = [&]() {
+    if (prod_left == 0) return;
+    const unsigned bytes = min((unsigned)STEP_SLOT_BYTES, elem_bytes - prod_off);
+    const uint32_t bar = bars_s + prod_slot * 8;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, %4, 0;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}"
+        ::"r"(bar), "r"(bytes), "r"(ring_s + prod_slot * STEP_SLOT_BYTES), "l"(prod_base + prod_off), "r"(lane) : "memory");
+    prod_slot = prod_slot + 1 == STEP_NST ? 0 : prod_slot + 1;
+    prod_off += bytes;
+    if (prod_off == elem_bytes) {
+      prod_off = 0;
+      prod_base += elem_step;
+      --prod_left;
     }
   };
-  produce();
+#pragma unroll
+  for (int i = 0; i < STEP_NST; ++i) produce_one();
+  unsigned cons_slot = 0, cons_parity = 0;  // slot / phase parity of the chunk being consumed
+
+  // this element's test input and base samples are loaded one element ahead
+  double xs_n[D], ev_n[T];
+  if (s_first < st.ns) {
+#pragma unroll
+    for (int a = 0; a < D; ++a) xs_n[a] = x[(size_t)(s_first * st.g_ny + j_out) * D + a];
+#pragma unroll
+    for (int r = 0; r < T; ++r) ev_n[r] = eps ? eps[(size_t)(s_first * st.g_ny + j_out) * T + r] : 0.0;
+  }
+  const int np = st.np;
 
   for (int s_idx = s_first; s_idx < st.ns; s_idx += nwarps_total) {
     const int b = s_idx * st.g_ny + j_out;
     __syncwarp();  // wv is about to be rewritten: every lane is done with the previous element
-    double xs[D];
+    double xs[D], ev[T];
 #pragma unroll
-    for (int a = 0; a < D; ++a) xs[a] = x[(size_t)b * D + a];
-
-    // ---- A: kernel vector (and the element's beta) ----------------------------------------------------------
-    for (int i = lane; i < m; i += 32) {
-      double kv[T];
-      kernel_row<D, T>(sXo + i * D, sTo[i], xs, il, os, kv);
+    for (int a = 0; a < D; ++a) xs[a] = xs_n[a];
 #pragma unroll
-      for (int r = 0; r < T; ++r) wv[i * TP + r] = kv[r];
-    }
+    for (int r = 0; r < T; ++r) ev[r] = ev_n[r];
+    const double* Xb = st.Xh + (size_t)b * st.cap_points * D;
     const double* bh = st.beta_h + (size_t)b * st.c_cap;
-    for (int k = lane; k < c; k += 32) {
-      double kv[T];
-      const double* xa = st.Xh + ((size_t)b * st.cap_points + st.hobs_pt[k]) * D;
-      const double be = bh[k];
-      kernel_row<D, T>(xa, st.hobs_task[k], xs, il, os, kv);
+    if (s_idx + nwarps_total < st.ns) {
+      const size_t bn_ = (size_t)(s_idx + nwarps_total) * st.g_ny + j_out;
 #pragma unroll
-      for (int r = 0; r < T; ++r) wv[(mo + k) * TP + r] = kv[r];
-      wb[mo + k] = be;
+      for (int a = 0; a < D; ++a) xs_n[a] = x[bn_ * D + a];
+#pragma unroll
+      for (int r = 0; r < T; ++r) ev_n[r] = eps ? eps[bn_ * T + r] : 0.0;
+      // pull the next element's hallucinated inputs and beta towards L2 while this one is being processed
+      const char* nx = (const char*)(st.Xh + bn_ * st.cap_points * D);
+      const char* nb = (const char*)(st.beta_h + bn_ * st.c_cap);
+      if (lane * 128 < np * D * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + lane * 128));
+      if (lane * 128 < c * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + lane * 128));
+    }
+
+    // ---- A: kernel vector, one exp per training POINT (and the element's beta) ------------------------------
+    // hallucinated points first: their global loads overlap with the real points' arithmetic
+    for (int p0 = 0; p0 < np; p0 += 64) {
+      const int pa = p0 + lane, pb = pa + 32;
+      const int ra = pa < np ? sHrow[pa] : -1, rb = pb < np ? sHrow[pb] : -1;
+      double xa[D], xb[D], ba[T], bb[T];
+      if (ra >= 0) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) xa[a] = Xb[(size_t)pa * D + a];
+#pragma unroll
+        for (int r = 0; r < T; ++r) ba[r] = bh[ra + r];
+      }
+      if (rb >= 0) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) xb[a] = Xb[(size_t)pb * D + a];
+#pragma unroll
+        for (int r = 0; r < T; ++r) bb[r] = bh[rb + r];
+      }
+      if (ra >= 0) {
+        double kb[T][T];
+        kernel_block<D, T>(xa, xs, il, os, kb);
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+          for (int tb = 0; tb < T; ++tb) wv[(mo + ra + ta) * T + tb] = kb[ta][tb];
+          wb[mo + ra + ta] = ba[ta];
+        }
+      }
+      if (rb >= 0) {
+        double kb[T][T];
+        kernel_block<D, T>(xb, xs, il, os, kb);
+#pragma unroll
+        for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+          for (int tb = 0; tb < T; ++tb) wv[(mo + rb + ta) * T + tb] = kb[ta][tb];
+          wb[mo + rb + ta] = bb[ta];
+        }
+      }
+    }
+    for (int p = lane; p < st.n_real; p += 32) {
+      double xa[D], kb[T][T];
+#pragma unroll
+      for (int a = 0; a < D; ++a) xa[a] = sXr[p * D + a];
+      kernel_block<D, T>(xa, xs, il, os, kb);
+#pragma unroll
+      for (int ta = 0; ta < T; ++ta) {
+        const int row = sRrow[p * T + ta];
+        if (row >= 0) {
+#pragma unroll
+          for (int tb = 0; tb < T; ++tb) wv[row * T + tb] = kb[ta][tb];
+        }
+      }
     }
     __syncwarp();
 
     // ---- B: shared rows against L_oo --------------------------------------------------------------------------
     for (int p8 = 0; p8 < Pm; ++p8) {
       const int n_off = 8 * p8;
-      const double* base = Lp + subpanel_off(p8, 0);
+      const uint32_t boff = (uint32_t)subpanel_off(p8, 0) * 8;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      mma_accumulate<TP>(acc, base + tig * 8 + gid, wv + tig * TP + gid, n_off >> 2);
-      subpanel_finish<T, TP>(acc, base + n_off * 8, wv + n_off * TP, min(8, m - n_off), lane);
+      if (LOO_SMEM) {
+        mma_accumulate<T>(acc, sL_s + boff + a_lane, wv_s + b_lane, n_off >> 2);
+      } else {
+        const double* lp = gL + boff / 8 + tig * 8 + gid;
+        for (int it = 0; it < (n_off >> 2); it += 2) {
+          const double a0 = lp[it * 32], a1 = lp[it * 32 + 32];
+          const double b0 = lds(wv_s + b_lane + it * 4 * T * 8), b1 = lds(wv_s + b_lane + (it + 1) * 4 * T * 8);
+          dmma(acc[0], acc[1], a0, b0);
+          dmma(acc[2], acc[3], a1, b1);
+        }
+      }
+      subpanel_finish<T, LOO_SMEM>(acc, sL_s + boff + n_off * 64, gL + boff / 8 + n_off * 8, wv_s + n_off * T * 8,
+                                   min(8, m - n_off), gid, tig);
     }
 
     // ---- C: own rows, streamed through the TMA ring -------------------------------------------------------------
-    for (int p8 = 0; p8 < P8; ++p8) {
-      const int n_off = mo + 8 * p8;
-      const int nch = (n_off + 8 + STEP_SEG - 1) / STEP_SEG;
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* slot_base = ring;
-      for (int ch = 0; ch < nch; ++ch) {
-        const unsigned slot = consumed & (STEP_NST - 1);
-        mbar_wait(bars + slot, (consumed / STEP_NST) & 1);
-        slot_base = ring + (size_t)slot * STEP_SEG * 8;
-        const int t0 = ch * STEP_SEG;
-        const int t1 = min(t0 + STEP_SEG, n_off);
-        if (t1 > t0) mma_accumulate<TP>(acc, slot_base + tig * 8 + gid, wv + (t0 + tig) * TP + gid, (t1 - t0) >> 2);
-        if (ch < nch - 1) {  // fully consumed (the diagonal block lives in the last chunk): refill the slot
-          __syncwarp();
-          ++consumed;
-          produce();
+    if (P8 > 0) {
+      mbar_wait_s(bars_s + cons_slot * 8, cons_parity);
+      unsigned left_in_elem = elem_bytes / 64;  // column groups of this element not yet consumed
+      int cpos = 0;                             // column groups consumed in the current chunk
+      // the current chunk is exhausted: hand its slot back to the producer and wait for the next one
+      auto next_chunk = [&]() {
+        __syncwarp();
+        produce_one();
+        cpos = 0;
+        if (++cons_slot == STEP_NST) { cons_slot = 0; cons_parity ^= 1; }
+        if (left_in_elem > 0) mbar_wait_s(bars_s + cons_slot * 8, cons_parity);
+      };
+      for (int p8 = 0; p8 < P8; ++p8) {
+        const int n_off = mo + 8 * p8;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t wa = wv_s + b_lane;
+        int rem = n_off;
+        while (rem > 0) {
+          const int piece = min(rem, STEP_SEG - cpos);
+          mma_accumulate<T>(acc, ring_s + cons_slot * STEP_SLOT_BYTES + cpos * 64 + a_lane, wa, piece >> 2);
+          wa += piece * T * 8;
+          rem -= piece;
+          cpos += piece;
+          left_in_elem -= piece;
+          if (cpos == STEP_SEG) next_chunk();
         }
+        const uint32_t dblk = ring_s + cons_slot * STEP_SLOT_BYTES + cpos * 64;
+        subpanel_finish<T, true>(acc, dblk, nullptr, wv_s + n_off * T * 8, min(8, c - 8 * p8), gid, tig);
+        if (p8 == P8 - 1 && (c & 7)) {  // the append below extends this block: keep it
+          sc2[lane] = lds(dblk + lane * 8);
+          sc2[lane + 32] = lds(dblk + (lane + 32) * 8);
+        }
+        cpos += 8;
+        left_in_elem -= 8;
+        if (cpos == STEP_SEG || left_in_elem == 0) next_chunk();
       }
-      subpanel_finish<T, TP>(acc, slot_base + (size_t)(n_off - (nch - 1) * STEP_SEG) * 8, wv + n_off * TP,
-                             min(8, c - 8 * p8), lane);
-      ++consumed;
-      produce();
     }
 
     // ---- D: posterior moments: C[r][s] = sum_t w[t][r] w[t][s],  C[r][7] = sum_t w[t][r] beta[t] ------------------
     {
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      const double* wp = wv + tig * TP + gid;
-      const double* bp = wb + tig;
+      uint32_t wa = wv_s + b_lane, ba = wb_s + tig * 8;
       const bool is_beta = gid == 7;
-#pragma unroll 2
       for (int t = 0; t < wv_rows; t += 8) {
-        const double a0 = wp[t * TP], a1 = wp[(t + 4) * TP];
-        const double e0 = bp[t], e1 = bp[t + 4];
+        const double a0 = lds<0>(wa), a1 = lds<4 * T * 8>(wa);
+        const double e0 = lds<0>(ba), e1 = lds<32>(ba);
         dmma(acc[0], acc[1], a0, is_beta ? e0 : a0);
         dmma(acc[2], acc[3], a1, is_beta ? e1 : a1);
+        wa += 8 * T * 8;
+        ba += 64;
       }
       *reinterpret_cast<double2*>(sc + gid * 8 + 2 * tig) = make_double2(acc[0] + acc[2], acc[1] + acc[3]);
       __syncwarp();
@@ -385,7 +541,7 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
     for (int r = 0; r < T; ++r) {
       double acc = macc[r];
 #pragma unroll
-      for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
+      for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * ev[s];
       yv[r] = level < 4 ? acc : nan("");
     }
     bool zero = opts.variance_is_zero >= 0.0;
@@ -413,10 +569,13 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
       for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
     }
-    if (!grow_factor) continue;
+    if (!grow_factor) {
+      if (lane == 0 && b == 0) st.hrow0[np] = -1;
+      continue;
+    }
     TriT<T> Sn = S, Ln;
 #pragma unroll
-    for (int r = 0; r < T; ++r) Sn.at(r, r) += st.noise[j_out * T + r];
+    for (int r = 0; r < T; ++r) Sn.at(r, r) += noise[r];
     if (!chol_T<T>(Sn, 0.0, Ln)) {
       if (lane == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
     }
@@ -428,10 +587,13 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
     for (int t = lane; t < mo + c; t += 32) {
       if (t >= m && t < mo) continue;  // padding columns stay 0
       double w[T];
-      load_w<T>(wv + t * TP, w);
+      for (int r = 0; r < T; ++r) w[r] = wv[t * T + r];
 #pragma unroll
       for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = w[r];
     }
+    double rdn[T];
+#pragma unroll
+    for (int r = 0; r < T; ++r) rdn[r] = 1.0 / Ln.at(r, r);
     if (lane == 0) {
       double bn[T];
 #pragma unroll
@@ -443,18 +605,38 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
           rowp[r][(size_t)(mo + c + s) * 8] = Ln.at(r, s);
         }
         bn[r] = t / Ln.at(r, r);
-        rowp[r][(size_t)(mo + c + r) * 8] = 1.0 / Ln.at(r, r);
+        rowp[r][(size_t)(mo + c + r) * 8] = rdn[r];
         st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
       }
       if (b == 0) {
 #pragma unroll
         for (int r = 0; r < T; ++r) {
-          st.hobs_pt[c + r] = st.np;
+          st.hobs_pt[c + r] = np;
           st.hobs_task[c + r] = r;
         }
+        st.hrow0[np] = c;
       }
     }
-    __syncwarp();
-    warp_update_dinv(st, b, c, c + T, lane);
+    // transposed inverses of the diagonal blocks the new rows belong to (gpmpc_state.cuh), lane j = column j:
+    //   inv(D)[i][j] = -(1/L_ii) sum_{t=j}^{i-1} D[i][t] inv(D)[t][j];  old rows' entries come from sc2 / wv,
+    //   new rows' from Ln and the values just computed
+    {
+      const int jc = lane & 7;
+      double dnew[T];
+#pragma unroll
+      for (int r = 0; r < T; ++r) {
+        const int i = (c + r) & 7, kb = c + r - i;
+        const int tend = min(i, c - kb);  // block rows [0, tend) existed before this step
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < 7; ++t)
+          if (t >= jc && t < tend) acc = fma(wv[(mo + kb + t) * T + r], sc2[t * 8 + jc], acc);
+#pragma unroll
+        for (int s = 0; s < r; ++s)
+          if (c + s >= kb) acc = fma(Ln.at(r, s), dnew[s], acc);
+        dnew[r] = jc == i ? rdn[r] : (jc < i ? -rdn[r] * acc : 0.0);
+        if (lane < 8 && jc < i) Le[subpanel_off(kb >> 3, mo) + (size_t)(mo + kb + i) * 8 + jc] = dnew[r];
+      }
+    }
   }
 }

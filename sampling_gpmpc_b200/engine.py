@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpmpc_b200.so")
+LIB_PATH = os.environ.get("GPMPC_B200_LIB", os.path.join(_HERE, "libgpmpc_b200.so"))  # override: kernel experiments
 
 MAX_D, MAX_T, MAX_NX = 6, 7, 8
 
