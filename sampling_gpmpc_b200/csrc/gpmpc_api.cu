@@ -185,6 +185,11 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
     return fail(nullptr, GPMPC_ERR_CUDA, "cudaMalloc(status) failed");
   }
   st.status = status;
+  if (dev_alloc(&st.fin, (size_t)st.B * (st.T + st.T * (st.T + 1) / 2)) != cudaSuccess) {
+    cudaFree(status);
+    delete h;
+    return fail(nullptr, GPMPC_ERR_CUDA, "cudaMalloc(fin) failed");
+  }
   *out = h;
   return GPMPC_OK;
 }
@@ -195,7 +200,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   free_factor_state(h);
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
-  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status);
+  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -404,6 +409,16 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 
 }  // extern "C"
 
+template <int T>
+static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                              const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
+                              cudaStream_t stream) {
+  k_step_finish<T><<<(st.B + 127) / 128, 128, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
 template <int D, int T, bool LOO_SMEM>
 static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                             const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
@@ -420,10 +435,10 @@ static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x
   const int want = (st.ns + warps - 1) / warps;
   const int resident = std::max(1, h->num_sms / st.g_ny);
   dim3 grid(std::min(want, resident), st.g_ny);
-  kern<<<grid, warps * 32, smem, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
+  kern<<<grid, warps * 32, smem, stream>>>(st, x, grow);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  return GPMPC_OK;
+  return launch_step_finish<T>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
 }
 
 template <int D, int T>

@@ -20,8 +20,9 @@
 //      8 x 8 diagonal block is applied as w_blk = inv(D) rhs with two more DMMAs (inv(D) is kept transposed in
 //      the block's upper triangle) -- no substitution chain anywhere.
 //   D  W^T [W | beta] with the same DMMA loop: Sigma* = K** - W^T W, mean = W^T beta
-//   E  T x T Cholesky with GPyTorch's jitter ladder, y = mean + L eps, zero-variance / truncation
-//   F  rank-T append: w goes to the T new rows' column groups, then the touched diagonal blocks' inverses
+//   F  rank-T append: w goes to the T new rows' column groups
+//   then k_step_finish (one THREAD per element): E  T x T Cholesky with the jitter ladder, draw, post-processing;
+//   the diagonal-block part of the append and the touched blocks' inverses
 //
 // HBM traffic per element-step = its own factor read once (8-row granularity) + T new rows written once + O(c)
 // inputs: HBM-bound by design (DESIGN.md "Roofline"); the host counts the algorithmic bytes per launch.
@@ -240,9 +241,7 @@ __host__ __device__ __forceinline__ int step_groups_per_element(int c, int mo) {
 
 template <int D, int T, bool LOO_SMEM>
 __global__ void __launch_bounds__(STEP_MAX_WARPS * 32, 1)
-k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
-       double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-       int* __restrict__ jitter_level, int grow_factor) {
+k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   extern __shared__ __align__(128) double smem[];
   const int j_out = blockIdx.y;
   const int nw = blockDim.x >> 5;
@@ -301,9 +300,6 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
 #pragma unroll
   for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
   const double os = st.os[j_out];
-  double noise[T];
-#pragma unroll
-  for (int r = 0; r < T; ++r) noise[r] = st.noise[j_out * T + r];
 
   // ---- producer (warp-uniform state; lane 0 issues): the factor streams of this warp's elements, one after
   //      the other, in chunks of STEP_SLOT_BYTES (the last chunk of an element is shorter) ----------------------
@@ -335,31 +331,25 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
   unsigned cons_slot = 0, cons_parity = 0;  // slot / phase parity of the chunk being consumed
 
   // this element's test input and base samples are loaded one element ahead
-  double xs_n[D], ev_n[T];
+  double xs_n[D];
   if (s_first < st.ns) {
 #pragma unroll
     for (int a = 0; a < D; ++a) xs_n[a] = x[(size_t)(s_first * st.g_ny + j_out) * D + a];
-#pragma unroll
-    for (int r = 0; r < T; ++r) ev_n[r] = eps ? eps[(size_t)(s_first * st.g_ny + j_out) * T + r] : 0.0;
   }
   const int np = st.np;
 
   for (int s_idx = s_first; s_idx < st.ns; s_idx += nwarps_total) {
     const int b = s_idx * st.g_ny + j_out;
     __syncwarp();  // wv is about to be rewritten: every lane is done with the previous element
-    double xs[D], ev[T];
+    double xs[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) xs[a] = xs_n[a];
-#pragma unroll
-    for (int r = 0; r < T; ++r) ev[r] = ev_n[r];
     const double* Xb = st.Xh + (size_t)b * st.cap_points * D;
     const double* bh = st.beta_h + (size_t)b * st.c_cap;
     if (s_idx + nwarps_total < st.ns) {
       const size_t bn_ = (size_t)(s_idx + nwarps_total) * st.g_ny + j_out;
 #pragma unroll
       for (int a = 0; a < D; ++a) xs_n[a] = x[bn_ * D + a];
-#pragma unroll
-      for (int r = 0; r < T; ++r) ev_n[r] = eps ? eps[bn_ * T + r] : 0.0;
       // pull the next element's hallucinated inputs and beta towards L2 while this one is being processed
       const char* nx = (const char*)(st.Xh + bn_ * st.cap_points * D);
       const char* nb = (const char*)(st.beta_h + bn_ * st.c_cap);
@@ -471,10 +461,6 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
         }
         const uint32_t dblk = ring_s + cons_slot * STEP_SLOT_BYTES + cpos * 64;
         subpanel_finish<T, true>(acc, dblk, nullptr, wv_s + n_off * T * 8, min(8, c - 8 * p8), gid, tig);
-        if (p8 == P8 - 1 && (c & 7)) {  // the append below extends this block: keep it
-          sc2[lane] = lds(dblk + lane * 8);
-          sc2[lane + 32] = lds(dblk + (lane + 32) * 8);
-        }
         cpos += 8;
         left_in_elem -= 8;
         if (cpos == STEP_SEG || left_in_elem == 0) next_chunk();
@@ -497,146 +483,167 @@ k_step(DevState st, const double* __restrict__ x, const double* __restrict__ eps
       *reinterpret_cast<double2*>(sc + gid * 8 + 2 * tig) = make_double2(acc[0] + acc[2], acc[1] + acc[3]);
       __syncwarp();
     }
-    TriT<T> S;
-    double macc[T];
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      macc[r] = sc[r * 8 + 7];
-#pragma unroll
-      for (int s = 0; s <= r; ++s) {
-        double kss = 0.0;
-        if (r == s) kss = (r == 0) ? os : os * (il[r > 0 ? r - 1 : 0] * il[r > 0 ? r - 1 : 0]);
-        S.at(r, s) = kss - sc[r * 8 + s];
+    // hand [sum_t w_t beta_t | sum_t w_t w_t^T (lower)] to the per-element finishing kernel
+    {
+      constexpr int FS = T + T * (T + 1) / 2;
+      double* fo = st.fin + (size_t)b * FS;
+      for (int q = lane; q < FS; q += 32) {
+        int r = q, s2 = 7;  // q < T: mean_r
+        if (q >= T) {
+          int u = q - T;  // u = r(r+1)/2 + s
+          r = 0;
+          while ((r + 1) * (r + 2) / 2 <= u) ++r;
+          s2 = u - r * (r + 1) / 2;
+        }
+        fo[q] = sc[r * 8 + s2];
       }
     }
-    double vr[T];
-#pragma unroll
-    for (int r = 0; r < T; ++r) vr[r] = fmax(S.at(r, r), GP_MIN_VARIANCE);
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < T; ++r) {
-        if (mean) mean[(size_t)b * T + r] = macc[r];
-        if (var) var[(size_t)b * T + r] = vr[r];
-      }
-    }
-    if (!eps) continue;
-
-    // ---- E: draw ------------------------------------------------------------------------------------
-    TriT<T> Lc;
-    int level = 0;
-    if (T == 1) {
-      Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
-    } else {
-      bool ok = chol_T<T>(S, 0.0, Lc);
-      double jit = st.jitter;
-      while (!ok && level < GP_MAX_TRIES) {
-        ++level;
-        ok = chol_T<T>(S, jit, Lc);
-        jit *= 10.0;
-      }
-      if (!ok) level = 4;
-    }
-    double yv[T];
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      double acc = macc[r];
-#pragma unroll
-      for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * ev[s];
-      yv[r] = level < 4 ? acc : nan("");
-    }
-    bool zero = opts.variance_is_zero >= 0.0;
-#pragma unroll
-    for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
-#pragma unroll
-    for (int r = 0; r < T; ++r) {
-      if (zero) yv[r] = macc[r];
-      if (opts.beta >= 0.0) {
-        const double sd = sqrt(vr[r]);
-        yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
-      }
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < T; ++r) y[(size_t)b * T + r] = yv[r];
-      if (jitter_level) jitter_level[b] = level;
-      if (level == 4) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
-    }
-
-    // ---- F: condition on (x*, y) --------------------------------------------------------------------
-    if (lane == 0) {
-#pragma unroll
-      for (int a = 0; a < D; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * D + a] = xs[a];
-#pragma unroll
-      for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
-    }
-    if (!grow_factor) {
-      if (lane == 0 && b == 0) st.hrow0[np] = -1;
-      continue;
-    }
-    TriT<T> Sn = S, Ln;
-#pragma unroll
-    for (int r = 0; r < T; ++r) Sn.at(r, r) += noise[r];
-    if (!chol_T<T>(Sn, 0.0, Ln)) {
-      if (lane == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
-    }
-    // new rows c .. c+T-1: entry of storage column t is w[t][r]; row c+r lives in sub-panel (c+r)/8
+    if (!grow_factor) continue;
+    // F (first half): the new rows' entries left of their diagonal block are w itself; row c+r lives in sub-panel
+    // (c+r)/8, entry of storage column t at + t*8.  The diagonal-block part depends on the draw: k_step_finish.
     double* Le = st.Lh + (size_t)b * st.elem_stride;
     double* rowp[T];
 #pragma unroll
     for (int r = 0; r < T; ++r) rowp[r] = Le + subpanel_off((c + r) >> 3, mo) + ((c + r) & 7);
     for (int t = lane; t < mo + c; t += 32) {
       if (t >= m && t < mo) continue;  // padding columns stay 0
-      double w[T];
-      for (int r = 0; r < T; ++r) w[r] = wv[t * T + r];
 #pragma unroll
-      for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = w[r];
+      for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = wv[t * T + r];
     }
-    double rdn[T];
+  }
+}
+
+// K1b: per-element scalar tail of the step, ONE THREAD per batch element (the warp kernel above would do this
+// arithmetic 32-fold redundantly): Sigma* = K** - W^T W, T x T Cholesky with GPyTorch's jitter ladder, y = mean +
+// L eps, zero-variance / truncation (src/agent.py:646-708), then the diagonal-block part of the rank-T append:
+// chol(Sigma* + noise), 1/L_kk, beta_new and the transposed block inverses (gpmpc_state.cuh).
+template <int T>
+__global__ void __launch_bounds__(128)
+k_step_finish(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
+              double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
+              int* __restrict__ jitter_level, int grow_factor) {
+  constexpr int FS = T + T * (T + 1) / 2;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= st.B) return;
+  const int j_out = b % st.g_ny, d = st.d, c = st.c, mo = st.mo;
+  const double* fi = st.fin + (size_t)b * FS;
+  const double os = st.os[j_out];
+  double macc[T];
+  TriT<T> S;
 #pragma unroll
-    for (int r = 0; r < T; ++r) rdn[r] = 1.0 / Ln.at(r, r);
-    if (lane == 0) {
-      double bn[T];
+  for (int r = 0; r < T; ++r) macc[r] = fi[r];
 #pragma unroll
-      for (int r = 0; r < T; ++r) {
-        double t = yv[r] - macc[r];
+  for (int r = 0; r < T; ++r)
 #pragma unroll
-        for (int s = 0; s < r; ++s) {
-          t -= Ln.at(r, s) * bn[s];
-          rowp[r][(size_t)(mo + c + s) * 8] = Ln.at(r, s);
-        }
-        bn[r] = t / Ln.at(r, r);
-        rowp[r][(size_t)(mo + c + r) * 8] = rdn[r];
-        st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
+    for (int s = 0; s <= r; ++s) {
+      double kss = 0.0;
+      if (r == s) {
+        if (r == 0) kss = os;
+        else { const double il = 1.0 / st.ls[j_out * d + r - 1]; kss = os * (il * il); }
       }
-      if (b == 0) {
-#pragma unroll
-        for (int r = 0; r < T; ++r) {
-          st.hobs_pt[c + r] = np;
-          st.hobs_task[c + r] = r;
-        }
-        st.hrow0[np] = c;
-      }
+      S.at(r, s) = kss - fi[T + r * (r + 1) / 2 + s];
     }
-    // transposed inverses of the diagonal blocks the new rows belong to (gpmpc_state.cuh), lane j = column j:
-    //   inv(D)[i][j] = -(1/L_ii) sum_{t=j}^{i-1} D[i][t] inv(D)[t][j];  old rows' entries come from sc2 / wv,
-    //   new rows' from Ln and the values just computed
-    {
-      const int jc = lane & 7;
-      double dnew[T];
+  double vr[T];
 #pragma unroll
-      for (int r = 0; r < T; ++r) {
-        const int i = (c + r) & 7, kb = c + r - i;
-        const int tend = min(i, c - kb);  // block rows [0, tend) existed before this step
+  for (int r = 0; r < T; ++r) {
+    vr[r] = fmax(S.at(r, r), GP_MIN_VARIANCE);
+    if (mean) mean[(size_t)b * T + r] = macc[r];
+    if (var) var[(size_t)b * T + r] = vr[r];
+  }
+  if (!eps) return;
+
+  // ---- E: draw ------------------------------------------------------------------------------------
+  TriT<T> Lc;
+  int level = 0;
+  if (T == 1) {
+    Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
+  } else {
+    bool ok = chol_T<T>(S, 0.0, Lc);
+    double jit = st.jitter;
+    while (!ok && level < GP_MAX_TRIES) {
+      ++level;
+      ok = chol_T<T>(S, jit, Lc);
+      jit *= 10.0;
+    }
+    if (!ok) level = 4;
+  }
+  double yv[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    double acc = macc[r];
+#pragma unroll
+    for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
+    yv[r] = level < 4 ? acc : nan("");
+  }
+  bool zero = opts.variance_is_zero >= 0.0;
+#pragma unroll
+  for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    if (zero) yv[r] = macc[r];
+    if (opts.beta >= 0.0) {
+      const double sd = sqrt(vr[r]);
+      yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
+    }
+    y[(size_t)b * T + r] = yv[r];
+  }
+  if (jitter_level) jitter_level[b] = level;
+  if (level == 4) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+
+  // ---- F (second half): condition on (x*, y) --------------------------------------------------------
+  for (int a = 0; a < d; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * d + a] = x[(size_t)b * d + a];
+#pragma unroll
+  for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
+  if (b == 0) st.hrow0[st.np] = grow_factor ? c : -1;
+  if (!grow_factor) return;
+  TriT<T> Sn = S, Ln;
+#pragma unroll
+  for (int r = 0; r < T; ++r) Sn.at(r, r) += st.noise[j_out * T + r];
+  if (!chol_T<T>(Sn, 0.0, Ln)) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
+  double bn[T], rdn[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    double t = yv[r] - macc[r];
+#pragma unroll
+    for (int s = 0; s < r; ++s) t -= Ln.at(r, s) * bn[s];
+    bn[r] = t / Ln.at(r, r);
+    rdn[r] = 1.0 / Ln.at(r, r);
+    st.beta_h[(size_t)b * st.c_cap + c + r] = bn[r];
+  }
+  if (b == 0) {
+#pragma unroll
+    for (int r = 0; r < T; ++r) {
+      st.hobs_pt[c + r] = st.np;
+      st.hobs_task[c + r] = r;
+    }
+  }
+  // diagonal blocks touched by rows c .. c+T-1 (at most two): blk[col][row] mirrors the 8 x 8 block in memory
+  // (lower: L, diagonal: 1/L_kk, upper: transposed inverse); the old rows' part and the new rows' entries under
+  // old columns (written by k_step) are read back, the new rows are completed and their slots written.
+  double* Le = st.Lh + (size_t)b * st.elem_stride;
+  int r0 = 0;
+  while (r0 < T) {
+    const int kb = (c + r0) & ~7;                    // first own row of this block
+    const int i_first = c + r0 - kb;                 // block row of the first new row
+    const int r1 = min(T, r0 + 8 - i_first);         // new rows [r0, r1) fall into this block
+    double* gblk = Le + subpanel_off(kb >> 3, mo) + (size_t)(mo + kb) * 8;
+    double blk[8][8];
+    for (int t = 0; t < i_first; ++t)                // old columns: old rows' slots and the new rows' L entries
+      for (int i = 0; i < i_first + (r1 - r0); ++i) blk[t][i] = gblk[t * 8 + i];
+    for (int r = r0; r < r1; ++r) {
+      const int i = i_first + (r - r0);
+      for (int s = r0; s < r; ++s) blk[i_first + (s - r0)][i] = Ln.v[r * (r + 1) / 2 + s];
+      blk[i][i] = rdn[r];
+      for (int jc = 0; jc < i; ++jc) {
         double acc = 0.0;
-#pragma unroll
-        for (int t = 0; t < 7; ++t)
-          if (t >= jc && t < tend) acc = fma(wv[(mo + kb + t) * T + r], sc2[t * 8 + jc], acc);
-#pragma unroll
-        for (int s = 0; s < r; ++s)
-          if (c + s >= kb) acc = fma(Ln.at(r, s), dnew[s], acc);
-        dnew[r] = jc == i ? rdn[r] : (jc < i ? -rdn[r] * acc : 0.0);
-        if (lane < 8 && jc < i) Le[subpanel_off(kb >> 3, mo) + (size_t)(mo + kb + i) * 8 + jc] = dnew[r];
+        for (int t = jc; t < i; ++t) acc = fma(blk[t][i], blk[t][jc], acc);
+        blk[i][jc] = -rdn[r] * acc;                  // slot (row jc, column i)
       }
+      double* rowi = Le + subpanel_off(kb >> 3, mo) + i;
+      for (int s = 0; s < r0; ++s) rowi[(size_t)(mo + c + s) * 8] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
+      for (int t = i_first; t <= i; ++t) gblk[t * 8 + i] = blk[t][i];   // new columns of row i (incl. 1/L_ii)
+      for (int jc = 0; jc < i; ++jc) gblk[i * 8 + jc] = blk[i][jc];     // transposed inverse row
     }
+    r0 = r1;
   }
 }
