@@ -453,7 +453,7 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   const size_t shared_tab = (nr_even * D + m_even) * 8 + (size_t)(((st.n_real * T + 1) & ~1) + ((st.np + 1) & ~1)) * 4 + 128;
   const size_t wv_rows = st.mo + 8 * P8;
   const size_t wv_sz = (wv_rows * T + 8 + 15) & ~(size_t)15, wb_sz = (wv_rows + 15) & ~(size_t)15;
-  const size_t per_warp = (wv_sz + wb_sz + 128 + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
+  const size_t per_warp = (wv_sz + wb_sz + (size_t)STEP_NST * STEP_SEG * 8) * 8 + STEP_NST * 8;
   const size_t budget = (size_t)h->max_dyn_smem;
   // L_oo lives in shared memory if at least 8 warps still fit beside it; otherwise it is read through L1/L2
   bool loo_smem = loop_sz * 8 + shared_tab + 8 * per_warp <= budget;

@@ -70,31 +70,22 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
     __syncthreads();
   }
   if (level > 0 && tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_JITTER | ((unsigned)level << 8));
-  // sub-panel copy for the fused rollout kernel (gpmpc_state.cuh): diagonal stored as 1/L_jj, rest of the
-  // upper triangle and the padding rows zero
+  // explicit inverse of L_oo in sub-panel layout for the fused rollout kernel (gpmpc_state.cuh): w_o = inv(L_oo) k_o
+  // is then a plain tensor-core product.  cond(L_oo) ~ 1e3 at the reference's configurations: the inverse costs
+  // ~1e-14 relative accuracy in the posterior variance, 5 orders below the parity tolerance.
+  // Thread jj solves L x = e_jj by forward substitution and scatters column jj; padding rows / upper part are 0.
   const int Pm = (m + 7) >> 3;
   double* LP = st.LooP + (size_t)j * subpanel_off(Pm, 0);
   for (int idx = tid; idx < (int)subpanel_off(Pm, 0); idx += nt) LP[idx] = 0.0;
   __syncthreads();
-  for (int idx = tid; idx < m * m; idx += nt) {
-    int i = idx / m, cc = idx % m;
-    if (cc <= i) LP[subpanel_off(i >> 3, 0) + (size_t)cc * 8 + (i & 7)] = (cc == i) ? 1.0 / A[idx] : A[idx];
-  }
-  __syncthreads();
-  // transposed inverses of the 8 x 8 diagonal blocks in their strictly upper slots (gpmpc_state.cuh)
-  if (tid < 32) {
-    for (int k = 0; k < m; ++k) {
-      const int i = k & 7, kb = k - i;
-      if (tid < i) {
-        const int jj = tid;
-        double acc = 0.0;
-        for (int t = jj; t < i; ++t)
-          acc = fma(A[(size_t)k * m + kb + t], __ldcg(LP + subpanel_off(kb >> 3, 0) + (size_t)(kb + t) * 8 + jj), acc);
-        __stcg(LP + subpanel_off(kb >> 3, 0) + (size_t)k * 8 + jj, -acc / A[(size_t)k * m + k]);
-      }
-      __syncwarp();
+  for (int jj = tid; jj < m; jj += nt) {
+    for (int i = jj; i < m; ++i) {
+      double acc = (i == jj) ? 1.0 : 0.0;
+      for (int k = jj; k < i; ++k) acc -= A[(size_t)i * m + k] * LP[subpanel_off(k >> 3, 0) + (size_t)jj * 8 + (k & 7)];
+      LP[subpanel_off(i >> 3, 0) + (size_t)jj * 8 + (i & 7)] = acc / A[(size_t)i * m + i];
     }
   }
+  __syncthreads();
   // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
   if (tid < 32) {
     const double* y = st.y_obs + (size_t)j * m;

@@ -46,7 +46,7 @@ struct DevState {
   const double* os;     // [g_ny]
   const double* noise;  // [g_ny][T]
   double* Loo;          // [g_ny][m][m] row-major lower Cholesky factor of K_oo + Sigma
-  double* LooP;         // [g_ny][subpanel_off(ceil(m/8), 0)] the same factor in sub-panel layout, diagonal = 1/L_jj
+  double* LooP;         // [g_ny][subpanel_off(ceil(m/8), 0)] inv(L_oo) in sub-panel layout (zeros above the diagonal)
   double* beta_o;       // [g_ny][m]  L_oo^{-1} y_o
   // per batch element --------------------------------------------------------------------
   double* Xh;           // [B][cap_points][d]

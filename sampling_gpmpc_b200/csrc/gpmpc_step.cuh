@@ -29,7 +29,9 @@
 #pragma once
 #include "gpmpc_state.cuh"
 
+#ifndef STEP_MAX_WARPS
 #define STEP_MAX_WARPS 16  // warps per CTA are chosen per launch (shared-memory budget), one CTA per SM
+#endif
 #define FULL_MASK 0xffffffffu
 #ifndef STEP_SEG
 #define STEP_SEG 64  // 8-row column groups per TMA chunk / ring slot (64 * 64 B = 4 KB); multiple of 8
@@ -262,14 +264,12 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   const int wv_rows = mo + 8 * P8;
   const int wv_sz = (wv_rows * T + 8 + 15) & ~15;            // per warp, doubles (+8: don't-care reads of idle lanes)
   const int wb_sz = (wv_rows + 15) & ~15;
-  const int per_warp = wv_sz + wb_sz + 128 + STEP_NST * STEP_SEG * 8;
+  const int per_warp = wv_sz + wb_sz + STEP_NST * STEP_SEG * 8;
   double* warp_base = (double*)(sHrow + ((st.np + 1) & ~1));
   warp_base = (double*)(((uintptr_t)warp_base + 127) & ~(uintptr_t)127);
   double* wv = warp_base + (size_t)warp * per_warp;          // [wv_rows][T]  k, then w
   double* wb = wv + wv_sz;                                   // [wv_rows]     beta by storage column
-  double* sc = wb + wb_sz;                                   // [8][8]        W^T [W | beta]
-  double* sc2 = sc + 64;                                     // [8][8]        last (partly filled) diagonal block
-  double* ring = sc2 + 64;                                   // [STEP_NST][STEP_SEG*8]
+  double* ring = wb + wb_sz;                                 // [STEP_NST][STEP_SEG*8]
   uint64_t* bars = (uint64_t*)(warp_base + (size_t)nw * per_warp) + warp * STEP_NST;
 
   if (lane < STEP_NST) mbar_init(bars + lane, 1);
@@ -412,25 +412,28 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
     }
     __syncwarp();
 
-    // ---- B: shared rows against L_oo --------------------------------------------------------------------------
-    for (int p8 = 0; p8 < Pm; ++p8) {
-      const int n_off = 8 * p8;
+    // ---- B: shared rows: w_o = inv(L_oo) k_o, tile-row by tile-row from the LAST one (row i needs k_j, j <= i only,
+    //      so the in-place write of a tile-row never disturbs the rows still to be computed) --------------------------
+    for (int p8 = Pm - 1; p8 >= 0; --p8) {
       const uint32_t boff = (uint32_t)subpanel_off(p8, 0) * 8;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       if (LOO_SMEM) {
-        mma_accumulate<T>(acc, sL_s + boff + a_lane, wv_s + b_lane, n_off >> 2);
+        mma_accumulate<T>(acc, sL_s + boff + a_lane, wv_s + b_lane, 2 * p8 + 2);
       } else {
         const double* lp = gL + boff / 8 + tig * 8 + gid;
-        for (int it = 0; it < (n_off >> 2); it += 2) {
+        for (int it = 0; it < 2 * p8 + 2; it += 2) {
           const double a0 = lp[it * 32], a1 = lp[it * 32 + 32];
           const double b0 = lds(wv_s + b_lane + it * 4 * T * 8), b1 = lds(wv_s + b_lane + (it + 1) * 4 * T * 8);
           dmma(acc[0], acc[1], a0, b0);
           dmma(acc[2], acc[3], a1, b1);
         }
       }
-      subpanel_finish<T, LOO_SMEM>(acc, sL_s + boff + n_off * 64, gL + boff / 8 + n_off * 8, wv_s + n_off * T * 8,
-                                   min(8, m - n_off), gid, tig);
+      // mma.sync: every lane's reads of this tile-row's inputs are complete
+      const uint32_t mine = wv_s + ((8 * p8 + gid) * T + 2 * tig) * 8;
+      if (2 * tig < T) sts(mine, acc[0] + acc[2]);
+      if (2 * tig + 1 < T) sts(mine + 8, acc[1] + acc[3]);
     }
+    __syncwarp();
 
     // ---- C: own rows, streamed through the TMA ring -------------------------------------------------------------
     if (P8 > 0) {
@@ -480,22 +483,16 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
         wa += 8 * T * 8;
         ba += 64;
       }
-      *reinterpret_cast<double2*>(sc + gid * 8 + 2 * tig) = make_double2(acc[0] + acc[2], acc[1] + acc[3]);
-      __syncwarp();
-    }
-    // hand [sum_t w_t beta_t | sum_t w_t w_t^T (lower)] to the per-element finishing kernel
-    {
+      // hand [sum_t w_t beta_t | sum_t w_t w_t^T (lower)] to the per-element finishing kernel: lane (gid, tig) holds
+      // C[gid][2 tig], C[gid][2 tig + 1];  C[r][7] = mean_r
       constexpr int FS = T + T * (T + 1) / 2;
       double* fo = st.fin + (size_t)b * FS;
-      for (int q = lane; q < FS; q += 32) {
-        int r = q, s2 = 7;  // q < T: mean_r
-        if (q >= T) {
-          int u = q - T;  // u = r(r+1)/2 + s
-          r = 0;
-          while ((r + 1) * (r + 2) / 2 <= u) ++r;
-          s2 = u - r * (r + 1) / 2;
-        }
-        fo[q] = sc[r * 8 + s2];
+      const double c0 = acc[0] + acc[2], c1 = acc[1] + acc[3];
+      if (gid < T) {
+        const int s0 = 2 * tig, s1 = 2 * tig + 1, tri = T + gid * (gid + 1) / 2;
+        if (s0 <= gid) fo[tri + s0] = c0;
+        if (s1 <= gid) fo[tri + s1] = c1;
+        if (s1 == 7) fo[gid] = c1;
       }
     }
     if (!grow_factor) continue;
