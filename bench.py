@@ -50,7 +50,7 @@ def workload_config(ns_per_gpu, n_gpus):
                     f"{HORIZON} horizon steps, factor grows to c=150 rows per (sample, output)",
         "ns_per_gpu": ns_per_gpu, "ns_total": ns_per_gpu * n_gpus, "horizon": HORIZON,
         "parallelism": f"samples sharded contiguously over {n_gpus} GPU(s), no data-path collective",
-        "l2": "per-GPU factor state (~88 GB at 125k samples) >> 126 MB L2: inputs larger than L2, no flush needed",
+        "l2": "per-GPU factor state (~58 GB at 125k samples) >> 126 MB L2: inputs larger than L2, no flush needed",
     }
 
 
@@ -289,8 +289,16 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = work_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
-    roofline = {"bound": "hbm", "kernel": "k_step<2,3> (fused rollout step)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+    # DRAM bytes per step launch from the committed ncu capture of this same workload (profiles/, per round)
+    traffic, traffic_src = None, None
+    caps = sorted(f for f in os.listdir(os.path.join(REPO, "profiles")) if "traffic" in f and f.endswith(".json"))
+    if caps and ns == 125000:
+        cap = json.load(open(os.path.join(REPO, "profiles", caps[-1])))
+        traffic, traffic_src = cap["traffic_bytes_per_step_launch"], "profiles/" + caps[-1]
+    roofline = {"bound": "hbm", "kernel": "k_step<2,3> + k_step_finish<3> (fused rollout step: one gpmpc_step call)",
+                "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms_per_launch": kern_ms / max(kern_launches, 1),
                 "launches_timed": kern_launches,
                 "algorithmic_bytes_per_launch": work_bytes / max(kern_launches, 1),

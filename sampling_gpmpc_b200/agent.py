@@ -284,15 +284,9 @@ class Agent:
             filt = torch.any(dist_norm <= min_distance, dim=2)  # (ns, g_ny, H)
             newY = newY.clone()
             newY[filt.unsqueeze(-1).expand_as(newY)] = float("nan")
-            flags = torch.stack([torch.all(filt.reshape(-1, filt.shape[-1]), dim=0),
-                                 torch.any(filt.reshape(-1, filt.shape[-1]), dim=0)]).to(torch.int32)
-            if self.world_size > 1:  # the reference's all/any run over every sample, i.e. over all ranks
-                import torch.distributed as dist
-                f_all, f_any = flags[0].clone(), flags[1].clone()
-                dist.all_reduce(f_all, op=dist.ReduceOp.MIN)
-                dist.all_reduce(f_any, op=dist.ReduceOp.MAX)
-                flags = torch.stack([f_all, f_any])
-            flags = flags.cpu().numpy().astype(bool)
+            from .rollout import reduce_point_flags  # the reference's all/any run over every sample, i.e. all ranks
+            f_all, f_any = reduce_point_flags(filt, self.world_size)
+            flags = torch.stack([f_all, f_any]).cpu().numpy().astype(bool)
             keep = ~flags[0]
             if not keep.all():
                 newX, newY = newX[:, :, keep, :], newY[:, :, keep, :]

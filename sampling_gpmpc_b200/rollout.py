@@ -70,12 +70,34 @@ class ForwardRollout:
 
     def all_gather_trajectories(self, traj: torch.Tensor) -> torch.Tensor:
         """(ns_local, nx, steps+1) per rank -> (ns_global, nx, steps+1) on every rank: one NCCL all-gather."""
-        if self.world_size == 1:
-            return traj
+        return gather_padded(traj, self.ns_global, self.world_size)
+
+
+def gather_padded(local: torch.Tensor, ns_global: int, world_size: int) -> torch.Tensor:
+    """All-gather of per-rank sample blocks (shard_bounds layout; the last shard may be shorter) into the
+    single-process layout: row s of the result is global sample s on every rank."""
+    if world_size == 1:
+        return local
+    import torch.distributed as dist
+    per = -(-ns_global // world_size)
+    pad = torch.zeros((per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world_size * per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    return out[:ns_global]
+
+
+def reduce_point_flags(filt: torch.Tensor, world_size: int):
+    """The reference's cross-sample reductions (src/agent.py:186-191 'filtered for ALL samples' and GPyTorch's
+    any-over-batch NaN mask) over every sample of every rank.  filt (ns_local, g_ny, H) bool ->
+    (all, any) bool (H,).  One pair of tiny all-reduces; the only data-path collective, and only when
+    Dyn_gp_min_data_dist >= 0."""
+    flat = filt.reshape(-1, filt.shape[-1])
+    f_all, f_any = flat.all(0).to(torch.int32), flat.any(0).to(torch.int32)
+    if flat.shape[0] == 0:  # an empty shard must not veto 'all'
+        f_all = torch.ones_like(f_all)
+    if world_size > 1:
         import torch.distributed as dist
-        per = -(-self.ns_global // self.world_size)
-        pad = torch.zeros((per, *traj.shape[1:]), dtype=traj.dtype, device=traj.device)
-        pad[: traj.shape[0]] = traj
-        out = torch.empty((self.world_size * per, *traj.shape[1:]), dtype=traj.dtype, device=traj.device)
-        dist.all_gather_into_tensor(out, pad)
-        return out[: self.ns_global]
+        dist.all_reduce(f_all, op=dist.ReduceOp.MIN)
+        dist.all_reduce(f_any, op=dist.ReduceOp.MAX)
+    return f_all.bool(), f_any.bool()
