@@ -296,6 +296,10 @@ class GPEngine:
         self._check(self.lib.gpmpc_status(self.h, C.byref(s), int(clear), _stream()), "gpmpc_status")
         return int(s.value)
 
+    def engine_status_ok(self) -> bool:
+        """True when no Cholesky failed (a jitter-ladder escalation of the real-data block is not a failure)."""
+        return self.status() & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD | ST_NAN_INPUT) == 0
+
     def raise_on_status(self):
         s = self.status(clear=True)
         if s & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD):

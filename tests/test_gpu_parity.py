@@ -121,6 +121,76 @@ def test_fused_rollout_matches_oracle_refit(T3):
     assert ratio <= 1.0, f"trajectory off by {ratio:.3g} x tolerance"
 
 
+def _synthetic_engine(ns, g_ny, d, T, n_real, with_grad_obs, seed):
+    """SURVEY.md 8(d) config 5 shapes: X ~ U[-1,1]^d, y = sum sin(x_i) (+ analytic gradient), l = 1, s^2 = 1."""
+    from sampling_gpmpc_b200.engine import GPEngine
+    g = torch.Generator().manual_seed(seed)
+    X = torch.rand(n_real, d, generator=g, dtype=torch.float64) * 2 - 1
+    Y = torch.full((g_ny, n_real, T), float("nan"), dtype=torch.float64)
+    for j in range(g_ny):
+        Y[j, :, 0] = torch.sin(X).sum(1) * (1.0 + 0.3 * j)
+        if T > 1 and with_grad_obs:
+            Y[j, :, 1:] = torch.cos(X) * (1.0 + 0.3 * j)
+    eng = GPEngine(ns, g_ny, d, T, n_real)
+    ls = np.linspace(0.8, 1.3, g_ny * d).reshape(g_ny, d)
+    eng.set_hypers(ls, np.linspace(1.0, 0.6, g_ny), np.full((g_ny, T), 1e-6), 1e-6)
+    eng.set_real_data(X, Y)
+    return eng
+
+
+@pytest.mark.parametrize("d,T,n_real,grad_obs", [(3, 4, 45, False), (3, 4, 45, True), (6, 7, 30, False), (2, 1, 20, False),
+                                                 (1, 2, 12, True), (4, 5, 40, False), (5, 6, 24, False)])
+def test_fused_step_matches_block_kernels_across_shapes(d, T, n_real, grad_obs):
+    """Every template instantiation of the fused step kernel (incl. the large-m variant that reads inv(L_oo) through
+    L2 instead of shared memory: m = 180) against the substitution-based block kernels, 14 conditioning steps."""
+    ns, g_ny, steps = 9, 2, 14
+    a = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 3)
+    b = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 3)
+    g = torch.Generator().manual_seed(17)
+    worst = 0.0
+    x = torch.rand(ns, 1, 1, d, generator=g, dtype=torch.float64) * 1.6 - 0.8
+    for t in range(steps):
+        x = (x + 0.05 * torch.randn(ns, 1, 1, d, generator=g, dtype=torch.float64)).clamp(-1, 1)  # random walk, step 0.05
+        xx = x.expand(ns, g_ny, 1, d).contiguous().cuda()
+        e = torch.randn(ns, g_ny, 1, T, generator=g, dtype=torch.float64).clamp(-3, 3).cuda()
+        opts = a.opts(beta=3.0)
+        m1, v1, y1, j1 = a.step(xx, e, opts)
+        m2, v2, y2, j2 = b.posterior(xx, e, opts)
+        b.append(xx, y2)
+        assert torch.equal(j1, j2), f"jitter decisions differ at step {t}"
+        for j in range(g_ny):
+            os_j = float(a.outputscale[j])
+            worst = max(worst, scaled_close(m1[:, j].cpu(), m2[:, j].cpu(), np.sqrt(os_j), RTOL),
+                        scaled_close(v1[:, j].cpu(), v2[:, j].cpu(), os_j, RTOL),
+                        scaled_close(y1[:, j].cpu(), y2[:, j].cpu(), np.sqrt(os_j), RTOL))
+    REPORT[f"step_vs_block/d{d}_T{T}_n{n_real}_{int(grad_obs)}"] = worst
+    _dump_report()
+    assert a.engine_status_ok() and b.engine_status_ok()
+    assert a.num_factor_rows == b.num_factor_rows == steps * T
+    assert worst <= 1.0, f"fused step off by {worst:.3g} x tolerance"
+
+
+def test_pendulum2d_rollout_matches_oracle_refit():
+    """True-reachable-set shape (benchmarking/simulate_true_reachable_set.py:179-259): real data WITH derivatives
+    (m = 180), d = 3, T = 4, g_ny = 2, zero-variance switch on, no feedback."""
+    from oracle.rollout_ref import reference_rollout
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    ns, steps = 6, 10
+    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps)
+    g = torch.Generator().manual_seed(2)
+    eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64).clamp(-2.5, 2.5)
+    u = (2.0 * torch.sin(torch.linspace(0, 3, steps, dtype=torch.float64))).reshape(steps, 1)
+    fr = ForwardRollout(params, condition=True)
+    traj = fr.run(u, eps).cpu().numpy()
+    ref = reference_rollout(params, fr.spec, u, eps, condition=True)
+    ratio = scaled_close(traj, ref, float(np.sqrt(outputscales(params).max())), RTOL)
+    REPORT["rollout/pendulum2D"] = dict(traj=ratio, status=fr.engine.status())
+    _dump_report()
+    assert fr.engine.status() == 0
+    assert ratio <= 1.0, f"trajectory off by {ratio:.3g} x tolerance"
+
+
 def test_step_equals_posterior_plus_append():
     """The fused warp kernel and the general block kernels are two implementations of one recursion."""
     from sampling_gpmpc_b200.rollout import ForwardRollout
