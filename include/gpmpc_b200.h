@@ -161,6 +161,52 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
                   const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
                   void* stream);
 
+/* ---- the data-set rules around the draw (Dyn_gp_min_data_dist >= 0) ------------------------------ */
+
+/* sample_gp's min-distance overwrite + truncation (src/agent.py:666-708), applied to y DEVICE [B*H*T] in place:
+ * where the nearest FULLY OBSERVED training point of the model (real, then recorded hallucinated; a point with a
+ * NaN target counts as infinitely far, agent.py:674-679) is within min_dist of test point (b, h), its targets
+ * replace the draw; then y is clipped to mean +- beta*sqrt(var) (beta < 0: no clipping; mean/var may be NULL). */
+int gpmpc_min_dist_overwrite(gpmpc_handle* h, const double* x, int32_t H, const double* mean, const double* var,
+                             double min_dist, double beta, double* y, void* stream);
+
+/* update_hallucinated_Dyn_dataset's filter (src/agent.py:166-181): labels y DEVICE [B*H*T] of every new point that
+ * is within min_dist of ANY input already in its element's data set (real; plus the recorded hallucinated ones
+ * if use_hallucinated) become NaN.  counts DEVICE int32 [g_ny*H] = number of this handle's samples filtered per
+ * (output, point): the caller sums it over ranks and forms the reference's all-over-samples (drop the point,
+ * agent.py:186-191) and any-over-batch (GPyTorch's NaN mask, SURVEY.md A.4 -> gpmpc_append's point_active). */
+int gpmpc_filter_new_points(gpmpc_handle* h, const double* x, int32_t H, double min_dist, int32_t use_hallucinated,
+                            double* y, int32_t* counts, void* stream);
+
+/* ---- formats either side of the path ---------------------------------------------- */
+
+/* The acados stage parameter vector of every stage in one launch (src/solver.py:98-131, layout fixed by
+ * src/utils/model.py:34-41):  out DEVICE [H][P],  P = ns*(nx*nx + nx*nu + 2*nx) + n_tail,
+ *   out[stage] = [ per sample i:  y_grad_i (nx*nx, row-major) | u_grad_i (nx*nu) | x_h[stage][i*nx..] | gp_val_i (nx) ]
+ *                ++ tail[stage]           (tail = hstack(u_h, xg, w, tilde_eps) rows, DEVICE [H][n_tail])
+ * lin DEVICE [ns][nx][H][1+nx+nu] is gpmpc_assemble's output, x_h DEVICE [H][ns*nx] the SQP iterate.
+ * use_feedback_K: y_grad += u_grad @ env->K_fb (solver.py:90). */
+int gpmpc_pack_plin(gpmpc_handle* h, const gpmpc_env* env, const double* lin, const double* x_h, const double* tail,
+                    int32_t n_tail, int32_t H, int32_t use_feedback_K, double* out, void* stream);
+
+/* Stage-wise reductions over the trajectories traj DEVICE [ns][nx][H1]: bounding box and the tightening
+ * Delta[i][t] = max_n |traj[n][i][t] - ref[i][t]| (extra/approx_sampling_mpc/README.md:19-27).  Outputs DEVICE
+ * [nx][H1], any may be NULL; ref DEVICE [nx][H1] (required for max_dev).  Sharded samples: reduce the three
+ * small arrays with MIN / MAX over ranks instead of gathering the trajectories. */
+int gpmpc_traj_stats(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, const double* ref,
+                     double* box_min, double* box_max, double* max_dev, void* stream);
+
+/* Convex hull of the per-stage point clouds (traj[:, i0, t], traj[:, i1, t]) over the samples
+ * (benchmarking/generate_convex_hull.py:88-100, scipy ConvexHull(...).vertices).  The GPU discards everything
+ * strictly inside the polygon of 16 directional extremes; the exact hull of the survivors is taken on the host.
+ * hull_idx HOST int32 [H1][max_vertices]: sample indices of stage t's vertices, counter-clockwise from the
+ * lexicographically smallest point; hull_n HOST int32 [H1].  SYNCHRONISES the stream. */
+int gpmpc_stage_hulls(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, int32_t i0, int32_t i1,
+                      int32_t max_vertices, int32_t* hull_idx, int32_t* hull_n, void* stream);
+/* Host helper (no device work): exact hull of n HOST points xy[n][2], e.g. to merge the per-rank hull vertices
+ * of sharded samples.  hull_pos HOST int32 [n] receives positions into xy, counter-clockwise. */
+int gpmpc_hull2d(const double* xy, int32_t n, int32_t* hull_pos, int32_t* hull_n);
+
 /* ---- introspection ----------------------------------------------------------------------------- */
 
 int32_t gpmpc_num_hallucinated(const gpmpc_handle* h);  /* points recorded per batch element */

@@ -249,24 +249,14 @@ class Agent:
 
     def _sample_gp_min_dist(self, x_input, base_samples):
         """Dyn_gp_min_data_dist >= 0 (agent.py:666-698): the nearest fully observed training point's targets
-        replace the draw when it is closer than the threshold.  The distance test is a cross-point search that
-        is not fused yet: draw without truncation in the kernel, overwrite, then truncate (agent.py:701-708)."""
+        replace the draw when it is closer than the threshold.  Draw (with the zero-variance rule) without
+        truncation, then ONE kernel does the nearest-point overwrite and the truncation (agent.py:701-708)."""
         ag = self.params["agent"]
         if base_samples is None:
             base_samples = torch.randn(*x_input.shape[:-1], self.in_dim_y, dtype=F64, device=self.torch_device)
         opts = self.engine.opts(-1.0, ag["Dyn_gp_variance_is_zero"])
         mean, var, y, jl = self.engine.posterior(x_input, base_samples, opts)
-        x_train, y_train = self.model_i.train_inputs[0], self.model_i.train_targets
-        H = x_input.shape[2]
-        dist_norm = torch.linalg.vector_norm(x_input[:, :, None, :, :] - x_train[:, :, :, None, :], dim=-1)
-        isnan = torch.any(torch.isnan(y_train), dim=3).unsqueeze(-1).expand(-1, -1, -1, H)
-        dist_norm = dist_norm.masked_fill(isnan, float("inf"))
-        too_small = torch.any(dist_norm <= ag["Dyn_gp_min_data_dist"], dim=2).unsqueeze(-1).expand(-1, -1, -1, self.in_dim_y)
-        idx = torch.min(dist_norm, dim=2)[1]
-        closest = torch.gather(y_train, 2, idx.unsqueeze(-1).expand(-1, -1, -1, self.in_dim_y))
-        y = torch.where(too_small, closest, y)
-        sd = torch.sqrt(var)
-        y = torch.min(torch.max(y, mean - ag["Dyn_gp_beta"] * sd), mean + ag["Dyn_gp_beta"] * sd)
+        self.engine.min_dist_overwrite(x_input, mean, var, y, ag["Dyn_gp_min_data_dist"], ag["Dyn_gp_beta"])
         self.model_i_call = _PosteriorView(mean, var, jl)
         self.model_i_samples = y
         return y
@@ -276,17 +266,13 @@ class Agent:
         min_distance = self.params["agent"]["Dyn_gp_min_data_dist"]
         active = None
         if min_distance >= 0.0:
-            # agent.py:166-191: NaN the labels of near-duplicates per sample, drop a point only if it is
-            # filtered for ALL samples; GPyTorch then masks a slot that is NaN for ANY batch element (A.4)
-            Xh, _ = self._hallucinated()
-            X_cond = torch.cat([self.Dyn_gp_X_train_batch, Xh], 2)
-            dist_norm = torch.linalg.vector_norm(newX[:, :, None, :, :] - X_cond[:, :, :, None, :], dim=-1)
-            filt = torch.any(dist_norm <= min_distance, dim=2)  # (ns, g_ny, H)
-            newY = newY.clone()
-            newY[filt.unsqueeze(-1).expand_as(newY)] = float("nan")
-            from .rollout import reduce_point_flags  # the reference's all/any run over every sample, i.e. all ranks
-            f_all, f_any = reduce_point_flags(filt, self.world_size)
-            flags = torch.stack([f_all, f_any]).cpu().numpy().astype(bool)
+            # agent.py:166-191: NaN the labels of near-duplicates per sample (one kernel), drop a point only if it is
+            # filtered for ALL samples of some output; GPyTorch then masks a slot that is NaN for ANY batch
+            # element (A.4).  The all / any run over every sample, i.e. over all ranks: one tiny all-reduce.
+            newY = newY.contiguous().clone()
+            counts = self.engine.filter_new_points(newX, newY, min_distance, use_hallucinated=not self._pending_reset)
+            from .rollout import reduce_filter_counts
+            flags = reduce_filter_counts(counts, self.ns_global, self.world_size)
             keep = ~flags[0]
             if not keep.all():
                 newX, newY = newX[:, :, keep, :], newY[:, :, keep, :]
@@ -345,3 +331,23 @@ class Agent:
         torch.cuda.current_stream().synchronize()
         h = host.numpy()
         return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]
+
+
+    # ---- f1: the acados stage parameters (solver.py:98-131) -------------------------------------
+    def pack_p_lin(self, lin: torch.Tensor, x_h, tail, use_feedback_K: bool = False) -> np.ndarray:
+        """lin = dyn_fg_jacobians_device(...) (ns,nx,H,1+nx+nu); x_h (H, ns*nx) the SQP iterate; tail (H, n_tail) =
+        hstack(u_h, xg, w, tilde_eps) per stage.  Returns the (H, P) array whose row `stage` is exactly the p_lin
+        the reference concatenates sample by sample: ONE kernel and ONE device->host copy instead of the
+        O(H ns^2) numpy concatenate loop."""
+        env = self.env_struct
+        if use_feedback_K:
+            from .engine import make_env_struct
+            K = np.asarray(self.params["optimizer"]["terminal_tightening"]["K"], dtype=np.float64)
+            env = make_env_struct(self.spec, K, np.zeros(self.nx))
+        x_h = torch.as_tensor(np.asarray(x_h), dtype=F64)
+        tail = None if tail is None else torch.as_tensor(np.asarray(tail), dtype=F64)
+        out = self.engine.pack_plin(env, lin, x_h, tail, use_feedback_K)
+        host = torch.empty(out.shape, dtype=F64, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()

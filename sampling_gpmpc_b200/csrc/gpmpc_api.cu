@@ -11,6 +11,7 @@
 
 #include "gpmpc_assemble.cuh"
 #include "gpmpc_block.cuh"
+#include "gpmpc_post.cuh"
 #include "gpmpc_step.cuh"
 
 namespace {
@@ -37,6 +38,9 @@ struct gpmpc_handle {
   int r_ns = 0;
   unsigned char* d_active = nullptr;
   int d_active_cap = 0;
+  // scratch of the consumers (gpmpc_traj_stats / gpmpc_stage_hulls), grown on demand
+  void* c_scratch = nullptr;
+  size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
@@ -202,7 +206,8 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
-  cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active);
+  cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
+  cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   delete h;
   return GPMPC_OK;
@@ -260,6 +265,21 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
 
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o);
+  cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
+  // per output: is every task of real point p observed?  (sample_gp's y_train_isnan, src/agent.py:674-679)
+  std::vector<int> full((size_t)g_ny * n);
+  for (int j = 0; j < g_ny; ++j)
+    for (int p = 0; p < n; ++p) {
+      bool ok = true;
+      for (int t = 0; t < T; ++t) ok = ok && !std::isnan(hy[((size_t)j * n + p) * T + t]);
+      full[(size_t)j * n + p] = ok ? 1 : 0;
+    }
+  double* Yr; int* rf;
+  CUDA_TRY(h, dev_alloc(&Yr, hy.size()));
+  CUDA_TRY(h, dev_alloc(&rf, full.size()));
+  CUDA_TRY(h, cudaMemcpyAsync(Yr, Y, hy.size() * 8, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(h, cudaMemcpyAsync(rf, full.data(), full.size() * 4, cudaMemcpyHostToDevice, stream));
+  st.Yr = Yr; st.real_full = rf;
   double *Xr, *yo; int *op, *ot;
   CUDA_TRY(h, dev_alloc(&Xr, (size_t)n * d));
   CUDA_TRY(h, dev_alloc(&op, (size_t)m));
@@ -594,6 +614,206 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
   h->last_bytes = bytes;
   h->last_flops = flops;
   return GPMPC_OK;
+}
+
+static int ensure_scratch(gpmpc_handle* h, size_t bytes) {
+  if (bytes <= h->c_scratch_bytes) return GPMPC_OK;
+  cudaFree(h->c_scratch);
+  h->c_scratch = nullptr;
+  h->c_scratch_bytes = 0;
+  CUDA_TRY(h, cudaMalloc(&h->c_scratch, bytes));
+  h->c_scratch_bytes = bytes;
+  return GPMPC_OK;
+}
+
+int gpmpc_min_dist_overwrite(gpmpc_handle* h, const double* x, int32_t H, const double* mean, const double* var,
+                             double min_dist, double beta, double* y, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || !y || H < 1 || (beta >= 0.0 && (!mean || !var))) return fail(h, GPMPC_ERR_ARG, "bad x / y / H / moments");
+  const long long pairs = (long long)h->st.B * H;
+  const int warps = 4;
+  k_min_dist_overwrite<<<(unsigned)((pairs + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      h->st, x, H, mean, var, min_dist, beta, y);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+int gpmpc_filter_new_points(gpmpc_handle* h, const double* x, int32_t H, double min_dist, int32_t use_hallucinated,
+                            double* y, int32_t* counts, void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!x || !y || !counts || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / counts / H");
+  CUDA_TRY(h, cudaMemsetAsync(counts, 0, (size_t)h->st.g_ny * H * 4, (cudaStream_t)stream));
+  const long long pairs = (long long)h->st.B * H;
+  const int warps = 4;
+  k_filter_new_points<<<(unsigned)((pairs + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      h->st, x, H, min_dist, use_hallucinated, y, counts);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+int gpmpc_pack_plin(gpmpc_handle* h, const gpmpc_env* env, const double* lin, const double* x_h, const double* tail,
+                    int32_t n_tail, int32_t H, int32_t use_feedback_K, double* out, void* stream) {
+  if (!h || !env || !lin || !x_h || !out || H < 1 || n_tail < 0 || (n_tail > 0 && !tail))
+    return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (env->nx < 1 || env->nx > GPMPC_MAX_NX || env->nu < 1 || env->nu > GPMPC_MAX_NX)
+    return fail(h, GPMPC_ERR_ARG, "bad env dims");
+  const int ns = h->st.ns, nx = env->nx, nu = env->nu;
+  const long long total = ((long long)ns * (nx * nx + nx * nu + 2 * nx) + n_tail) * H;
+  const int threads = 256;
+  const int blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)h->num_sms * 8);
+  k_pack_plin<<<blocks, threads, 0, (cudaStream_t)stream>>>(ns, nx, nu, H, n_tail, use_feedback_K ? 1 : 0, *env, lin,
+                                                             x_h, tail, out);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+int gpmpc_traj_stats(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, const double* ref,
+                     double* box_min, double* box_max, double* max_dev, void* stream_) {
+  if (!h || !traj || ns < 1 || nx < 1 || H1 < 1) return fail(h, GPMPC_ERR_ARG, "bad traj / dims");
+  if (max_dev && !ref) return fail(h, GPMPC_ERR_ARG, "max_dev needs a reference trajectory");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int cols = nx * H1, threads = 128, bx = (cols + threads - 1) / threads;
+  // enough sample ranges to fill the machine a few times over; each reads its rows coalesced along (i, t)
+  const int parts = std::max(1, std::min(ns, (h->num_sms * 8 + bx - 1) / bx));
+  int rc = ensure_scratch(h, (size_t)parts * 3 * cols * 8);
+  if (rc) return rc;
+  double* part = (double*)h->c_scratch;
+  k_traj_stats_partial<<<dim3(bx, parts), threads, 0, stream>>>(ns, cols, traj, ref, part);
+  k_traj_stats_final<<<bx, threads, 0, stream>>>(parts, cols, part, box_min, box_max, max_dev);
+  h->launches += 2;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+// exact 2-D hull of a handful of points (Andrew's monotone chain, strict turns: collinear points are not vertices,
+// like qhull's default).  pts sorted by (x, y, idx); returns positions into pts, counter-clockwise from the
+// lexicographically smallest point.
+namespace {
+struct HullPt { double x, y; int idx; };
+inline long double orient(const HullPt& a, const HullPt& b, const HullPt& c) {
+  return ((long double)b.x - a.x) * ((long double)c.y - a.y) - ((long double)b.y - a.y) * ((long double)c.x - a.x);
+}
+std::vector<int> monotone_chain(std::vector<HullPt>& p) {
+  std::sort(p.begin(), p.end(), [](const HullPt& a, const HullPt& b) {
+    return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.idx < b.idx);
+  });
+  // identical coordinates: keep the lowest sample index
+  size_t w = 0;
+  for (size_t i = 0; i < p.size(); ++i)
+    if (w == 0 || p[i].x != p[w - 1].x || p[i].y != p[w - 1].y) p[w++] = p[i];
+  p.resize(w);
+  const int n = (int)p.size();
+  std::vector<int> hull;
+  if (n <= 2) {
+    for (int i = 0; i < n; ++i) hull.push_back(i);
+    return hull;
+  }
+  hull.resize(2 * (size_t)n);
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    while (k >= 2 && orient(p[hull[k - 2]], p[hull[k - 1]], p[i]) <= 0) --k;
+    hull[k++] = i;
+  }
+  for (int i = n - 2, t = k + 1; i >= 0; --i) {
+    while (k >= t && orient(p[hull[k - 2]], p[hull[k - 1]], p[i]) <= 0) --k;
+    hull[k++] = i;
+  }
+  hull.resize(k - 1);
+  return hull;
+}
+}  // namespace
+
+int gpmpc_hull2d(const double* xy, int32_t n, int32_t* hull_pos, int32_t* hull_n) {
+  if (!xy || !hull_pos || !hull_n || n < 0) return GPMPC_ERR_ARG;
+  std::vector<HullPt> p((size_t)n);
+  for (int i = 0; i < n; ++i) p[i] = HullPt{xy[2 * i], xy[2 * i + 1], i};
+  const std::vector<int> hv = monotone_chain(p);
+  for (size_t k = 0; k < hv.size(); ++k) hull_pos[k] = p[hv[k]].idx;
+  *hull_n = (int32_t)hv.size();
+  return GPMPC_OK;
+}
+
+int gpmpc_stage_hulls(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, int32_t i0, int32_t i1,
+                      int32_t max_vertices, int32_t* hull_idx, int32_t* hull_n, void* stream_) {
+  if (!h || !traj || !hull_idx || !hull_n || ns < 1 || nx < 1 || H1 < 1 || max_vertices < 1 || i0 < 0 || i1 < 0 ||
+      i0 >= nx || i1 >= nx || i0 == i1)
+    return fail(h, GPMPC_ERR_ARG, "bad traj / dims / coordinate pair");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HullDirs dirs;
+  for (int k = 0; k < HULL_DIRS; ++k) {  // counter-clockwise
+    dirs.cx[k] = std::cos(2.0 * M_PI * k / HULL_DIRS);
+    dirs.cy[k] = std::sin(2.0 * M_PI * k / HULL_DIRS);
+  }
+  const int bx = (H1 + 31) / 32, ty = 8;
+  const int parts = std::max(1, std::min((ns + ty - 1) / ty, (h->num_sms * 4 + bx - 1) / bx));
+  // survivors per stage: the polygon of HULL_DIRS extremes leaves a thin rim; start generous, grow if it overflows
+  int cap = std::max(4096, std::min(ns, ns / 8 + 1024));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const size_t n_ext = (size_t)H1 * HULL_DIRS;
+    const size_t off_pval = 0, off_poly = off_pval + (size_t)parts * n_ext * 8, off_cxy = off_poly + n_ext * 16,
+                 off_pidx = off_cxy + (size_t)H1 * cap * 16, off_ext = off_pidx + (size_t)parts * n_ext * 4,
+                 off_cand = off_ext + n_ext * 4, off_cnt = off_cand + (size_t)H1 * cap * 4,
+                 total = off_cnt + (size_t)H1 * 4;
+    int rc = ensure_scratch(h, total);
+    if (rc) return rc;
+    char* base = (char*)h->c_scratch;
+    double* pval = (double*)(base + off_pval);
+    double* poly = (double*)(base + off_poly);
+    double* cxy = (double*)(base + off_cxy);
+    int* pidx = (int*)(base + off_pidx);
+    int* ext = (int*)(base + off_ext);
+    int* cand = (int*)(base + off_cand);
+    int* cnt = (int*)(base + off_cnt);
+    CUDA_TRY(h, cudaMemsetAsync(cnt, 0, (size_t)H1 * 4, stream));
+    k_hull_extremes_partial<<<dim3(bx, parts), dim3(32, ty), 0, stream>>>(ns, nx, H1, i0, i1, dirs, traj, pval, pidx);
+    k_hull_extremes_final<<<(unsigned)((n_ext + 127) / 128), 128, 0, stream>>>(parts, nx, H1, i0, i1, pval, pidx, traj,
+                                                                              poly, ext);
+    k_hull_filter<<<dim3(bx, parts), dim3(32, ty), 0, stream>>>(ns, nx, H1, i0, i1, cap, traj, poly, cand, cxy, cnt);
+    h->launches += 3;
+    CUDA_TRY(h, cudaGetLastError());
+    std::vector<int> hc((size_t)H1), hext(n_ext);
+    std::vector<double> hpoly(n_ext * 2);
+    CUDA_TRY(h, cudaMemcpyAsync(hc.data(), cnt, (size_t)H1 * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hext.data(), ext, n_ext * 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(h, cudaMemcpyAsync(hpoly.data(), poly, n_ext * 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(h, cudaStreamSynchronize(stream));
+    const int worst = *std::max_element(hc.begin(), hc.end());
+    if (worst > cap) {  // degenerate cloud (e.g. collinear): every point survived the filter
+      if (attempt == 1 || cap >= ns) return fail(h, GPMPC_ERR_CAPACITY, "hull candidate list overflow");
+      cap = ns;
+      continue;
+    }
+    std::vector<int> hcand((size_t)H1 * cap);
+    std::vector<double> hxy((size_t)H1 * cap * 2);
+    // one strided copy of the used prefixes would need per-stage lengths; the lists are small, copy whole rows up to worst
+    if (worst > 0) {
+      CUDA_TRY(h, cudaMemcpy2DAsync(hcand.data(), (size_t)cap * 4, cand, (size_t)cap * 4, (size_t)worst * 4, H1,
+                                    cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(h, cudaMemcpy2DAsync(hxy.data(), (size_t)cap * 16, cxy, (size_t)cap * 16, (size_t)worst * 16, H1,
+                                    cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(h, cudaStreamSynchronize(stream));
+    }
+    for (int t = 0; t < H1; ++t) {
+      std::vector<HullPt> p;
+      p.reserve((size_t)hc[t] + HULL_DIRS);
+      for (int k = 0; k < hc[t]; ++k)
+        p.push_back(HullPt{hxy[((size_t)t * cap + k) * 2], hxy[((size_t)t * cap + k) * 2 + 1], hcand[(size_t)t * cap + k]});
+      for (int k = 0; k < HULL_DIRS; ++k)
+        p.push_back(HullPt{hpoly[((size_t)t * HULL_DIRS + k) * 2], hpoly[((size_t)t * HULL_DIRS + k) * 2 + 1],
+                           hext[(size_t)t * HULL_DIRS + k]});
+      const std::vector<int> hv = monotone_chain(p);
+      if ((int)hv.size() > max_vertices) return fail(h, GPMPC_ERR_CAPACITY, "more hull vertices than max_vertices");
+      hull_n[t] = (int32_t)hv.size();
+      for (size_t k = 0; k < hv.size(); ++k) hull_idx[(size_t)t * max_vertices + k] = p[hv[k]].idx;
+    }
+    return GPMPC_OK;
+  }
+  return fail(h, GPMPC_ERR_CAPACITY, "hull candidate list overflow");
 }
 
 int32_t gpmpc_num_hallucinated(const gpmpc_handle* h) { return h ? h->st.np : -1; }

@@ -42,6 +42,8 @@ struct DevState {
   const int* obs_pt;    // [m] real point of observed scalar i
   const int* obs_task;  // [m] its task
   const double* y_obs;  // [g_ny][m]
+  const double* Yr;     // [g_ny][n_real][T] real targets as given (NaN = unobserved), for the min-distance overwrite
+  const int* real_full; // [g_ny][n_real] 1 if every task of the real point is observed for that output
   const double* ls;     // [g_ny][d]
   const double* os;     // [g_ny]
   const double* noise;  // [g_ny][T]

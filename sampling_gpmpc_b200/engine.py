@@ -56,6 +56,12 @@ ABI = {
     "gpmpc_step": (C.c_int, [_P, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _D, _D, _P]),
     "gpmpc_assemble": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _I, _D, _P]),
     "gpmpc_rollout": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _P]),
+    "gpmpc_min_dist_overwrite": (C.c_int, [_P, _D, _I, _D, _D, C.c_double, C.c_double, _D, _P]),
+    "gpmpc_filter_new_points": (C.c_int, [_P, _D, _I, C.c_double, _I, _D, _D, _P]),
+    "gpmpc_pack_plin": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, _I, _I, _I, _D, _P]),
+    "gpmpc_traj_stats": (C.c_int, [_P, _D, _I, _I, _I, _D, _D, _D, _D, _P]),
+    "gpmpc_stage_hulls": (C.c_int, [_P, _D, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "gpmpc_hull2d": (C.c_int, [C.POINTER(C.c_double), _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "gpmpc_num_hallucinated": (C.c_int32, [_P]),
     "gpmpc_num_factor_rows": (C.c_int32, [_P]),
     "gpmpc_num_real_observed": (C.c_int32, [_P]),
@@ -129,6 +135,20 @@ def make_env_struct(spec, feedback_K=None, x_equi=None) -> GpmpcEnv:
         for i, v in enumerate(np.asarray(x_equi, dtype=np.float64).reshape(-1)):
             e.x_equi[i] = v
     return e
+
+
+def hull2d(xy: np.ndarray) -> np.ndarray:
+    """Exact 2-D hull of a few host points (n,2) -> positions of the vertices, counter-clockwise (host helper of
+    the library; merges per-rank hull vertices of sharded samples)."""
+    lib = load_library()
+    xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+    pos = np.empty((max(1, xy.shape[0]),), dtype=np.int32)
+    n = C.c_int32(0)
+    rc = lib.gpmpc_hull2d(xy.ctypes.data_as(C.POINTER(C.c_double)), xy.shape[0], pos.ctypes.data_as(C.POINTER(C.c_int32)),
+                          C.byref(n))
+    if rc != 0:
+        raise GPEngineError(f"gpmpc_hull2d failed ({rc})")
+    return pos[: n.value].copy()
 
 
 class GPEngine:
@@ -269,6 +289,70 @@ class GPEngine:
                                     _ptr(traj), _stream())
         self._check(rc, "gpmpc_rollout")
         return traj
+
+    # ---- data-set rules, p_lin, trajectory consumers ---------------------------------------------
+    def min_dist_overwrite(self, x: torch.Tensor, mean, var, y: torch.Tensor, min_dist: float, beta: float):
+        """In place on y (ns,g_ny,H,T): nearest fully observed training targets where closer than min_dist, then
+        truncation to mean +- beta sqrt(var) (src/agent.py:666-708)."""
+        H = x.shape[-2]
+        assert y.is_contiguous() and y.shape == (self.ns, self.g_ny, H, self.T)
+        rc = self.lib.gpmpc_min_dist_overwrite(self.h, _ptr(self._x(x, H)), H, _ptr(mean), _ptr(var), float(min_dist),
+                                               float(beta), _ptr(y), _stream())
+        self._check(rc, "gpmpc_min_dist_overwrite")
+        return y
+
+    def filter_new_points(self, x: torch.Tensor, y: torch.Tensor, min_dist: float, use_hallucinated: bool = True):
+        """NaNs (in place) the labels y (ns,g_ny,H,T) of new points within min_dist of the element's data set;
+        returns counts (g_ny,H) int32 on the device: samples of this shard filtered per (output, point)."""
+        H = x.shape[-2]
+        assert y.is_contiguous() and y.shape == (self.ns, self.g_ny, H, self.T)
+        counts = torch.empty((self.g_ny, H), dtype=torch.int32, device=self.device)
+        rc = self.lib.gpmpc_filter_new_points(self.h, _ptr(self._x(x, H)), H, float(min_dist), int(use_hallucinated),
+                                              _ptr(y), _ptr(counts), _stream())
+        self._check(rc, "gpmpc_filter_new_points")
+        return counts
+
+    def pack_plin(self, env: GpmpcEnv, lin: torch.Tensor, x_h: torch.Tensor, tail: Optional[torch.Tensor],
+                  use_feedback_K: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """lin (ns,nx,H,1+nx+nu), x_h (H,ns*nx), tail (H,n_tail) -> p_lin of every stage (H,P) (solver.py:98-131)."""
+        ns, nx, H, w = lin.shape
+        nu = w - 1 - nx
+        n_tail = 0 if tail is None else tail.shape[1]
+        P = ns * (nx * nx + nx * nu + 2 * nx) + n_tail
+        x_h = x_h.to(self.device, torch.float64).contiguous()
+        tail = None if tail is None else tail.to(self.device, torch.float64).contiguous()
+        assert x_h.shape == (H, ns * nx) and lin.is_contiguous()
+        if out is None:
+            out = torch.empty((H, P), dtype=torch.float64, device=self.device)
+        rc = self.lib.gpmpc_pack_plin(self.h, C.byref(env), _ptr(lin), _ptr(x_h), _ptr(tail), n_tail, H,
+                                      int(use_feedback_K), _ptr(out), _stream())
+        self._check(rc, "gpmpc_pack_plin")
+        return out
+
+    def traj_stats(self, traj: torch.Tensor, ref: Optional[torch.Tensor] = None):
+        """traj (ns,nx,H1) -> box_min, box_max (nx,H1) [, max_dev (nx,H1) = max_n |traj - ref|]."""
+        ns, nx, H1 = traj.shape
+        traj = traj.contiguous()
+        mk = lambda: torch.empty((nx, H1), dtype=torch.float64, device=self.device)
+        lo, hi = mk(), mk()
+        dev = mk() if ref is not None else None
+        ref = None if ref is None else ref.to(self.device, torch.float64).contiguous()
+        rc = self.lib.gpmpc_traj_stats(self.h, _ptr(traj), ns, nx, H1, _ptr(ref), _ptr(lo), _ptr(hi), _ptr(dev), _stream())
+        self._check(rc, "gpmpc_traj_stats")
+        return (lo, hi) if ref is None else (lo, hi, dev)
+
+    def stage_hulls(self, traj: torch.Tensor, i0: int = 0, i1: int = 1, max_vertices: int = 512):
+        """Per-stage convex hull of (traj[:, i0, t], traj[:, i1, t]): list over t of int32 sample-index arrays,
+        counter-clockwise (generate_convex_hull.py:88-100)."""
+        ns, nx, H1 = traj.shape
+        traj = traj.contiguous()
+        idx = np.empty((H1, max_vertices), dtype=np.int32)
+        n = np.empty((H1,), dtype=np.int32)
+        rc = self.lib.gpmpc_stage_hulls(self.h, _ptr(traj), ns, nx, H1, i0, i1, max_vertices,
+                                        idx.ctypes.data_as(C.POINTER(C.c_int32)), n.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        _stream())
+        self._check(rc, "gpmpc_stage_hulls")
+        return [idx[t, : n[t]].copy() for t in range(H1)]
 
     # ---- introspection -------------------------------------------------------------------------
     @property

@@ -87,17 +87,13 @@ def gather_padded(local: torch.Tensor, ns_global: int, world_size: int) -> torch
     return out[:ns_global]
 
 
-def reduce_point_flags(filt: torch.Tensor, world_size: int):
-    """The reference's cross-sample reductions (src/agent.py:186-191 'filtered for ALL samples' and GPyTorch's
-    any-over-batch NaN mask) over every sample of every rank.  filt (ns_local, g_ny, H) bool ->
-    (all, any) bool (H,).  One pair of tiny all-reduces; the only data-path collective, and only when
-    Dyn_gp_min_data_dist >= 0."""
-    flat = filt.reshape(-1, filt.shape[-1])
-    f_all, f_any = flat.all(0).to(torch.int32), flat.any(0).to(torch.int32)
-    if flat.shape[0] == 0:  # an empty shard must not veto 'all'
-        f_all = torch.ones_like(f_all)
+def reduce_filter_counts(counts: torch.Tensor, ns_global: int, world_size: int) -> np.ndarray:
+    """counts (g_ny, H) int32 = this shard's samples whose new point h was filtered for output j
+    (gpmpc_filter_new_points).  Sum over ranks, then the reference's flags (src/agent.py:186-191 and GPyTorch's
+    any-over-batch NaN mask): returns bool (2, H): [0] point filtered for ALL samples of some
+    output (drop it), [1] filtered for ANY batch element (keep it in the data set, mask it in the factor)."""
     if world_size > 1:
         import torch.distributed as dist
-        dist.all_reduce(f_all, op=dist.ReduceOp.MIN)
-        dist.all_reduce(f_any, op=dist.ReduceOp.MAX)
-    return f_all.bool(), f_any.bool()
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    c = counts.cpu().numpy()
+    return np.stack([(c == ns_global).any(0), (c > 0).any(0)])

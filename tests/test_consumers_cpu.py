@@ -1,0 +1,88 @@
+"""CPU: the oracle restatements of the rows either side of the hot path (oracle/consumers_ref.py) and the library's
+host-only hull helper (gpmpc_hull2d has no device work, so it runs here)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import consumers_ref as ref
+
+
+def test_p_lin_layout_matches_the_acados_model_unpacking(golden_dir):
+    """src/utils/model.py:34-41 reads p_lin back as [A_i (nx*nx) | B_i (nx*nu) | x_lin_i (nx) | f_i (nx)] per sample,
+    then u_lin, xg, w, tilde_eps.  Build p_lin from a golden fixture's linearisation with the reference's loop and
+    unpack it with that rule."""
+    z = np.load(f"{golden_dir}/pendulum1D_sqp.npz")
+    gp_val, y_grad, u_grad, x_h, u_h = z["gp_val_0"], z["y_grad_0"], z["u_grad_0"], z["x_h_0"], z["u_h_0"]
+    ns, nx, H, nu = gp_val.shape[0], gp_val.shape[1], gp_val.shape[2], u_grad.shape[3]
+    xg, w = np.arange(H * 2, dtype=float).reshape(H, 2), np.zeros((H, nx))
+    te = [np.array([0.1 * t]) for t in range(H)]
+    p = ref.pack_p_lin(gp_val, y_grad, u_grad, x_h[:H], u_h, xg, w, te, ns, nx)
+    per = nx * nx + nx * nu + 2 * nx
+    assert len(p) == H and all(v.shape == (ns * per + nu + 2 + nx + 1,) for v in p)
+    for stage in (0, H - 1):
+        for i in (0, ns - 1):
+            blk = p[stage][i * per:(i + 1) * per]
+            assert np.array_equal(blk[:nx * nx].reshape(nx, nx), y_grad[i, :, stage, :])
+            assert np.array_equal(blk[nx * nx:nx * nx + nx * nu].reshape(nx, nu), u_grad[i, :, stage, :])
+            assert np.array_equal(blk[nx * nx + nx * nu:nx * nx + nx * nu + nx], x_h[stage, i * nx:(i + 1) * nx])
+            assert np.array_equal(blk[-nx:], gp_val[i, :, stage, 0])
+        assert np.array_equal(p[stage][ns * per:ns * per + nu], u_h[stage])
+        assert p[stage][-1] == 0.1 * stage
+
+
+def test_min_dist_oracle_on_a_hand_case():
+    """agent.py:666-708 semantics on a case small enough to read: NaN-target points never match, the nearest
+    fully observed one does, the result is clipped."""
+    x_train = torch.tensor([[[[0.0, 0.0], [1.0, 0.0], [1.0, 1e-6]]]])
+    y_train = torch.tensor([[[[5.0, float("nan")], [7.0, 8.0], [9.0, 10.0]]]])
+    x = torch.tensor([[[[0.0, 0.0], [1.0, 4e-7], [3.0, 3.0]]]])
+    y = torch.full((1, 1, 3, 2), 0.25)
+    mean, var = torch.zeros(1, 1, 3, 2), torch.full((1, 1, 3, 2), 4.0)
+    out = ref.min_dist_overwrite(x, x_train, y_train, y, mean, var, 1e-5, 2.5)
+    assert out[0, 0, 0].tolist() == [0.25, 0.25]   # duplicate of a point with a NaN target: not overwritten
+    assert out[0, 0, 1].tolist() == [5.0, 5.0]     # nearest fully observed: [7, 8] clipped to 0 + 2.5*2
+    assert out[0, 0, 2].tolist() == [0.25, 0.25]
+    newY, filt, f_all = ref.filter_new_points(x, y, x_train, 1e-5)
+    assert filt[0, 0].tolist() == [True, True, False] and f_all.tolist() == [True, True, False]
+    assert torch.isnan(newY[0, 0, :2]).all() and not torch.isnan(newY[0, 0, 2]).any()
+
+
+@pytest.fixture(scope="module")
+def hull2d():
+    import __graft_entry__ as g
+    g.build()
+    from sampling_gpmpc_b200.engine import hull2d
+    return hull2d
+
+
+@pytest.mark.parametrize("n,kind", [(3, "gauss"), (10, "gauss"), (1000, "gauss"), (20000, "gauss"), (5000, "disc"), (400, "grid")])
+def test_hull2d_matches_qhull(hull2d, n, kind):
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(n)
+    if kind == "gauss":
+        p = rng.normal(size=(n, 2))
+    elif kind == "disc":
+        a, r = rng.uniform(0, 2 * np.pi, n), np.sqrt(rng.uniform(0, 1, n))
+        p = np.stack([r * np.cos(a), r * np.sin(a)], 1)
+    else:  # integer grid: many collinear boundary points, which are NOT vertices (qhull's default, strict turns here)
+        g = np.arange(int(np.sqrt(n)), dtype=float)
+        p = np.stack(np.meshgrid(g, g), -1).reshape(-1, 2)
+    got, want = list(hull2d(p)), list(ConvexHull(p).vertices)
+    assert sorted(got) == sorted(want)
+    k = want.index(got[0])
+    assert got == want[k:] + want[:k], "not the same counter-clockwise cycle"
+
+
+def test_hull2d_degenerate(hull2d):
+    assert list(hull2d(np.array([[0.0, 0], [1, 1], [2, 2], [0.5, 0.5]]))) == [0, 2]
+    assert list(hull2d(np.array([[1.0, 1], [1, 1], [1, 1]]))) == [0]
+    assert list(hull2d(np.zeros((0, 2)))) == []
+
+
+def test_traj_stats_and_hull_oracle_shapes():
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(50, 4, 6)).cumsum(-1)
+    lo, hi, dev = ref.traj_stats(X, X.mean(0))
+    assert lo.shape == hi.shape == dev.shape == (4, 6) and (dev >= 0).all() and (lo <= hi).all()
+    hulls = ref.stage_hulls(X)
+    assert len(hulls) == 6 and all(len(h) >= 3 for h in hulls)

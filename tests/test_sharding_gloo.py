@@ -2,7 +2,7 @@
 
 The dynamics samples are independent, so the N>1 path is: contiguous shards of the sample index (global
 indices kept), no data-path collective, ONE all-gather of the trajectories for the consumers, and -- only when
-Dyn_gp_min_data_dist >= 0 -- an all-reduce of the per-point all/any flags.  The arithmetic itself needs the GPU
+Dyn_gp_min_data_dist >= 0 -- an all-reduce of the per-(output, point) filter counts.  The arithmetic itself needs the GPU
 (tests/test_gpu_parity.py); here the sharding, the gather layout and the flag reduction are checked with the
 same functions the product calls, on CPU tensors.
 """
@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sampling_gpmpc_b200.rollout import gather_padded, reduce_point_flags, shard_bounds
+from sampling_gpmpc_b200.rollout import gather_padded, reduce_filter_counts, shard_bounds
 
 
 def _free_port():
@@ -42,9 +42,12 @@ def _worker(rank, world, port, ns_global, q):
         filt_global = torch.rand(ns_global, 2, 7, generator=gen) < 0.5
         filt_global[:, :, 0] = True    # point 0: filtered for all samples -> dropped
         filt_global[:, :, 1] = False   # point 1: filtered for none
-        f_all, f_any = reduce_point_flags(filt_global[lo:hi], world)
-        ok_flags = bool(torch.equal(f_all, filt_global.reshape(-1, 7).all(0))) and \
-            bool(torch.equal(f_any, filt_global.reshape(-1, 7).any(0)))
+        filt_global[:, 0, 2] = True    # point 2: all samples of ONE output -> dropped too (agent.py:186-191)
+        counts = filt_global[lo:hi].sum(0).to(torch.int32)  # what gpmpc_filter_new_points hands back per shard
+        flags = reduce_filter_counts(counts, ns_global, world)
+        ok_flags = np.array_equal(flags[0], filt_global.all(0).any(0).numpy()) and \
+            np.array_equal(flags[1], filt_global.reshape(-1, 7).any(0).numpy()) and bool(flags[0][0]) and \
+            bool(flags[0][2]) and not flags[0][1]
         q.put((rank, lo, hi, ok_gather, ok_flags))
     finally:
         dist.destroy_process_group()
