@@ -461,10 +461,47 @@ static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x
   return launch_step_finish<T>(h, st, x, eps, o, mean, var, y, jl, grow, stream);
 }
 
+// c == 0 and nothing appended: the shared-factor kernel (8 / T elements per tensor-core tile)
+template <int D, int T>
+static int launch_step_shared(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
+                              const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl,
+                              cudaStream_t stream, bool* handled) {
+  constexpr int G = 8 / T;
+  const int Pm = (st.m + 7) / 8;
+  const size_t loop_sz = subpanel_off(Pm, 0);
+  const size_t nr_even = (st.n_real + 1) & ~1;
+  const size_t fixed = (loop_sz + nr_even * D + st.mo) * 8 + (size_t)((st.n_real * T + 1) & ~1) * 4 + 128;
+  const size_t per_warp = ((size_t)st.mo * 8 + 8 * D) * 8;
+  const size_t budget = (size_t)h->max_dyn_smem;
+  *handled = fixed + 4 * per_warp <= budget;
+  if (!*handled) return GPMPC_OK;  // inv(L_oo) too large for shared memory: the general kernel takes over
+  const int groups = (st.ns + G - 1) / G;
+  int warps = (int)std::min<size_t>(STEP_MAX_WARPS, (budget - fixed) / per_warp);
+  const int per_cta_need = (groups * st.g_ny + h->num_sms - 1) / h->num_sms;
+  warps = std::max(1, std::min(warps, per_cta_need));
+  auto kern = k_step_shared<D, T>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+    configured = true;
+  }
+  const int want = (groups + warps - 1) / warps;
+  const int resident = std::max(1, h->num_sms / st.g_ny);
+  dim3 grid(std::min(want, resident), st.g_ny);
+  kern<<<grid, warps * 32, fixed + (size_t)warps * per_warp, stream>>>(st, x);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return launch_step_finish<T>(h, st, x, eps, o, mean, var, y, jl, 0, stream);
+}
+
 template <int D, int T>
 static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                        const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                        cudaStream_t stream, bool* handled) {
+  if (st.c == 0 && !grow) {
+    int rc = launch_step_shared<D, T>(h, st, x, eps, o, mean, var, y, jl, stream, handled);
+    if (rc || *handled) return rc;
+  }
   // shared-memory budget, mirroring the carve-up at the top of k_step
   const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
   const size_t loop_sz = subpanel_off(Pm, 0);

@@ -10,7 +10,7 @@ __device__ __forceinline__ double point_dist(const double* __restrict__ a, const
   double s = 0.0;
   for (int k = 0; k < d; ++k) {
     const double r = a[k] - b[k];
-    s += r * r;
+    s = __dadd_rn(s, __dmul_rn(r, r));  // no FMA contraction: the comparison against min_dist must not depend on it
   }
   return sqrt(s);
 }
@@ -59,7 +59,8 @@ __global__ void k_min_dist_overwrite(DevState st, const double* __restrict__ x, 
     }
     if (beta >= 0.0) {
       const double mu = mean[pair * T + lane], sd = sqrt(var[pair * T + lane]);
-      v = fmin(fmax(v, mu - beta * sd), mu + beta * sd);
+      const double hw = __dmul_rn(beta, sd);  // torch: mean -+ beta * sqrt(var) as separate roundings
+      v = fmin(fmax(v, __dsub_rn(mu, hw)), __dadd_rn(mu, hw));
     }
     y[pair * T + lane] = v;
   }

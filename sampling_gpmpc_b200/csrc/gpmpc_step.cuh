@@ -510,6 +510,122 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   }
 }
 
+// K1s: the step when NO element has own factor rows and none are appended (c == 0, grow == 0): the value-only model
+// of benchmarking/simulate_forward_sampling_car.py as shipped (use_model_without_derivatives: the model ignores
+// the hallucinated set, src/agent.py:221-226), and posterior-only queries on real data.  Everything is a product
+// with the SHARED inv(L_oo): FP64-pipe bound, not HBM bound (SURVEY.md 8d "Regime A"), so the job is to fill the
+// tensor-core tile: one warp takes G = 8 / T elements (consecutive samples of output j) at a time and puts their
+// G*T right-hand sides side by side in the N = 8 dimension of mma.sync.m8n8k4.f64 -- with T = 1 that is 8 samples per
+// DMMA instead of 1 -- and the kernel vectors of the G elements are spread over all 32 lanes ((real point, element)
+// pairs), one exp per pair.
+//   A  K[mo][8]: column g*T + tb = cov(train scalar, task tb at x_g)              (wv8, row stride 8 doubles)
+//   B  W = inv(L_oo) K, tile-rows last to first, in place                         (as K1 phase B, all 8 columns live)
+//   D  C = W^T W (diagonal T x T blocks = the elements' W^T W),  M = W^T beta_o    -> st.fin, then k_step_finish
+template <int D, int T>
+__global__ void __launch_bounds__(STEP_MAX_WARPS * 32, 1)
+k_step_shared(DevState st, const double* __restrict__ x) {
+  constexpr int G = 8 / T;       // elements per warp pass
+  constexpr int FS = T + T * (T + 1) / 2;
+  extern __shared__ __align__(128) double smem[];
+  const int j_out = blockIdx.y;
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int m = st.m, mo = st.mo, Pm = (m + 7) >> 3;
+  const int loop_sz = (int)subpanel_off(Pm, 0);
+  const int nr_even = (st.n_real + 1) & ~1;
+  // carve-up (mirrored by launch_step_shared): inv(L_oo) | real inputs | beta_o (zero padded to mo) | row table | per warp
+  double* sL = smem;
+  double* sXr = sL + loop_sz;
+  double* sBo = sXr + (size_t)nr_even * D;
+  int* sRrow = (int*)(sBo + mo);
+  double* warp_base = (double*)(sRrow + ((st.n_real * T + 1) & ~1));
+  warp_base = (double*)(((uintptr_t)warp_base + 127) & ~(uintptr_t)127);
+  const int per_warp = mo * 8 + 8 * D;
+  double* wv = warp_base + (size_t)warp * per_warp;  // [mo][8]
+  double* sx = wv + (size_t)mo * 8;                  // [G][D] test inputs of the group
+
+  const double* gL = st.LooP + (size_t)j_out * loop_sz;
+  for (int idx = threadIdx.x; idx < loop_sz; idx += blockDim.x) sL[idx] = gL[idx];
+  for (int idx = threadIdx.x; idx < st.n_real * D; idx += blockDim.x) sXr[idx] = st.Xr[idx];
+  for (int idx = threadIdx.x; idx < st.n_real * T; idx += blockDim.x) sRrow[idx] = -1;
+  for (int idx = threadIdx.x; idx < mo; idx += blockDim.x) sBo[idx] = idx < m ? st.beta_o[(size_t)j_out * m + idx] : 0.0;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sRrow[st.obs_pt[idx] * T + st.obs_task[idx]] = idx;
+  for (int idx = lane; idx < mo * 8; idx += 32) wv[idx] = 0.0;  // padding rows [m, mo) and unused columns stay 0
+  __syncthreads();
+
+  const uint32_t wv_s = smem_u32(wv), sL_s = smem_u32(sL), bo_s = smem_u32(sBo);
+  const uint32_t a_lane = tig * 64 + gid * 8;   // A fragment: column group run of inv(L_oo)
+  const uint32_t b_lane = (tig * 8 + gid) * 8;  // B fragment: wv[4k + tig][gid]
+  double il[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
+  const double os = st.os[j_out];
+  const int n_groups = (st.ns + G - 1) / G;
+  const int nwarps_total = gridDim.x * nw;
+
+  for (int grp = blockIdx.x * nw + warp; grp < n_groups; grp += nwarps_total) {
+    const int s0 = grp * G;
+    const int g_live = min(G, st.ns - s0);
+    __syncwarp();  // previous group's reads of wv / sx are complete
+    if (lane < G * D) {
+      const int g = lane / D, a = lane % D;
+      sx[lane] = g < g_live ? x[((size_t)(s0 + g) * st.g_ny + j_out) * D + a] : 0.0;
+    }
+    __syncwarp();
+    // ---- A: (real point, element) pairs over the lanes ----------------------------------------------------------
+    for (int idx = lane; idx < st.n_real * G; idx += 32) {
+      const int p = idx / G, g = idx % G;
+      double xa[D], xs[D], kb[T][T];
+#pragma unroll
+      for (int a = 0; a < D; ++a) { xa[a] = sXr[p * D + a]; xs[a] = sx[g * D + a]; }
+      kernel_block<D, T>(xa, xs, il, os, kb);
+#pragma unroll
+      for (int ta = 0; ta < T; ++ta) {
+        const int row = sRrow[p * T + ta];
+        if (row >= 0) {
+#pragma unroll
+          for (int tb = 0; tb < T; ++tb) wv[row * 8 + g * T + tb] = kb[ta][tb];
+        }
+      }
+    }
+    __syncwarp();
+    // ---- B: W = inv(L_oo) K -------------------------------------------------------------------------------------
+    for (int p8 = Pm - 1; p8 >= 0; --p8) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      mma_accumulate<8>(acc, sL_s + (uint32_t)subpanel_off(p8, 0) * 8 + a_lane, wv_s + b_lane, 2 * p8 + 2);
+      const uint32_t mine = wv_s + ((8 * p8 + gid) * 8 + 2 * tig) * 8;
+      sts(mine, acc[0] + acc[2]);
+      sts(mine + 8, acc[1] + acc[3]);
+    }
+    __syncwarp();
+    // ---- D: C = W^T W and M = W^T beta_o (every column of M is the same vector) ---------------------------------------
+    double cw[4] = {0.0, 0.0, 0.0, 0.0}, cm[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+      uint32_t wa = wv_s + b_lane, ba = bo_s + tig * 8;
+      for (int t = 0; t < mo; t += 8) {
+        const double a0 = lds<0>(wa), a1 = lds<256>(wa);
+        const double e0 = lds<0>(ba), e1 = lds<32>(ba);
+        dmma(cw[0], cw[1], a0, a0);
+        dmma(cw[2], cw[3], a1, a1);
+        dmma(cm[0], cm[1], a0, e0);
+        dmma(cm[2], cm[3], a1, e1);
+        wa += 512;
+        ba += 64;
+      }
+    }
+    // lane (gid, tig) holds C[gid][2 tig], C[gid][2 tig + 1]; row gid belongs to element g = gid / T, task r = gid % T
+    const int g = gid / T, r = gid - g * T;
+    if (g < g_live) {
+      double* fo = st.fin + ((size_t)(s0 + g) * st.g_ny + j_out) * FS;
+      const int c0 = 2 * tig - g * T, c1 = c0 + 1;  // task index of the two columns within element g
+      if (c0 >= 0 && c0 <= r) fo[T + r * (r + 1) / 2 + c0] = cw[0] + cw[2];
+      if (c1 >= 0 && c1 <= r) fo[T + r * (r + 1) / 2 + c1] = cw[1] + cw[3];
+      if (tig == 0) fo[r] = cm[0] + cm[2];
+    }
+  }
+}
+
 // K1b: per-element scalar tail of the step, ONE THREAD per batch element (the warp kernel above would do this
 // arithmetic 32-fold redundantly): Sigma* = K** - W^T W, T x T Cholesky with GPyTorch's jitter ladder, y = mean +
 // L eps, zero-variance / truncation (src/agent.py:646-708), then the diagonal-block part of the rank-T append:

@@ -170,6 +170,44 @@ def test_fused_step_matches_block_kernels_across_shapes(d, T, n_real, grad_obs):
     assert worst <= 1.0, f"fused step off by {worst:.3g} x tolerance"
 
 
+@pytest.mark.parametrize("d,T,n_real,grad_obs,ns", [(2, 1, 45, False, 37), (2, 3, 45, False, 9), (3, 4, 45, True, 7), (6, 7, 30, False, 5),
+                                                    (1, 2, 12, True, 33), (4, 1, 40, False, 64), (5, 6, 24, False, 3), (3, 1, 20, False, 1)])
+def test_shared_factor_step_matches_block_kernels(d, T, n_real, grad_obs, ns):
+    """The shared-factor step kernel (no own rows, nothing appended: 8 / T elements per tensor-core tile; the path of
+    simulate_forward_sampling_car.py as shipped and of posterior-only queries) against the block kernels, for every
+    (d, T) instantiation and sample counts that do not fill the last tile; record-only handle, 3 recorded steps."""
+    g_ny = 3
+    a = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 5)
+    b = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 5)
+    for e in (a, b):
+        e.reset_hallucinated()
+        e.set_condition_on_hallucinated(False)
+    g = torch.Generator().manual_seed(23)
+    worst = 0.0
+    for t in range(3):
+        xx = (torch.rand(ns, g_ny, 1, d, generator=g, dtype=torch.float64) * 1.8 - 0.9).cuda()
+        e = torch.randn(ns, g_ny, 1, T, generator=g, dtype=torch.float64).clamp(-3, 3).cuda()
+        opts = a.opts(beta=3.0)
+        m0, v0 = a.step(xx, None)                # posterior only
+        m1, v1, y1, j1 = a.step(xx, e, opts)     # draw + record
+        m2, v2, y2, j2 = b.posterior(xx, e, opts)
+        b.append(xx, y2)
+        assert torch.equal(m0, m1) and torch.equal(v0, v1)
+        assert torch.equal(j1, j2)
+        for j in range(g_ny):
+            os_j = float(a.outputscale[j])
+            worst = max(worst, scaled_close(m1[:, j].cpu(), m2[:, j].cpu(), np.sqrt(os_j), RTOL),
+                        scaled_close(v1[:, j].cpu(), v2[:, j].cpu(), os_j, RTOL),
+                        scaled_close(y1[:, j].cpu(), y2[:, j].cpu(), np.sqrt(os_j), RTOL))
+    REPORT[f"shared_step_vs_block/d{d}_T{T}_n{n_real}_{int(grad_obs)}"] = worst
+    _dump_report()
+    assert a.engine_status_ok() and a.num_factor_rows == 0 and a.num_hallucinated == 3
+    Xa, Ya = a.export_hallucinated()
+    Xb, Yb = b.export_hallucinated()
+    assert torch.equal(Xa, Xb)
+    assert worst <= 1.0, f"shared-factor step off by {worst:.3g} x tolerance"
+
+
 def test_pendulum2d_rollout_matches_oracle_refit():
     """True-reachable-set shape (benchmarking/simulate_true_reachable_set.py:179-259): real data WITH derivatives
     (m = 180), d = 3, T = 4, g_ny = 2, zero-variance switch on, no feedback."""
