@@ -42,6 +42,11 @@ struct gpmpc_handle {
   void* c_scratch = nullptr;
   size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
+  // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) when m >= wo_min_m and inv(L_oo)
+  // does not fit in shared memory beside the warps (GPMPC_WO_MIN_M overrides the threshold, for experiments)
+  int wo_min_m = 256;
+  int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
+  size_t wo_count = 0;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -178,6 +183,8 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->max_dyn_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+  if (const char* e = getenv("GPMPC_WO_MIN_M")) h->wo_min_m = atoi(e);
+  if (const char* e = getenv("GPMPC_WO_MAX_NB")) h->wo_max_nb = std::min(3, std::max(1, atoi(e)));
   DevState& st = h->st;
   st.ns = dims->ns; st.g_ny = dims->g_ny; st.d = dims->d; st.T = dims->T; st.n_real = dims->n_real;
   st.B = dims->ns * dims->g_ny;
@@ -204,7 +211,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   free_factor_state(h);
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
-  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin);
+  cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin); cudaFree(st.Wo);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
@@ -439,11 +446,30 @@ static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double*
   return GPMPC_OK;
 }
 
-template <int D, int T, bool LOO_SMEM>
+// Regime A (large m): W_o = inv(L_oo) K_o for every element, NB column blocks of 8 per tile
+template <int D, int T, int NB>
+static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double* x, cudaStream_t stream) {
+  constexpr int E = 8 * NB / T;
+  auto kern = k_shared_rows<D, T, NB>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+    configured = true;
+  }
+  const size_t smem = ((size_t)st.mo * 8 * NB + ((E * D + 1) & ~1)) * 8;
+  const int n_tiles = (st.ns + E - 1) / E;
+  dim3 grid(std::min(n_tiles, std::max(1, h->num_sms / st.g_ny)), st.g_ny);
+  kern<<<grid, SR_THREADS, smem, stream>>>(st, x);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+template <int D, int T, bool LOO_SMEM, bool WO = false>
 static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                             const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                             int warps, size_t smem, cudaStream_t stream) {
-  auto kern = k_step<D, T, LOO_SMEM>;
+  auto kern = k_step<D, T, LOO_SMEM, WO>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
@@ -514,6 +540,36 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   const size_t budget = (size_t)h->max_dyn_smem;
   // L_oo lives in shared memory if at least 8 warps still fit beside it; otherwise it is read through L1/L2
   bool loo_smem = loop_sz * 8 + shared_tab + 8 * per_warp <= budget;
+  // ... or, for large m, not by this kernel at all: batched GEMM first (k_shared_rows), NB = column blocks per tile
+  int nb = 0;
+  if (!loo_smem && m >= h->wo_min_m)
+    for (nb = h->wo_max_nb; nb >= 1; --nb)
+      if ((size_t)st.mo * 8 * nb * 8 + 1024 <= budget) break;
+  if (nb >= 1) {
+    const size_t fixed_wo = m_even * 8 + (size_t)((st.np + 1) & ~1) * 4 + 128;
+    if (fixed_wo + per_warp <= budget) {
+      const size_t need = (size_t)st.B * st.mo * T;
+      if (h->wo_count < need) {
+        cudaFree(h->st.Wo);
+        h->st.Wo = nullptr;
+        h->wo_count = 0;
+        CUDA_TRY(h, dev_alloc(&h->st.Wo, need));
+        h->wo_count = need;
+      }
+      DevState stw = st;
+      stw.Wo = h->st.Wo;
+      int rc = nb == 3 ? launch_shared_rows<D, T, 3>(h, stw, x, stream)
+               : nb == 2 ? launch_shared_rows<D, T, 2>(h, stw, x, stream)
+                         : launch_shared_rows<D, T, 1>(h, stw, x, stream);
+      if (rc) return rc;
+      int warps = (int)std::min<size_t>(STEP_MAX_WARPS, (budget - fixed_wo) / per_warp);
+      const int per_cta_need = (st.ns * st.g_ny + h->num_sms - 1) / h->num_sms;
+      warps = std::max(1, std::min(warps, std::max(per_cta_need, 1)));
+      *handled = true;
+      return launch_step_impl<D, T, false, true>(h, stw, x, eps, o, mean, var, y, jl, grow, warps,
+                                                 fixed_wo + (size_t)warps * per_warp, stream);
+    }
+  }
   const size_t fixed = shared_tab + (loo_smem ? loop_sz * 8 : 0);
   *handled = fixed + per_warp <= budget;
   if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over

@@ -241,9 +241,13 @@ __host__ __device__ __forceinline__ int step_groups_per_element(int c, int mo) {
   return (int)(subpanel_off((c + 7) / 8, mo) / 8);
 }
 
-template <int D, int T, bool LOO_SMEM>
+// WO = true (large m, "Regime A"): the shared rows  w_o = inv(L_oo) k_o  of every element were produced by the batched
+// tensor-core GEMM k_shared_rows (below) into st.Wo; this kernel copies them into wv instead of running phases A
+// (real points) and B, so that inv(L_oo) is streamed once per TILE of elements instead of once per element.
+template <int D, int T, bool LOO_SMEM, bool WO = false>
 __global__ void __launch_bounds__(STEP_MAX_WARPS * 32, 1)
 k_step(DevState st, const double* __restrict__ x, int grow_factor) {
+  static_assert(!(WO && LOO_SMEM), "WO replaces the in-kernel product with inv(L_oo)");
   extern __shared__ __align__(128) double smem[];
   const int j_out = blockIdx.y;
   const int nw = blockDim.x >> 5;
@@ -256,11 +260,11 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
 
   // ---- shared-memory carve-up (sizes mirrored by launch_step in gpmpc_api.cu) -----------------------------
   double* sL = smem;                                         // [loop_sz] L_oo sub-panels (only if LOO_SMEM)
-  const int nr_even = (st.n_real + 1) & ~1;
+  const int nr_even = WO ? 0 : (st.n_real + 1) & ~1;          // WO: no real inputs / row table in shared memory
   double* sXr = sL + (LOO_SMEM ? loop_sz : 0);               // [nr_even*D] real inputs
   double* sBo = sXr + (size_t)nr_even * D;                   // [m_even]
   int* sRrow = (int*)(sBo + m_even);                         // [n_real*T] factor row of (real point, task), -1 = unobserved
-  int* sHrow = sRrow + ((st.n_real * T + 1) & ~1);           // [np] first own row of hallucinated point p, -1 = not in the factor
+  int* sHrow = sRrow + (WO ? 0 : (st.n_real * T + 1) & ~1);  // [np] first own row of hallucinated point p, -1 = not in the factor
   const int wv_rows = mo + 8 * P8;
   const int wv_sz = (wv_rows * T + 8 + 15) & ~15;            // per warp, doubles (+8: don't-care reads of idle lanes)
   const int wb_sz = (wv_rows + 15) & ~15;
@@ -277,12 +281,15 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   const double* gL = st.LooP + (size_t)j_out * loop_sz;
   if (LOO_SMEM)
     for (int idx = threadIdx.x; idx < loop_sz; idx += blockDim.x) sL[idx] = gL[idx];
-  for (int idx = threadIdx.x; idx < st.n_real * D; idx += blockDim.x) sXr[idx] = st.Xr[idx];
-  for (int idx = threadIdx.x; idx < st.n_real * T; idx += blockDim.x) sRrow[idx] = -1;
+  if (!WO) {
+    for (int idx = threadIdx.x; idx < st.n_real * D; idx += blockDim.x) sXr[idx] = st.Xr[idx];
+    for (int idx = threadIdx.x; idx < st.n_real * T; idx += blockDim.x) sRrow[idx] = -1;
+  }
   for (int idx = threadIdx.x; idx < st.np; idx += blockDim.x) sHrow[idx] = st.hrow0[idx];
   for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sBo[idx] = st.beta_o[(size_t)j_out * m + idx];
   __syncthreads();
-  for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sRrow[st.obs_pt[idx] * T + st.obs_task[idx]] = idx;
+  if (!WO)
+    for (int idx = threadIdx.x; idx < m; idx += blockDim.x) sRrow[st.obs_pt[idx] * T + st.obs_task[idx]] = idx;
   // padding rows [m, mo) and rows >= c of wv / wb are zero for the whole launch
   for (int idx = lane; idx < wv_sz + wb_sz; idx += 32) wv[idx] = 0.0;
   __syncthreads();
@@ -355,6 +362,22 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
       const char* nb = (const char*)(st.beta_h + bn_ * st.c_cap);
       if (lane * 128 < np * D * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + lane * 128));
       if (lane * 128 < c * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + lane * 128));
+      if (WO) {
+        const char* nw_ = (const char*)(st.Wo + bn_ * (size_t)mo * T);
+        for (int o = lane * 128; o < mo * T * 8; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nw_ + o));
+      }
+    }
+    if (WO) {
+      // shared rows from the batched GEMM: [mo][T] doubles, the layout of wv
+      const double2* wo = (const double2*)(st.Wo + (size_t)b * mo * T);
+      double2* wv2 = (double2*)wv;
+      const int n2 = mo * T / 2;
+      int i2 = lane;
+      for (; i2 + 96 < n2; i2 += 128) {
+        const double2 v0 = __ldcg(wo + i2), v1 = __ldcg(wo + i2 + 32), v2 = __ldcg(wo + i2 + 64), v3 = __ldcg(wo + i2 + 96);
+        wv2[i2] = v0; wv2[i2 + 32] = v1; wv2[i2 + 64] = v2; wv2[i2 + 96] = v3;
+      }
+      for (; i2 < n2; i2 += 32) wv2[i2] = __ldcg(wo + i2);
     }
 
     // ---- A: kernel vector, one exp per training POINT (and the element's beta) ------------------------------
@@ -396,7 +419,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
         }
       }
     }
-    for (int p = lane; p < st.n_real; p += 32) {
+    for (int p = lane; !WO && p < st.n_real; p += 32) {
       double xa[D], kb[T][T];
 #pragma unroll
       for (int a = 0; a < D; ++a) xa[a] = sXr[p * D + a];
@@ -414,7 +437,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
 
     // ---- B: shared rows: w_o = inv(L_oo) k_o, tile-row by tile-row from the LAST one (row i needs k_j, j <= i only,
     //      so the in-place write of a tile-row never disturbs the rows still to be computed) --------------------------
-    for (int p8 = Pm - 1; p8 >= 0; --p8) {
+    for (int p8 = Pm - 1; !WO && p8 >= 0; --p8) {
       const uint32_t boff = (uint32_t)subpanel_off(p8, 0) * 8;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       if (LOO_SMEM) {
@@ -506,6 +529,107 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
       if (t >= m && t < mo) continue;  // padding columns stay 0
 #pragma unroll
       for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = wv[t * T + r];
+    }
+  }
+}
+
+// K1a: the shared rows of EVERY element as one batched tensor-core product ("Regime A"): for large m
+// the per-element product with inv(L_oo) is FP64-contraction bound and, done one element at a time, re-streams the
+// m x m factor from L2 for every element.  Here a CTA takes a TILE of E = 8 NB / T consecutive samples of output j:
+//   A  K[mo][8 NB] in shared memory: row i = observed real scalar i, column e*T + tb = cov(scalar i, task tb at x_e)
+//      ((scalar, element) pairs over the threads, one exp per pair; columns rotated per row so that the B-fragment
+//      loads of mma.m8n8k4 are bank-conflict free without padding the rows)
+//   B  W = inv(L_oo) K: every warp takes 8-row panels of inv(L_oo) (longest first), streams the panel ONCE from
+//      L2 straight into A fragments (coalesced 256-byte rows of the sub-panel layout, 8 k-steps prefetched in
+//      registers) and multiplies it with all NB column blocks: NB DMMAs per A load, all 8 columns of every MMA live
+//   C  the accumulators go to st.Wo[b][row][T], the layout of k_step's wv array (k_step<.., WO = true> picks them up)
+// inv(L_oo) traffic from L2 per element drops by E (8 at T = 3) against the one-element-per-pass path.
+#define SR_THREADS 512
+template <int NC>
+__device__ __forceinline__ int sr_rot(int row) { return NC == 16 ? 4 * (row & 3) : 4 * ((row >> 1) & 1); }
+
+template <int D, int T, int NB>
+__global__ void __launch_bounds__(SR_THREADS, 1)
+k_shared_rows(DevState st, const double* __restrict__ x) {
+  constexpr int NC = 8 * NB, E = NC / T;
+  constexpr uint32_t KSTEP = 4 * NC * 8;  // bytes of K per k-step (4 rows)
+  extern __shared__ __align__(128) double smem[];
+  const int j_out = blockIdx.y;
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int m = st.m, mo = st.mo, Pm = mo >> 3;
+  double* sK = smem;                  // [mo][NC]
+  double* sx = sK + (size_t)mo * NC;  // [E][D]
+  const double* gL = st.LooP + (size_t)j_out * subpanel_off(Pm, 0);
+  for (int idx = threadIdx.x; idx < mo * NC; idx += blockDim.x) sK[idx] = 0.0;  // padding rows / columns stay 0
+  double il[D];
+#pragma unroll
+  for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
+  const double os = st.os[j_out];
+  uint32_t colo[NB];  // byte offset of column nb*8 + gid in this lane's rows (row & 3 == tig)
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) colo[nb] = (uint32_t)(((nb * 8 + gid + sr_rot<NC>(tig)) % NC) * 8);
+  const uint32_t brow = smem_u32(sK) + tig * NC * 8;
+  const int n_tiles = (st.ns + E - 1) / E;
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int s0 = tile * E, e_live = min(E, st.ns - s0);
+    __syncthreads();  // the previous tile's reads of sK / sx are complete
+    if (threadIdx.x < E * D) {
+      const int e = threadIdx.x / D, a = threadIdx.x - e * D;
+      sx[threadIdx.x] = e < e_live ? x[((size_t)(s0 + e) * st.g_ny + j_out) * D + a] : 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m * E; idx += blockDim.x) {
+      const int i = idx / E, e = idx - i * E;
+      double xs[D], out[T];
+#pragma unroll
+      for (int a = 0; a < D; ++a) xs[a] = sx[e * D + a];
+      kernel_row<D, T>(st.Xr + (size_t)st.obs_pt[i] * D, st.obs_task[i], xs, il, os, out);
+      const int rot = sr_rot<NC>(i);
+#pragma unroll
+      for (int tb = 0; tb < T; ++tb) sK[i * NC + (e * T + tb + rot) % NC] = out[tb];
+    }
+    __syncthreads();
+
+    for (int pi = warp; pi < Pm; pi += nw) {
+      const int p = Pm - 1 - pi, n4 = 2 * p + 2;  // k-steps of 4 columns in this panel
+      const double* ap = gL + subpanel_off(p, 0) + tig * 8 + gid;
+      double acc[NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.0;
+      double abuf[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) abuf[i] = i < n4 ? __ldcg(ap + i * 32) : 0.0;
+      uint32_t bb = brow;
+      for (int k0 = 0; k0 < n4; k0 += 8) {
+        double acur[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acur[i] = abuf[i];
+        ap += 256;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) abuf[i] = k0 + 8 + i < n4 ? __ldcg(ap + i * 32) : 0.0;
+#define SR_KSTEP(i)                                                                    \
+        if (k0 + (i) < n4) {                                                           \
+          _Pragma("unroll") for (int nb = 0; nb < NB; ++nb) {                          \
+            const double bv = lds<(i) * KSTEP>(bb + colo[nb]);                         \
+            dmma(acc[nb][2 * ((i) & 1)], acc[nb][2 * ((i) & 1) + 1], acur[i], bv);     \
+          }                                                                            \
+        }
+        SR_KSTEP(0) SR_KSTEP(1) SR_KSTEP(2) SR_KSTEP(3) SR_KSTEP(4) SR_KSTEP(5) SR_KSTEP(6) SR_KSTEP(7)
+#undef SR_KSTEP
+        bb += 8 * KSTEP;
+      }
+      const int row = 8 * p + gid;
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col = nb * 8 + 2 * tig + hh;
+          const int e = col / T, tb = col - e * T;
+          if (e < e_live)
+            st.Wo[(((size_t)(s0 + e) * st.g_ny + j_out) * mo + row) * T + tb] = acc[nb][hh] + acc[nb][2 + hh];
+        }
     }
   }
 }

@@ -139,10 +139,14 @@ def _synthetic_engine(ns, g_ny, d, T, n_real, with_grad_obs, seed):
 
 
 @pytest.mark.parametrize("d,T,n_real,grad_obs", [(3, 4, 45, False), (3, 4, 45, True), (6, 7, 30, False), (2, 1, 20, False),
-                                                 (1, 2, 12, True), (4, 5, 40, False), (5, 6, 24, False)])
+                                                 (1, 2, 12, True), (4, 5, 40, False), (5, 6, 24, False),
+                                                 # m >= 256: shared rows by the batched tensor-core GEMM (k_shared_rows)
+                                                 (3, 4, 70, True), (6, 7, 40, True), (2, 3, 300, False), (2, 1, 260, False),
+                                                 (4, 5, 52, True), (2, 3, 334, True)])
 def test_fused_step_matches_block_kernels_across_shapes(d, T, n_real, grad_obs):
-    """Every template instantiation of the fused step kernel (incl. the large-m variant that reads inv(L_oo) through
-    L2 instead of shared memory: m = 180) against the substitution-based block kernels, 14 conditioning steps."""
+    """Every template instantiation of the fused step kernel (incl. the variant that reads inv(L_oo) through L2 instead
+    of shared memory: m = 180, and the large-m path m >= 256 whose shared rows come from the batched GEMM
+    k_shared_rows with 3 / 2 / 1 column blocks per tile) against the substitution-based block kernels, 14 steps."""
     ns, g_ny, steps = 9, 2, 14
     a = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 3)
     b = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 3)
@@ -168,6 +172,35 @@ def test_fused_step_matches_block_kernels_across_shapes(d, T, n_real, grad_obs):
     assert a.engine_status_ok() and b.engine_status_ok()
     assert a.num_factor_rows == b.num_factor_rows == steps * T
     assert worst <= 1.0, f"fused step off by {worst:.3g} x tolerance"
+
+
+@pytest.mark.parametrize("nb,d,T,n_real,grad_obs", [(2, 3, 4, 70, True), (1, 3, 4, 70, True), (2, 6, 7, 40, True), (1, 6, 7, 40, True),
+                                                    (2, 2, 1, 260, False), (1, 2, 3, 300, False)])
+def test_shared_rows_gemm_tile_widths(nb, d, T, n_real, grad_obs, monkeypatch):
+    """k_shared_rows with 2 and 1 column blocks per tile (what m > ~1200 / ~1800 selects) forced at m ~ 280 through
+    GPMPC_WO_MAX_NB: tile sizes that do not divide the sample count, T that does not divide the tile width."""
+    monkeypatch.setenv("GPMPC_WO_MAX_NB", str(nb))
+    ns, g_ny, steps = 13, 2, 5
+    a = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 7)
+    monkeypatch.setenv("GPMPC_WO_MIN_M", "1000000")  # b: the per-element product with inv(L_oo) through L2
+    b = _synthetic_engine(ns, g_ny, d, T, n_real, grad_obs, 7)
+    g = torch.Generator().manual_seed(29)
+    worst = 0.0
+    for t in range(steps):
+        xx = (torch.rand(ns, g_ny, 1, d, generator=g, dtype=torch.float64) * 1.8 - 0.9).cuda()
+        e = torch.randn(ns, g_ny, 1, T, generator=g, dtype=torch.float64).clamp(-3, 3).cuda()
+        m1, v1, y1, j1 = a.step(xx, e, a.opts(beta=3.0))
+        m2, v2, y2, j2 = b.step(xx, e, b.opts(beta=3.0))
+        assert torch.equal(j1, j2)
+        for j in range(g_ny):
+            os_j = float(a.outputscale[j])
+            worst = max(worst, scaled_close(m1[:, j].cpu(), m2[:, j].cpu(), np.sqrt(os_j), RTOL),
+                        scaled_close(v1[:, j].cpu(), v2[:, j].cpu(), os_j, RTOL),
+                        scaled_close(y1[:, j].cpu(), y2[:, j].cpu(), np.sqrt(os_j), RTOL))
+    REPORT[f"shared_rows_nb{nb}/d{d}_T{T}_n{n_real}"] = worst
+    _dump_report()
+    assert a.engine_status_ok() and b.engine_status_ok()
+    assert worst <= 1.0, f"batched shared rows off by {worst:.3g} x tolerance"
 
 
 @pytest.mark.parametrize("d,T,n_real,grad_obs,ns", [(2, 1, 45, False, 37), (2, 3, 45, False, 9), (3, 4, 45, True, 7), (6, 7, 30, False, 5),
