@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
   for (int jj = tid; jj < m; jj += nt) {
     for (int i = jj; i < m; ++i) {
       double acc = (i == jj) ? 1.0 : 0.0;
-      for (int k = jj; k < i; ++k) acc -= A[(size_t)i * m + k] * LP[subpanel_off(k >> 3, 0) + (size_t)jj * 8 + (k & 7)];
-      LP[subpanel_off(i >> 3, 0) + (size_t)jj * 8 + (i & 7)] = acc / A[(size_t)i * m + i];
+      for (int k = jj; k < i; ++k) acc -= A[(size_t)i * m + k] * LP[subpanel_off(k >> 3, 0) + sp_idx(jj, k & 7)];
+      LP[subpanel_off(i >> 3, 0) + sp_idx(jj, i & 7)] = acc / A[(size_t)i * m + i];
     }
   }
   __syncthreads();

@@ -9,10 +9,14 @@
 #define GP_MAX_TRIES 3         // gpytorch.settings.cholesky_max_tries
 
 // ---- sub-panel layout of a lower-triangular factor -------------------------------------------------------
-// Rows are grouped in SUB-PANELS of 8.  Sub-panel p holds, for every storage column t < off + 8p + 8, the 8
-// consecutive doubles  L[8p .. 8p+7][t]  ("column group", 64 bytes); groups are stored one after the other in
-// column order and sub-panels one after the other in row order, so an element's factor is ONE contiguous
-// stream that the fused step kernel pulls through shared memory with TMA bulk copies in consumption order.
+// Rows are grouped in SUB-PANELS of 8.  Sub-panel p holds the 8 rows L[8p .. 8p+7][t] of every storage column
+// t < off + 8p + 8 (64 bytes per column, "column group"); sub-panels follow one another in row order, so an
+// element's factor is ONE contiguous stream that the fused step kernel pulls through shared memory with TMA bulk
+// copies in consumption order.  Inside a sub-panel the columns are taken four at a time ("k-block", 256 bytes = the
+// A operand of one mma.m8n8k4) and a k-block is stored as [row half h][column 0..3][row 0..3 of the half]
+// (sp_idx): the 16 lanes of a half-warp then read one contiguous 128-byte run when they load the A fragment
+// (lane = 4*row + column), i.e. conflict-free; the plain [column][8 rows] order put a half-warp on banks 0-7 and
+// 16-23 only (2-way conflict on every A load, measured: 289 conflict wavefronts per element-step at c = 30).
 //   off = 0 for the shared real-data factor L_oo (storage column = column);
 //   off = mo = roundup8(m) for an element's own rows: storage columns [0, m) are the shared columns, [m, mo)
 //   are zero padding (so that every column range the kernel iterates over in steps of 4 is aligned), and
@@ -25,6 +29,11 @@
 __host__ __device__ __forceinline__ size_t subpanel_off(int p, int off) {
   // doubles before sub-panel p:  8 * sum_{q<p} (off + 8q + 8)
   return (size_t)8 * ((size_t)p * (off + 8) + (size_t)4 * p * (p - 1));
+}
+
+// index (doubles) inside a sub-panel of the entry (storage column t, row r of the sub-panel, 0 <= r < 8)
+__host__ __device__ __forceinline__ size_t sp_idx(int t, int r) {
+  return (size_t)(t >> 2) * 32 + ((r >> 2) & 1) * 16 + (t & 3) * 4 + (r & 3);
 }
 
 struct DevState {
@@ -107,7 +116,7 @@ __device__ __forceinline__ const double* train_scalar(const DevState& st, int b,
 // diagonal slot, which holds 1 / L[m+k][m+k]
 __device__ __forceinline__ double* own_entry(const DevState& st, int b, int k, int col) {
   const int t = col < st.m ? col : col - st.m + st.mo;
-  return st.Lh + (size_t)b * st.elem_stride + subpanel_off(k >> 3, st.mo) + (size_t)t * 8 + (k & 7);
+  return st.Lh + (size_t)b * st.elem_stride + subpanel_off(k >> 3, st.mo) + sp_idx(t, k & 7);
 }
 
 // strictly-lower entry L[i][col] (col < i) of the full bordered factor [[L_oo, 0], [own rows]] (output j)

@@ -179,8 +179,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// c += L[8 rows][4*n4 columns] * w[4*n4 columns][.]: column groups contiguous from shared address `la` (lane
-// address: + tig*64 + gid*8), w rows from `wa` (lane address: + (tig*T + gid)*8).  n4 is even; two accumulator sets.
+// c += L[8 rows][4*n4 columns] * w[4*n4 columns][.]: k-blocks (256 B each, gpmpc_state.cuh) contiguous from shared
+// address `la` (lane address: + a_lane_off), w rows from `wa` (lane address: + (tig*T + gid)*8).  n4 is even; two
+// accumulator sets.
+// byte offset of this lane's A-fragment element (row gid, column tig) inside a k-block
+__device__ __forceinline__ uint32_t a_lane_off(int gid, int tig) { return (uint32_t)sp_idx(tig, gid) * 8; }
+
 template <int T>
 __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint32_t wa, int n4) {
   constexpr int WSTEP = 4 * T * 8;  // bytes of w per 4 columns
@@ -220,11 +224,11 @@ __device__ __forceinline__ void subpanel_finish(const double (&c)[4], uint32_t d
   // inv(D)[gid][k], k = tig and tig + 4: slot (row k, column gid) of the block, zero above the diagonal
   double a0 = 0.0, a1 = 0.0;
   if (DBLK_SHARED) {
-    if (tig <= gid) a0 = lds(dblk_s + (gid * 8 + tig) * 8);
-    if (tig + 4 <= gid) a1 = lds(dblk_s + (gid * 8 + tig + 4) * 8);
+    if (tig <= gid) a0 = lds(dblk_s + (uint32_t)sp_idx(gid, tig) * 8);
+    if (tig + 4 <= gid) a1 = lds(dblk_s + (uint32_t)sp_idx(gid, tig + 4) * 8);
   } else {
-    if (tig <= gid) a0 = dblk_g[gid * 8 + tig];
-    if (tig + 4 <= gid) a1 = dblk_g[gid * 8 + tig + 4];
+    if (tig <= gid) a0 = dblk_g[sp_idx(gid, tig)];
+    if (tig + 4 <= gid) a1 = dblk_g[sp_idx(gid, tig + 4)];
   }
   __syncwarp();
   const double b0 = lds(wblk + (tig * T + gid) * 8), b1 = lds(wblk + ((tig + 4) * T + gid) * 8);
@@ -299,7 +303,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
 
   const uint32_t wv_s = smem_u32(wv), wb_s = smem_u32(wb), ring_s = smem_u32(ring), bars_s = smem_u32(bars);
   const uint32_t sL_s = smem_u32(sL);
-  const uint32_t a_lane = tig * 64 + gid * 8;        // lane offset into a run of column groups (A fragment)
+  const uint32_t a_lane = a_lane_off(gid, tig);      // lane offset into a run of k-blocks (A fragment)
   const uint32_t b_lane = (tig * T + gid) * 8;       // lane offset into wv rows (B fragment)
   const int nwarps_total = gridDim.x * nw;
   const int s_first = blockIdx.x * nw + warp;
@@ -443,7 +447,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
       if (LOO_SMEM) {
         mma_accumulate<T>(acc, sL_s + boff + a_lane, wv_s + b_lane, 2 * p8 + 2);
       } else {
-        const double* lp = gL + boff / 8 + tig * 8 + gid;
+        const double* lp = gL + boff / 8 + a_lane / 8;
         for (int it = 0; it < 2 * p8 + 2; it += 2) {
           const double a0 = lp[it * 32], a1 = lp[it * 32 + 32];
           const double b0 = lds(wv_s + b_lane + it * 4 * T * 8), b1 = lds(wv_s + b_lane + (it + 1) * 4 * T * 8);
@@ -524,11 +528,12 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
     double* Le = st.Lh + (size_t)b * st.elem_stride;
     double* rowp[T];
 #pragma unroll
-    for (int r = 0; r < T; ++r) rowp[r] = Le + subpanel_off((c + r) >> 3, mo) + ((c + r) & 7);
+    for (int r = 0; r < T; ++r) rowp[r] = Le + subpanel_off((c + r) >> 3, mo) + sp_idx(0, (c + r) & 7);
     for (int t = lane; t < mo + c; t += 32) {
       if (t >= m && t < mo) continue;  // padding columns stay 0
+      const size_t to = sp_idx(t, 0);
 #pragma unroll
-      for (int r = 0; r < T; ++r) rowp[r][(size_t)t * 8] = wv[t * T + r];
+      for (int r = 0; r < T; ++r) rowp[r][to] = wv[t * T + r];
     }
   }
 }
@@ -594,7 +599,7 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
 
     for (int pi = warp; pi < Pm; pi += nw) {
       const int p = Pm - 1 - pi, n4 = 2 * p + 2;  // k-steps of 4 columns in this panel
-      const double* ap = gL + subpanel_off(p, 0) + tig * 8 + gid;
+      const double* ap = gL + subpanel_off(p, 0) + sp_idx(tig, gid);
       double acc[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.0;
@@ -679,7 +684,7 @@ k_step_shared(DevState st, const double* __restrict__ x) {
   __syncthreads();
 
   const uint32_t wv_s = smem_u32(wv), sL_s = smem_u32(sL), bo_s = smem_u32(sBo);
-  const uint32_t a_lane = tig * 64 + gid * 8;   // A fragment: column group run of inv(L_oo)
+  const uint32_t a_lane = a_lane_off(gid, tig); // A fragment: k-block run of inv(L_oo)
   const uint32_t b_lane = (tig * 8 + gid) * 8;  // B fragment: wv[4k + tig][gid]
   double il[D];
 #pragma unroll
@@ -866,7 +871,7 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
     double* gblk = Le + subpanel_off(kb >> 3, mo) + (size_t)(mo + kb) * 8;
     double blk[8][8];
     for (int t = 0; t < i_first; ++t)                // old columns: old rows' slots and the new rows' L entries
-      for (int i = 0; i < i_first + (r1 - r0); ++i) blk[t][i] = gblk[t * 8 + i];
+      for (int i = 0; i < i_first + (r1 - r0); ++i) blk[t][i] = gblk[sp_idx(t, i)];
     for (int r = r0; r < r1; ++r) {
       const int i = i_first + (r - r0);
       for (int s = r0; s < r; ++s) blk[i_first + (s - r0)][i] = Ln.v[r * (r + 1) / 2 + s];
@@ -876,10 +881,10 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
         for (int t = jc; t < i; ++t) acc = fma(blk[t][i], blk[t][jc], acc);
         blk[i][jc] = -rdn[r] * acc;                  // slot (row jc, column i)
       }
-      double* rowi = Le + subpanel_off(kb >> 3, mo) + i;
-      for (int s = 0; s < r0; ++s) rowi[(size_t)(mo + c + s) * 8] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
-      for (int t = i_first; t <= i; ++t) gblk[t * 8 + i] = blk[t][i];   // new columns of row i (incl. 1/L_ii)
-      for (int jc = 0; jc < i; ++jc) gblk[i * 8 + jc] = blk[i][jc];     // transposed inverse row
+      double* rowi = Le + subpanel_off(kb >> 3, mo);
+      for (int s = 0; s < r0; ++s) rowi[sp_idx(mo + c + s, i)] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
+      for (int t = i_first; t <= i; ++t) gblk[sp_idx(t, i)] = blk[t][i];   // new columns of row i (incl. 1/L_ii)
+      for (int jc = 0; jc < i; ++jc) gblk[sp_idx(i, jc)] = blk[i][jc];     // transposed inverse row
     }
     r0 = r1;
   }
