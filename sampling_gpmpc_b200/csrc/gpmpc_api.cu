@@ -42,9 +42,10 @@ struct gpmpc_handle {
   void* c_scratch = nullptr;
   size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
-  // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) when m >= wo_min_m and inv(L_oo)
-  // does not fit in shared memory beside the warps (GPMPC_WO_MIN_M overrides the threshold, for experiments)
-  int wo_min_m = 256;
+  // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) whenever inv(L_oo) does not fit in
+  // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
+  // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
+  int wo_min_m = 1;
   int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   size_t wo_count = 0;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)

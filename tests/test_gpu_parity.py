@@ -140,7 +140,7 @@ def _synthetic_engine(ns, g_ny, d, T, n_real, with_grad_obs, seed):
 
 @pytest.mark.parametrize("d,T,n_real,grad_obs", [(3, 4, 45, False), (3, 4, 45, True), (6, 7, 30, False), (2, 1, 20, False),
                                                  (1, 2, 12, True), (4, 5, 40, False), (5, 6, 24, False),
-                                                 # m >= 256: shared rows by the batched tensor-core GEMM (k_shared_rows)
+                                                 # larger m (with (3,4,45,True): m = 180 above): shared rows by the batched tensor-core GEMM (k_shared_rows)
                                                  (3, 4, 70, True), (6, 7, 40, True), (2, 3, 300, False), (2, 1, 260, False),
                                                  (4, 5, 52, True), (2, 3, 334, True)])
 def test_fused_step_matches_block_kernels_across_shapes(d, T, n_real, grad_obs):
