@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ns-per-gpu", type=int, default=125000)
-    ap.add_argument("--cpu-samples", type=int, default=48, help="bounded sample for the CPU legs")
+    ap.add_argument("--cpu-samples", type=int, default=192, help="bounded sample for the CPU legs (~10 s of host work)")
     ap.add_argument("--no-extras", action="store_true", help="skip the as-shipped / SQP side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -143,7 +143,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def extras(torch, device):
+def extras(torch, device, cpu_leg=True):
     """Side measurements reported next to the headline (not the bench value): the script as shipped
     (value-only model, no conditioning) and ms per SQP GP linearisation at the pendulum1D shape."""
     import numpy as np
@@ -178,18 +178,42 @@ def extras(torch, device):
     rng = np.random.default_rng(0)
     x_h = np.tile(np.stack([np.linspace(2.2, 3.1, H), np.linspace(2.0, 0.1, H)], 1), (1, 70)) + 0.01 * rng.standard_normal((H, 140))
     u_h = np.linspace(-3, 3, H).reshape(H, 1)
-    times = []
+    times, dev_times = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iterates = []
     for i in range(8):
+        iterates.append(x_h.copy())
         agent.mpc_iteration(i)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        e0.record()
         agent.train_hallucinated_dynGP(0)
         agent.dyn_fg_jacobians(agent.get_batch_x_hat(x_h, u_h), 0)
+        e1.record()
         times.append((time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize()
+        dev_times.append(e0.elapsed_time(e1))
         x_h = x_h + 0.005 * rng.standard_normal(x_h.shape)
     out["sqp_linearisation_ms"] = {"host_observed_ms_incl_d2h": float(np.median(times[2:])),
+                                   "device_ms": float(np.median(dev_times[2:])),
                                    "shape": "pendulum1D: ns=70, H=17, T=3 (q=51), n_obs=87",
                                    "calls": "train_hallucinated_dynGP + dyn_fg_jacobians (solver.py:84-94)"}
+    if cpu_leg:
+        # the same calls through the oracle's Agent restatement (full re-fit per call, all host threads)
+        from oracle.agent_ref import RefAgent
+        from sampling_gpmpc_b200.envs import make_env_spec
+        spec = make_env_spec(params)
+        Xr, Yr = spec.initial_training_data(params)
+        ref = RefAgent(params, spec, Xr, Yr, epistimic_random_vector=agent.epistimic_random_vector.cpu())
+        ct = []
+        for i in range(5):
+            ref.mpc_iteration(i)
+            t0 = time.perf_counter()
+            ref.train_hallucinated_dynGP(0)
+            ref.dyn_fg_jacobians(ref.get_batch_x_hat(iterates[i], u_h), 0)
+            ct.append((time.perf_counter() - t0) * 1e3)
+        out["sqp_linearisation_ms"]["cpu_port_ms"] = float(np.median(ct[1:]))
+        out["sqp_linearisation_ms"]["cpu_threads"] = torch.get_num_threads()
     return out
 
 
@@ -323,7 +347,7 @@ def run_ours(args):
         del fr, eng, eps_dev, traj
         torch.cuda.empty_cache()
         try:
-            line["extra"] = extras(torch, device)
+            line["extra"] = extras(torch, device, cpu_leg=not args.no_cpu_baseline)
         except Exception as exc:  # side measurements must never take the headline down
             line["extra"] = {"error": repr(exc)}
     print(json.dumps(line), flush=True)
