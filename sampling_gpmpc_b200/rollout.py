@@ -73,6 +73,29 @@ class ForwardRollout:
         return gather_padded(traj, self.ns_global, self.world_size)
 
 
+def save_X_traj(traj: torch.Tensor, save_dir: str, epistemic_idx: int, chunk: Optional[int] = None) -> list:
+    """On-disk hand-off of benchmarking/simulate_forward_sampling_car.py:157-161: ``data_X_traj_<k>.pkl`` = pickle of the
+    numpy array (ns, nx, H+1), which generate_convex_hull.py:77-84 and the plotting scripts load and ``np.vstack``.  The
+    reference writes one file per job of 4000 samples (2500 jobs); here ONE rollout holds every sample, so ``chunk``
+    splits it into files ``k, k+1, ...`` of ``chunk`` samples each for consumers that expect that many (default: one
+    file).  The copy goes through one pinned staging buffer.  Returns the paths written."""
+    import os
+    import pickle
+    ns = traj.shape[0]
+    chunk = ns if not chunk else int(chunk)
+    host = torch.empty(traj.shape, dtype=traj.dtype, pin_memory=traj.is_cuda)
+    host.copy_(traj, non_blocking=False)
+    arr = host.numpy()
+    os.makedirs(save_dir, exist_ok=True)
+    paths = []
+    for i, lo in enumerate(range(0, ns, chunk)):
+        path = os.path.join(save_dir, f"data_X_traj_{epistemic_idx + i}.pkl")
+        with open(path, "wb") as f:
+            pickle.dump(np.ascontiguousarray(arr[lo:lo + chunk]), f)
+        paths.append(path)
+    return paths
+
+
 def gather_padded(local: torch.Tensor, ns_global: int, world_size: int) -> torch.Tensor:
     """All-gather of per-rank sample blocks (shard_bounds layout; the last shard may be shorter) into the
     single-process layout: row s of the result is global sample s on every rank."""

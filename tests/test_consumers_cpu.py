@@ -1,5 +1,7 @@
 """CPU: the oracle restatements of the rows either side of the hot path (oracle/consumers_ref.py) and the library's
 host-only hull helper (gpmpc_hull2d has no device work, so it runs here)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -86,3 +88,19 @@ def test_traj_stats_and_hull_oracle_shapes():
     assert lo.shape == hi.shape == dev.shape == (4, 6) and (dev >= 0).all() and (lo <= hi).all()
     hulls = ref.stage_hulls(X)
     assert len(hulls) == 6 and all(len(h) >= 3 for h in hulls)
+
+
+def test_save_X_traj_matches_the_reference_pickle_format(tmp_path):
+    """data_X_traj_<k>.pkl (simulate_forward_sampling_car.py:157-161) as generate_convex_hull.py:77-84 reads it back."""
+    import pickle
+    from sampling_gpmpc_b200.rollout import save_X_traj
+    traj = torch.arange(10 * 4 * 6, dtype=torch.float64).reshape(10, 4, 6)
+    (p,) = save_X_traj(traj, str(tmp_path), 3)
+    assert p.endswith("data_X_traj_3.pkl")
+    with open(p, "rb") as f:
+        back = pickle.load(f)
+    assert isinstance(back, np.ndarray) and back.dtype == np.float64 and np.array_equal(back, traj.numpy())
+    paths = save_X_traj(traj, str(tmp_path / "jobs"), 0, chunk=4)
+    assert [os.path.basename(q) for q in paths] == ["data_X_traj_0.pkl", "data_X_traj_1.pkl", "data_X_traj_2.pkl"]
+    parts = [pickle.load(open(q, "rb")) for q in paths]
+    assert np.array_equal(np.vstack(parts), traj.numpy())  # the consumer's np.vstack over the job files
