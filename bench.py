@@ -283,10 +283,9 @@ def run_ours(args):
 
     # ---- end-to-end through the public call with HOST buffers ("e2e") ----------------------------------
     def e2e_step():
-        eps_d = eps_host.to(device, non_blocking=True)     # this step's base samples, pinned host -> device
-        u_d = u_host.to(device, non_blocking=True)
-        fr.run(u_d, eps_d, traj)
-        traj_host.copy_(traj, non_blocking=True)            # the step's result, device -> pinned host
+        # the public host-buffer call: base samples pinned host -> device (streamed in behind the first horizon
+        # steps), rollout, trajectories device -> pinned host
+        fr.run_from_host(u_host, eps_host, traj, traj_host)
     for _ in range(2):
         e2e_step()
     barrier()

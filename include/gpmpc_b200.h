@@ -161,6 +161,15 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
                   const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
                   void* stream);
 
+/* The same rollout with the base samples still in flight from the host: eps_ready HOST array of n_steps CUDA event
+ * handles (cudaEvent_t, NULL entries allowed, the array itself may be NULL); before step t is queued the stream waits
+ * for eps_ready[t], recorded by the caller on its copy stream after the host-to-device copy of eps[t] was queued.
+ * The upload of epistimic_random_vector (simulate_forward_sampling_car.py:84-90, 126) then overlaps the horizon
+ * instead of preceding it. */
+int gpmpc_rollout_gated(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
+                        const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
+                        void* const* eps_ready, void* stream);
+
 /* ---- the data-set rules around the draw (Dyn_gp_min_data_dist >= 0) ------------------------------ */
 
 /* sample_gp's min-distance overwrite + truncation (src/agent.py:666-708), applied to y DEVICE [B*H*T] in place:

@@ -654,6 +654,12 @@ int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, cons
 int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
                   const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
                   void* stream_) {
+  return gpmpc_rollout_gated(h, env, x0, u_ff, eps, opts, n_steps, traj, nullptr, stream_);
+}
+
+int gpmpc_rollout_gated(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
+                        const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
+                        void* const* eps_ready, void* stream_) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!env || !x0 || !u_ff || !eps || !opts || !traj || n_steps < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
@@ -691,6 +697,8 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
     h->ev_used = 0;
   }
   for (int t = 0; t < n_steps; ++t) {
+    // base samples of step t may still be on their way from the host (copy stream): wait for their event here
+    if (eps_ready && eps_ready[t]) CUDA_TRY(h, cudaStreamWaitEvent(stream, (cudaEvent_t)eps_ready[t], 0));
     if (h->timing) CUDA_TRY(h, cudaEventRecord(h->ev[2 * t], stream));
     rc = gpmpc_step(h, h->r_xstar, eps + (size_t)t * eps_stride, opts, nullptr, nullptr, h->r_y, nullptr, stream);
     if (rc) return rc;

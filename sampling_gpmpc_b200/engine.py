@@ -56,6 +56,8 @@ ABI = {
     "gpmpc_step": (C.c_int, [_P, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _D, _D, _P]),
     "gpmpc_assemble": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _I, _D, _P]),
     "gpmpc_rollout": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _P]),
+    "gpmpc_rollout_gated": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.POINTER(GpmpcSampleOpts), _I, _D,
+                                      C.POINTER(C.c_void_p), _P]),
     "gpmpc_min_dist_overwrite": (C.c_int, [_P, _D, _I, _D, _D, C.c_double, C.c_double, _D, _P]),
     "gpmpc_filter_new_points": (C.c_int, [_P, _D, _I, C.c_double, _I, _D, _D, _P]),
     "gpmpc_pack_plin": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, _I, _I, _I, _D, _P]),
@@ -288,6 +290,36 @@ class GPEngine:
         rc = self.lib.gpmpc_rollout(self.h, C.byref(env), _ptr(x0), _ptr(u_ff), _ptr(eps), C.byref(opts), n_steps,
                                     _ptr(traj), _stream())
         self._check(rc, "gpmpc_rollout")
+        return traj
+
+    def rollout_from_host(self, env: GpmpcEnv, x0: torch.Tensor, u_ff: torch.Tensor, eps_host: torch.Tensor,
+                          opts: GpmpcSampleOpts, eps_dev: torch.Tensor, copy_stream: "torch.cuda.Stream",
+                          traj: Optional[torch.Tensor] = None, chunk_steps: int = 5) -> torch.Tensor:
+        """The rollout with the base samples in PINNED HOST memory: eps_host (n_steps, B*T) is copied to eps_dev
+        (same shape, device) in chunks of `chunk_steps` horizon steps on `copy_stream`; step t waits only for the event
+        of its own chunk (gpmpc_rollout_gated), so all but the first chunk's upload overlaps the horizon."""
+        n_steps = u_ff.shape[0]
+        assert eps_host.is_pinned() and eps_host.shape == eps_dev.shape == (n_steps, self.B * self.T)
+        x0 = x0.to(self.device, torch.float64).contiguous()
+        u_ff = u_ff.to(self.device, torch.float64, non_blocking=True).contiguous()
+        if traj is None:
+            traj = torch.empty((self.ns, env.nx, n_steps + 1), dtype=torch.float64, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        copy_stream.wait_stream(cur)  # eps_dev may still be read by work queued earlier on the compute stream
+        ready = (C.c_void_p * n_steps)()
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for t0 in range(0, n_steps, chunk_steps):
+                t1 = min(n_steps, t0 + chunk_steps)
+                eps_dev[t0:t1].copy_(eps_host[t0:t1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+                ready[t0] = ev.cuda_event
+        rc = self.lib.gpmpc_rollout_gated(self.h, C.byref(env), _ptr(x0), _ptr(u_ff), _ptr(eps_dev), C.byref(opts),
+                                          n_steps, _ptr(traj), ready, _stream())
+        self._check(rc, "gpmpc_rollout_gated")
+        self._keep_events = events  # alive until the next call (the waits are already queued)
         return traj
 
     # ---- data-set rules, p_lin, trajectory consumers ---------------------------------------------

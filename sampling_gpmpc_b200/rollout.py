@@ -68,6 +68,24 @@ class ForwardRollout:
         self.engine.reset_hallucinated()
         return self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
 
+    def run_from_host(self, u_ff: torch.Tensor, eps_host: torch.Tensor, traj: Optional[torch.Tensor] = None,
+                      traj_host: Optional[torch.Tensor] = None, chunk_steps: int = 5) -> torch.Tensor:
+        """`run` for base samples that live in pinned host memory (the reference generates them on the host,
+        src/agent.py:76-104): eps_host (steps, ns, g_ny, 1, T) pinned.  The upload streams in chunks of `chunk_steps`
+        horizon steps on a side stream while the rollout runs; with `traj_host` (pinned) the trajectories are copied
+        back behind the last step.  Returns the device trajectories (ns, nx, steps+1)."""
+        steps = u_ff.shape[0]
+        eps2 = eps_host.reshape(steps, -1)
+        if getattr(self, "_eps_dev", None) is None or self._eps_dev.shape != eps2.shape:
+            self._eps_dev = torch.empty(eps2.shape, dtype=F64, device=self.device)
+            self._copy_stream = torch.cuda.Stream(self.device)
+        self.engine.reset_hallucinated()
+        out = self.engine.rollout_from_host(self.env, self.x0, u_ff, eps2, self.opts, self._eps_dev, self._copy_stream,
+                                            traj, chunk_steps)
+        if traj_host is not None:
+            traj_host.copy_(out, non_blocking=True)
+        return out
+
     def all_gather_trajectories(self, traj: torch.Tensor) -> torch.Tensor:
         """(ns_local, nx, steps+1) per rank -> (ns_global, nx, steps+1) on every rank: one NCCL all-gather."""
         return gather_padded(traj, self.ns_global, self.world_size)

@@ -241,6 +241,28 @@ def test_shared_factor_step_matches_block_kernels(d, T, n_real, grad_obs, ns):
     assert worst <= 1.0, f"shared-factor step off by {worst:.3g} x tolerance"
 
 
+def test_rollout_from_pinned_host_buffers_is_bit_identical():
+    """ForwardRollout.run_from_host (gpmpc_rollout_gated: base samples streamed in from pinned host memory in chunks,
+    every step waiting only for its own chunk's event) == run() on device-resident inputs, for chunk sizes that do and
+    do not divide the horizon; twice in a row (the staging buffer is reused while the copy stream is still busy)."""
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    ns, steps = 3000, 23
+    params = configs.car_residual_fs(num_dyn_samples=ns, steps=steps, with_derivatives=True)
+    g = torch.Generator().manual_seed(3)
+    fr = ForwardRollout(params, condition=True)
+    u = (0.2 * torch.randn(steps, 2, generator=g, dtype=torch.float64)).pin_memory()
+    for rep, chunk in enumerate((5, 23, 1, 7)):
+        eps = torch.randn(steps, ns, 3, 1, 3, generator=g, dtype=torch.float64).clamp(-3, 3).pin_memory()
+        want = fr.run(u.cuda(), eps.cuda()).clone()
+        host = torch.empty(want.shape, dtype=torch.float64).pin_memory()
+        got = fr.run_from_host(u, eps, traj_host=host, chunk_steps=chunk)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), f"chunk {chunk}"
+        assert torch.equal(host, want.cpu())
+    assert fr.engine.status() == 0
+
+
 def test_pendulum2d_rollout_matches_oracle_refit():
     """True-reachable-set shape (benchmarking/simulate_true_reachable_set.py:179-259): real data WITH derivatives
     (m = 180), d = 3, T = 4, g_ny = 2, zero-variance switch on, no feedback."""
