@@ -235,6 +235,10 @@ int64_t gpmpc_launch_count(const gpmpc_handle* h);
 /* Per-launch timing of the fused step kernel inside gpmpc_rollout: when on, a CUDA event pair brackets every
  * step-kernel launch on the rollout's stream; gpmpc_rollout_kernel_ms waits for the last one and returns the
  * summed device time and the number of launches of the last rollout (bench.py's roofline.achieved). */
+/* Which kernel serves gpmpc_posterior: mma != 0 (default) the FP64 tensor-core kernel (k_posterior_mma: shared rows by
+ * the explicit inverse of L_oo, own rows by 8-row sub-panels), mma == 0 the scalar forward-substitution kernel -- the
+ * same posterior by independent arithmetic, kept as the reference semantics for the parity tests. */
+int gpmpc_set_block_kernels(gpmpc_handle* h, int32_t mma);
 int gpmpc_set_timing(gpmpc_handle* h, int32_t on);
 int gpmpc_rollout_kernel_ms(gpmpc_handle* h, double* total_ms, int32_t* launches);
 const char* gpmpc_version(void);

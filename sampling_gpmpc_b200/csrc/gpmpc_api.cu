@@ -13,6 +13,7 @@
 #include "gpmpc_block.cuh"
 #include "gpmpc_post.cuh"
 #include "gpmpc_step.cuh"
+#include "gpmpc_block_mma.cuh"
 
 namespace {
 std::string g_create_error;
@@ -46,7 +47,10 @@ struct gpmpc_handle {
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
   // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
   int wo_min_m = 1;
-  int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
+  int wo_max_nb = 3;
+  // SQP-mode model call: tensor-core kernel k_posterior_mma (default) or the scalar substitution kernel k_posterior
+  // (gpmpc_set_block_kernels / GPMPC_BLOCK_SCALAR=1: the independent reference semantics the parity tests compare with)
+  bool block_mma = true;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   size_t wo_count = 0;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
@@ -164,6 +168,34 @@ static void count_work(gpmpc_handle* h, int H, bool append) {
   h->last_flops = flops * B;
 }
 
+template <int D, int T>
+static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const double* x, int H, double* mean, double* var,
+                                const double* eps, const gpmpc_sample_opts& o, double* y, int* jl, cudaStream_t stream) {
+  auto kern = k_posterior_mma<D, T>;
+  const int smem = PM_SLAB * 8 * (int)sizeof(double);
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<st.B, PM_THREADS, smem, stream>>>(st, x, H, mean, var, eps, o, y, jl);
+  return GPMPC_OK;
+}
+
+static int dispatch_posterior_mma(gpmpc_handle* h, const DevState& st, const double* x, int H, double* mean,
+                                  double* var, const double* eps, const gpmpc_sample_opts& o, double* y, int* jl,
+                                  cudaStream_t stream) {
+#define PM_CASE(D_)                                                                                       \
+  case D_:                                                                                                \
+    return st.T == 1 ? launch_posterior_mma<D_, 1>(h, st, x, H, mean, var, eps, o, y, jl, stream)         \
+                     : launch_posterior_mma<D_, D_ + 1>(h, st, x, H, mean, var, eps, o, y, jl, stream);
+  switch (st.d) {
+    PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) PM_CASE(5) PM_CASE(6)
+  }
+#undef PM_CASE
+  return fail(h, GPMPC_ERR_ARG, "unsupported d");
+}
+
 extern "C" {
 
 const char* gpmpc_version(void) { return "gpmpc_b200 0.1 (sm_100a)"; }
@@ -185,6 +217,7 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   cudaDeviceGetAttribute(&h->max_dyn_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   if (const char* e = getenv("GPMPC_WO_MIN_M")) h->wo_min_m = atoi(e);
+  if (const char* e = getenv("GPMPC_BLOCK_SCALAR")) h->block_mma = atoi(e) == 0;
   if (const char* e = getenv("GPMPC_WO_MAX_NB")) h->wo_max_nb = std::min(3, std::max(1, atoi(e)));
   DevState& st = h->st;
   st.ns = dims->ns; st.g_ny = dims->g_ny; st.d = dims->d; st.T = dims->T; st.n_real = dims->n_real;
@@ -366,7 +399,12 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
-  k_posterior<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, x, H, mean, var, eps, o, y, jitter_level);
+  if (h->block_mma && H * st.T <= 8 * (PM_THREADS / 32) * PM_MAXOWN) {
+    rc = dispatch_posterior_mma(h, st, x, H, mean, var, eps, o, y, jitter_level, (cudaStream_t)stream);
+    if (rc) return rc;
+  } else {
+    k_posterior<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, x, H, mean, var, eps, o, y, jitter_level);
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   h->cache_version = h->factor_version;
@@ -958,6 +996,12 @@ int gpmpc_last_launch_work(const gpmpc_handle* h, double* bytes, double* flops) 
 }
 
 int64_t gpmpc_launch_count(const gpmpc_handle* h) { return h ? h->launches : -1; }
+
+int gpmpc_set_block_kernels(gpmpc_handle* h, int32_t mma) {
+  if (!h) return fail(h, GPMPC_ERR_ARG, "null handle");
+  h->block_mma = mma != 0;
+  return GPMPC_OK;
+}
 
 int gpmpc_set_timing(gpmpc_handle* h, int32_t on) {
   if (!h) return GPMPC_ERR_ARG;

@@ -73,6 +73,7 @@ ABI = {
     "gpmpc_last_launch_work": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "gpmpc_launch_count": (C.c_int64, [_P]),
     "gpmpc_set_timing": (C.c_int, [_P, _I]),
+    "gpmpc_set_block_kernels": (C.c_int, [_P, _I]),
     "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
 }
@@ -430,6 +431,10 @@ class GPEngine:
         b, f = C.c_double(0), C.c_double(0)
         self.lib.gpmpc_last_launch_work(self.h, C.byref(b), C.byref(f))
         return b.value, f.value
+
+    def set_block_kernels(self, mma: bool):
+        """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
+        self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
 
     def set_timing(self, on: bool):
         self._check(self.lib.gpmpc_set_timing(self.h, int(on)), "gpmpc_set_timing")
