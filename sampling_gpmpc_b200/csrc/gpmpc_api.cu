@@ -168,17 +168,46 @@ static void count_work(gpmpc_handle* h, int H, bool append) {
   h->last_flops = flops * B;
 }
 
+// dynamic shared memory for the packed q x q Cholesky of the draw / append (0: does not fit, global-memory path)
+static size_t tri_bytes(gpmpc_handle* h, int q) {
+  const size_t b = (size_t)q * (q + 1) / 2 * sizeof(double);
+  return b + 1024 <= (size_t)h->max_dyn_smem ? b : 0;
+}
+
+static int configure_block_smem(gpmpc_handle* h) {
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(h, cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_append, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
+    configured = true;
+  }
+  return GPMPC_OK;
+}
+
 template <int D, int T>
 static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const double* x, int H, double* mean, double* var,
                                 const double* eps, const gpmpc_sample_opts& o, double* y, int* jl, cudaStream_t stream) {
-  auto kern = k_posterior_mma<D, T>;
-  const int smem = PM_SLAB * 8 * (int)sizeof(double);
+  auto solve = k_pm_solve<D, T>;
+  auto gram = k_pm_gram<T>;
+  const int q = H * st.T, QB = (q + 7) / 8;
+  const size_t slab = (size_t)PM_SLAB * 8 * sizeof(double);
   static bool configured = false;  // per instantiation
   if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_pm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
     configured = true;
   }
-  kern<<<st.B, PM_THREADS, smem, stream>>>(st, x, H, mean, var, eps, o, y, jl);
+  // the column blocks of one element over ceil(QB / 4) CTAs; the Gram tiles over enough CTAs to fill the GPU
+  dim3 gs(st.B, (QB + PM_WARPS - 1) / PM_WARPS);
+  solve<<<gs, PM_WARPS * 32, slab, stream>>>(st, x, H);
+  const int tiles = QB * (QB + 1) / 2 + QB;
+  const int want = std::max(1, std::min((tiles + PM_WARPS - 1) / PM_WARPS, (4 * h->num_sms + st.B - 1) / st.B));
+  dim3 gg(st.B, want);
+  gram<<<gg, PM_WARPS * 32, 0, stream>>>(st, x, H);
+  size_t tri = eps ? tri_bytes(h, q) : 0;
+  if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;
+  k_pm_finish<<<st.B, BLK_THREADS, tri, stream>>>(st, H, mean, var, eps, o, y, jl, tri ? 1 : 0);
+  h->launches += 2;
   return GPMPC_OK;
 }
 
@@ -399,7 +428,7 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
-  if (h->block_mma && H * st.T <= 8 * (PM_THREADS / 32) * PM_MAXOWN) {
+  if (h->block_mma && H * st.T <= PM_MAX_Q) {
     rc = dispatch_posterior_mma(h, st, x, H, mean, var, eps, o, y, jitter_level, (cudaStream_t)stream);
     if (rc) return rc;
   } else {
@@ -422,7 +451,11 @@ int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* op
     return fail(h, GPMPC_ERR_STATE, "gpmpc_sample needs a preceding gpmpc_posterior on the current factor");
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (h->cache_H * st.T);
-  k_sample<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, h->cache_H, eps, *opts, y, jitter_level);
+  rc = configure_block_smem(h);
+  if (rc) return rc;
+  size_t tri = tri_bytes(h, h->cache_H * st.T);
+  if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;
+  k_sample<<<st.B, BLK_THREADS, tri, (cudaStream_t)stream>>>(st, h->cache_H, eps, *opts, y, jitter_level, tri ? 1 : 0);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
@@ -460,7 +493,11 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   const int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
-  k_append<<<st.B, BLK_THREADS, 0, stream>>>(st, x, y, d_act, H, st.np, reuse, grow ? 1 : 0);
+  rc = configure_block_smem(h);
+  if (rc) return rc;
+  size_t tri = grow ? tri_bytes(h, H * st.T) : 0;
+  if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;  // k_append also holds 2 KB of static shared memory
+  k_append<<<st.B, BLK_THREADS, tri, stream>>>(st, x, y, d_act, H, st.np, reuse, grow ? 1 : 0, tri ? 1 : 0);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   if (d_act) CUDA_TRY(h, cudaStreamSynchronize(stream));  // caller may reuse point_active's host memory

@@ -36,6 +36,31 @@ __device__ int block_cholesky(double* A, int n, int ld) {
   return 0;
 }
 
+// The same factorisation on a PACKED lower triangle in shared memory (P[r(r+1)/2 + s], s <= r): the q x q matrices of
+// the SQP-mode draw / append are latency bound in global memory (three L2 round trips per pivot); in shared memory a
+// pivot step costs a few hundred cycles.  Same pivot test, same return value.
+__device__ int block_cholesky_packed(double* P, int n) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;  // 16 columns x (nt / 16) rows of the trailing block per pass
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    const double akk = P[k * (k + 1) / 2 + k];
+    if (!(akk > 0.0)) return k + 1;
+    const double lkk = sqrt(akk);
+    __syncthreads();
+    if (tid == 0) P[k * (k + 1) / 2 + k] = lkk;
+    for (int i = k + 1 + tid; i < n; i += nt) P[i * (i + 1) / 2 + k] /= lkk;
+    __syncthreads();
+    for (int i = k + 1 + ty; i < n; i += ny) {
+      const int ro = i * (i + 1) / 2;
+      const double lik = P[ro + k];
+      for (int cc = k + 1 + tx; cc <= i; cc += 16) P[ro + cc] -= lik * P[cc * (cc + 1) / 2 + k];
+    }
+  }
+  __syncthreads();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K0: shared real-data block.  grid = g_ny, block = BLK_THREADS.
 // ------------------------------------------------------------------------------------------------
@@ -171,8 +196,10 @@ __device__ void block_posterior(const DevState& st, int b, const double* __restr
 
 // chol(Sigma*) with the psd_safe_cholesky ladder, y = mu + L eps, then sample_gp's post-processing
 // (zero-variance -> mean, truncation to mean +- beta sqrt(var); src/agent.py:646-663,701-708).
+// tri != NULL: shared-memory scratch of at least q(q+1)/2 doubles for the factorisation (packed lower triangle).
 __device__ void block_sample(const DevState& st, int b, int H, const double* __restrict__ eps,
-                             gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level) {
+                             gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level,
+                             double* tri = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int T = st.T, q = H * T;
   const double* S = st.S + (size_t)b * q * q;
@@ -188,13 +215,21 @@ __device__ void block_sample(const DevState& st, int b, int H, const double* __r
   } else {
     for (;;) {
       double add = level == 0 ? 0.0 : st.jitter * pow(10.0, (double)(level - 1));
-      for (int idx = tid; idx < q * q; idx += nt) {
-        int r = idx / q, s = idx % q;
-        double v = s <= r ? S[idx] : 0.0;
-        if (s == r) v += add;
-        C[idx] = v;
+      int info;
+      if (tri) {
+        __syncthreads();
+        for (int r = tid; r < q; r += nt)  // row r of the lower triangle is contiguous in both layouts
+          for (int s = 0; s <= r; ++s) tri[r * (r + 1) / 2 + s] = S[(size_t)r * q + s] + (s == r ? add : 0.0);
+        info = block_cholesky_packed(tri, q);
+      } else {
+        for (int idx = tid; idx < q * q; idx += nt) {
+          int r = idx / q, s = idx % q;
+          double v = s <= r ? S[idx] : 0.0;
+          if (s == r) v += add;
+          C[idx] = v;
+        }
+        info = block_cholesky(C, q, q);
       }
-      int info = block_cholesky(C, q, q);
       if (info == 0) break;
       // NaN anywhere makes GPyTorch raise NanError instead of climbing the ladder
       if (level == GP_MAX_TRIES) {
@@ -209,7 +244,9 @@ __device__ void block_sample(const DevState& st, int b, int H, const double* __r
   if (tid == 0 && jitter_level) jitter_level[b] = level;
   for (int r = tid; r < q; r += nt) {
     double acc = mu[r];
-    if (level < 4)
+    if (level < 4 && tri && q > 1)
+      for (int s = 0; s <= r; ++s) acc += tri[r * (r + 1) / 2 + s] * e[s];
+    else if (level < 4)
       for (int s = 0; s <= r; ++s) acc += C[(size_t)r * q + s] * e[s];
     else
       acc = nan("");
@@ -251,10 +288,12 @@ k_posterior(DevState st, const double* __restrict__ x, int H, double* __restrict
   if (eps) block_sample(st, b, H, eps, opts, y, jitter_level);
 }
 
+// tri_ok: the launch carries q(q+1)/2 doubles of dynamic shared memory for the packed Cholesky
 __global__ void __launch_bounds__(BLK_THREADS)
 k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts opts, double* __restrict__ y,
-         int* __restrict__ jitter_level) {
-  block_sample(st, blockIdx.x, H, eps, opts, y, jitter_level);
+         int* __restrict__ jitter_level, int tri_ok) {
+  extern __shared__ __align__(16) double dyn_tri[];
+  block_sample(st, blockIdx.x, H, eps, opts, y, jitter_level, tri_ok ? dyn_tri : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -265,7 +304,8 @@ k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts o
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK_THREADS)
 k_append(DevState st, const double* __restrict__ x, const double* __restrict__ ylab,
-         const unsigned char* __restrict__ active, int H, int pt_base, int reuse, int grow_factor) {
+         const unsigned char* __restrict__ active, int H, int pt_base, int reuse, int grow_factor, int tri_ok) {
+  extern __shared__ __align__(16) double dyn_tri[];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int j = b % st.g_ny, d = st.d, T = st.T, q = H * T;
   const int n = st.m + st.c;
@@ -314,16 +354,28 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   double* C = st.C + (size_t)b * q * q;  // used as qa x qa, leading dim qa
   const double* mu = st.mu + (size_t)b * q;
   const double* noise = st.noise + j * T;
-  for (int idx = tid; idx < qa * qa; idx += nt) {
-    int rr = idx / qa, ss = idx % qa;
-    double v = 0.0;
-    if (ss <= rr) {
-      v = S[(size_t)sh_act[rr] * q + sh_act[ss]];
-      if (ss == rr) v += noise[sh_act[rr] % T];
+  int info;
+  if (tri_ok) {
+    for (int rr = tid; rr < qa; rr += nt)
+      for (int ss = 0; ss <= rr; ++ss)
+        dyn_tri[rr * (rr + 1) / 2 + ss] = S[(size_t)sh_act[rr] * q + sh_act[ss]] + (ss == rr ? noise[sh_act[rr] % T] : 0.0);
+    info = block_cholesky_packed(dyn_tri, qa);
+    if (info == 0)  // the rest of the kernel reads the factor from C (row-major, leading dim qa)
+      for (int rr = tid; rr < qa; rr += nt)
+        for (int ss = 0; ss <= rr; ++ss) C[(size_t)rr * qa + ss] = dyn_tri[rr * (rr + 1) / 2 + ss];
+    __syncthreads();
+  } else {
+    for (int idx = tid; idx < qa * qa; idx += nt) {
+      int rr = idx / qa, ss = idx % qa;
+      double v = 0.0;
+      if (ss <= rr) {
+        v = S[(size_t)sh_act[rr] * q + sh_act[ss]];
+        if (ss == rr) v += noise[sh_act[rr] % T];
+      }
+      C[idx] = v;
     }
-    C[idx] = v;
+    info = block_cholesky(C, qa, qa);
   }
-  int info = block_cholesky(C, qa, qa);
   if (info != 0) {
     if (tid == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
     return;
@@ -351,7 +403,9 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     }
   }
   __syncthreads();
-  if (tid < 32) warp_update_dinv(st, b, st.c, st.c + qa, tid);
+  // transposed inverses of the 8 x 8 diagonal blocks the new rows touch: the blocks are independent, one warp each
+  for (int kb = (st.c & ~7) + 8 * (tid >> 5); kb < st.c + qa; kb += 8 * (nt >> 5))
+    warp_update_dinv(st, b, max(kb, st.c), min(kb + 8, st.c + qa), tid & 31);
   if (b == 0)
     for (int rr = tid; rr < qa; rr += nt) {
       st.hobs_pt[st.c + rr] = pt_base + sh_act[rr] / T;

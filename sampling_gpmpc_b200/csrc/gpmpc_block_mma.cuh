@@ -4,60 +4,67 @@
 // triangular solve W = L^{-1} K_{o*} with q right-hand sides (q n^2 / 2 MACs) and by Sigma* = K** - W^T W (q^2 n / 2):
 // contraction bound once the hallucinated set has grown over a few SQP iterations (car-residual config: q = 150, n up
 // to several thousand), where the scalar kernel k_posterior (gpmpc_block.cuh, kept as the substitution-based reference
-// semantics) reaches ~1 % of the FP64 peak.  One CTA per batch element, 8 warps, each warp owns 8-column blocks of the
-// right-hand sides (columns never interact, so no CTA-wide synchronisation is needed for W itself):
+// semantics) reaches ~1 % of the FP64 peak.  The right-hand sides are cut into 8-column blocks; columns never interact
+// in the solve, so a warp owns ONE block for the whole solve and the blocks of an element are spread over several
+// CTAs (grid = elements x splits: SQP mode has only tens to hundreds of elements, fewer than SMs):
+//  k_pm_solve (grid B x ceil(QB / 4), 4 warps):
 //   0  K_{o*}: one exp per (training point, test point) pair, the T x T derivative block from it
 //   1  shared rows: W_o = inv(L_oo) K_o, tile-rows last to first, in place (as K1 phase B)
 //   2  own rows, left-looking over the 8-row sub-panels of the element's factor stream: the sub-panel's k-blocks are
 //      staged in shared memory once (all column blocks need the same A operand), every warp runs the DMMA chain
 //      dot = L[rows][cols < n_off] W over its column blocks with W read back through L2, rhs = K - dot, and the 8 x 8
 //      diagonal block is applied as inv(D) rhs (two more DMMAs; inverse kept in the block's upper triangle)
+//  k_pm_gram (grid B x splits, 4 warps):
 //   3  Sigma* = K** - W^T W by 8 x 8 output tiles (A and B fragments are the same access pattern on W), mean = W^T beta
-// then the draw / post-processing of gpmpc_block.cuh (block_sample) in the same launch.
+//  k_pm_finish (grid B): mean / variance out, then the draw / post-processing of gpmpc_block.cuh (block_sample, packed
+//  Cholesky in shared memory).
 // W [n][q], S [q][q], mu [q], xc keep the layouts of the scalar kernel: k_sample / k_append consume either.
 #pragma once
 #include "gpmpc_block.cuh"
 #include "gpmpc_step.cuh"
 
-#define PM_THREADS 256
-#define PM_MAXOWN 4     // column blocks per warp (q <= 8 * 8 * 4 = 256 test scalars per call)
-#define PM_SLAB 1024    // storage columns of a sub-panel staged per pass (64 KB of shared memory)
+#define PM_WARPS 4       // warps per CTA = column blocks per CTA of k_pm_solve
+#define PM_SLAB 1024     // storage columns of a sub-panel staged per pass (64 KB of shared memory)
+#define PM_MAX_Q 2048    // test scalars per call served by this path (QB <= 256 column blocks)
 
 template <int D, int T>
-__global__ void __launch_bounds__(PM_THREADS, 2)
-k_posterior_mma(DevState st, const double* __restrict__ x, int H, double* __restrict__ mean,
-                double* __restrict__ var, const double* __restrict__ eps, gpmpc_sample_opts opts,
-                double* __restrict__ y, int* __restrict__ jitter_level) {
+__global__ void __launch_bounds__(PM_WARPS * 32, 3)
+k_pm_solve(DevState st, const double* __restrict__ x, int H) {
   extern __shared__ __align__(128) double sA[];  // [PM_SLAB * 8] one slab of a sub-panel (k-block layout)
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int j = b % st.g_ny;
-  const int m = st.m, mo = st.mo, c = st.c, n = m + c, q = H * T;
+  const int m = st.m, mo = st.mo, c = st.c, q = H * T;
   const int QB = (q + 7) >> 3;
   double* W = st.W + (size_t)b * st.W_stride;
-  double* S = st.S + (size_t)b * q * q;
-  double* mu = st.mu + (size_t)b * q;
-  double* xc = st.xc + (size_t)b * H * D;
   const double* xb = x + (size_t)b * H * D;
   double il[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j * D + a];
   const double os = st.os[j];
 
-  // ---- 0: kernel matrix ---------------------------------------------------------------------------------------
-  for (int idx = tid; idx < H * D; idx += nt) xc[idx] = xb[idx];
-  for (int idx = tid; idx < m * H; idx += nt) {
-    const int i = idx / H, h = idx - i * H;
+  // ---- 0: kernel matrix, this CTA's columns [c_lo, c_hi) -----------------------------------------------------
+  const int c_lo = blockIdx.y * PM_WARPS * 8, c_hi = min(q, c_lo + PM_WARPS * 8);
+  const int h_lo = c_lo / T, h_n = (c_hi - 1) / T - h_lo + 1;  // test points touching those columns
+  if (blockIdx.y == 0) {
+    double* xc = st.xc + (size_t)b * H * D;
+    for (int idx = tid; idx < H * D; idx += nt) xc[idx] = xb[idx];
+  }
+  for (int idx = tid; idx < m * h_n; idx += nt) {
+    const int i = idx / h_n, h = h_lo + idx - i * h_n;
     double xs[D], out[T];
 #pragma unroll
     for (int a = 0; a < D; ++a) xs[a] = xb[h * D + a];
     kernel_row<D, T>(st.Xr + (size_t)st.obs_pt[i] * D, st.obs_task[i], xs, il, os, out);
 #pragma unroll
-    for (int tb = 0; tb < T; ++tb) W[(size_t)i * q + h * T + tb] = out[tb];
+    for (int tb = 0; tb < T; ++tb) {
+      const int col = h * T + tb;
+      if (col >= c_lo && col < c_hi) W[(size_t)i * q + col] = out[tb];
+    }
   }
-  for (int idx = tid; idx < st.np * H; idx += nt) {
-    const int p = idx / H, h = idx - p * H;
+  for (int idx = tid; idx < st.np * h_n; idx += nt) {
+    const int p = idx / h_n, h = h_lo + idx - p * h_n;
     const int r0 = st.hrow0[p];
     if (r0 < 0) continue;  // recorded but masked point: no factor rows
     double xa[D], xs[D], kb[T][T];
@@ -70,41 +77,42 @@ k_posterior_mma(DevState st, const double* __restrict__ x, int H, double* __rest
 #pragma unroll
     for (int ta = 0; ta < T; ++ta)
 #pragma unroll
-      for (int tb = 0; tb < T; ++tb) W[(size_t)(m + r0 + ta) * q + h * T + tb] = kb[ta][tb];
+      for (int tb = 0; tb < T; ++tb) {
+        const int col = h * T + tb;
+        if (col >= c_lo && col < c_hi) W[(size_t)(m + r0 + ta) * q + col] = kb[ta][tb];
+      }
   }
   __syncthreads();
 
-  // W row of storage column t (the factor's column order): t < m shared, [m, mo) padding (none), t >= mo own
   const uint32_t a_lane = a_lane_off(gid, tig);
-  int own[PM_MAXOWN];  // this warp's column blocks
-  int nown = 0;
-  for (int cb = warp; cb < QB && nown < PM_MAXOWN; cb += nw) own[nown++] = cb;
+  const int cb = blockIdx.y * PM_WARPS + warp;   // this warp's column block
+  const bool has = cb < QB;                      // (idle warps still take part in the CTA barriers below)
+  const int colB = cb * 8 + gid;                 // B-fragment column of this lane
+  const bool cok = has && colB < q;
+  const int colC = cb * 8 + 2 * tig;             // C-fragment columns colC, colC + 1
 
   // ---- 1: shared rows ------------------------------------------------------------------------------------------
-  {
+  if (has) {
     const int Pm = (m + 7) >> 3;
     const double* gL = st.LooP + (size_t)j * subpanel_off(Pm, 0);
-    for (int o = 0; o < nown; ++o) {
-      const int colB = own[o] * 8 + gid;  // B-fragment column of this lane
-      for (int p8 = Pm - 1; p8 >= 0; --p8) {
-        const double* ap = gL + subpanel_off(p8, 0) + a_lane / 8;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < 2 * p8 + 2; k += 2) {
-          const double a0 = __ldcg(ap + k * 32), a1 = __ldcg(ap + k * 32 + 32);
-          const int r0 = 4 * k + tig, r1 = r0 + 4;
-          const double b0 = (r0 < m && colB < q) ? __ldcg(W + (size_t)r0 * q + colB) : 0.0;
-          const double b1 = (r1 < m && colB < q) ? __ldcg(W + (size_t)r1 * q + colB) : 0.0;
-          dmma(acc[0], acc[1], a0, b0);
-          dmma(acc[2], acc[3], a1, b1);
-        }
-        // mma.sync: every lane's reads of this tile-row's inputs have completed
-        const int row = 8 * p8 + gid, col = own[o] * 8 + 2 * tig;
-        if (row < m) {
-          if (col < q) __stcg(W + (size_t)row * q + col, acc[0] + acc[2]);
-          if (col + 1 < q) __stcg(W + (size_t)row * q + col + 1, acc[1] + acc[3]);
-        }
-        __syncwarp();
+    for (int p8 = Pm - 1; p8 >= 0; --p8) {
+      const double* ap = gL + subpanel_off(p8, 0) + a_lane / 8;
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int k = 0; k < 2 * p8 + 2; k += 2) {
+        const double a0 = __ldcg(ap + k * 32), a1 = __ldcg(ap + k * 32 + 32);
+        const int r0 = 4 * k + tig, r1 = r0 + 4;
+        const double b0 = (r0 < m && cok) ? __ldcg(W + (size_t)r0 * q + colB) : 0.0;
+        const double b1 = (r1 < m && cok) ? __ldcg(W + (size_t)r1 * q + colB) : 0.0;
+        dmma(acc[0], acc[1], a0, b0);
+        dmma(acc[2], acc[3], a1, b1);
       }
+      // mma.sync: every lane's reads of this tile-row's inputs have completed
+      const int row = 8 * p8 + gid;
+      if (row < m) {
+        if (colC < q) __stcg(W + (size_t)row * q + colC, acc[0] + acc[2]);
+        if (colC + 1 < q) __stcg(W + (size_t)row * q + colC + 1, acc[1] + acc[3]);
+      }
+      __syncwarp();
     }
   }
 
@@ -112,15 +120,25 @@ k_posterior_mma(DevState st, const double* __restrict__ x, int H, double* __rest
   const int P8 = (c + 7) >> 3;
   const double* Le = st.Lh + (size_t)b * st.elem_stride;
   const uint32_t sA_s = smem_u32(sA);
+  // W row of storage column t (the factor's column order): t < m shared, [m, mo) padding (none), t >= mo own
+  auto load_b = [&](double (&bv)[8], int s0, int k, int k_end) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = s0 + 4 * (k + u) + tig;
+      const int r = t < m ? t : (t >= mo ? t - mo + m : -1);
+      bv[u] = (cok && r >= 0 && k + u < k_end) ? __ldcg(W + (size_t)r * q + colB) : 0.0;
+    }
+  };
   for (int p = 0; p < P8; ++p) {
     const int n_off = mo + 8 * p;           // off-diagonal storage columns of this sub-panel
     const int ncol = n_off + 8;             // + its diagonal block
     const double* gp = Le + subpanel_off(p, mo);
-    double acc[PM_MAXOWN][4];
-#pragma unroll
-    for (int o = 0; o < PM_MAXOWN; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = 0.0;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int s0 = 0; s0 < ncol; s0 += PM_SLAB) {
       const int s1 = min(ncol, s0 + PM_SLAB);
+      const int k_end = (min(s1, n_off) - s0) >> 2;  // k-steps of off-diagonal columns in this slab
+      double bn[8];
+      load_b(bn, s0, 0, k_end);  // W rows of earlier sub-panels: independent of the staging below
       __syncthreads();  // the previous slab is no longer read
       {
         const double2* src = (const double2*)(gp + (size_t)s0 * 8);
@@ -128,106 +146,118 @@ k_posterior_mma(DevState st, const double* __restrict__ x, int H, double* __rest
         for (int idx = tid; idx < (s1 - s0) * 4; idx += nt) dst[idx] = __ldcg(src + idx);
       }
       __syncthreads();
-      const int k_end = (min(s1, n_off) - s0) >> 2;  // k-steps of off-diagonal columns in this slab
+      // 8 k-steps per round; the W loads (L2 round trips) of the NEXT round are in flight during this round's chain
+      for (int k = 0; k < k_end; k += 8) {
+        double av[8], bv[8];
 #pragma unroll
-      for (int o = 0; o < PM_MAXOWN; ++o) {
-        if (o < nown) {
-          const int colB = own[o] * 8 + gid;
-          const bool cok = colB < q;
-          for (int k = 0; k < k_end; k += 2) {
-            const double a0 = lds(sA_s + k * 256 + a_lane), a1 = lds(sA_s + k * 256 + 256 + a_lane);
-            const int t0 = s0 + 4 * k + tig, t1 = t0 + 4;
-            // storage column -> W row
-            const int r0 = t0 < m ? t0 : (t0 >= mo ? t0 - mo + m : -1);
-            const int r1 = t1 < m ? t1 : (t1 >= mo ? t1 - mo + m : -1);
-            const double b0 = (cok && r0 >= 0) ? __ldcg(W + (size_t)r0 * q + colB) : 0.0;
-            const double b1 = (cok && r1 >= 0) ? __ldcg(W + (size_t)r1 * q + colB) : 0.0;
-            dmma(acc[o][0], acc[o][1], a0, b0);
-            dmma(acc[o][2], acc[o][3], a1, b1);
-          }
-        }
+        for (int u = 0; u < 8; ++u) bv[u] = bn[u];
+        if (k + 8 < k_end) load_b(bn, s0, k + 8, k_end);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) av[u] = k + u < k_end ? lds(sA_s + (k + u) * 256 + a_lane) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dmma(acc[2 * (u & 1)], acc[2 * (u & 1) + 1], av[u], bv[u]);
       }
-      if (s1 == ncol) {
+      if (s1 == ncol && has) {
         // the slab ends with the diagonal block: rhs = K - dot, w_blk = inv(D) rhs
         const uint32_t dblk = sA_s + (uint32_t)(n_off - s0) * 64;
         const int nvalid = min(8, c - 8 * p);
         double a0 = 0.0, a1 = 0.0;
         if (tig <= gid) a0 = lds(dblk + (uint32_t)sp_idx(gid, tig) * 8);
         if (tig + 4 <= gid) a1 = lds(dblk + (uint32_t)sp_idx(gid, tig + 4) * 8);
-#pragma unroll
-        for (int o = 0; o < PM_MAXOWN; ++o) {
-          if (o < nown) {
-            const int col = own[o] * 8 + 2 * tig;
-            double* wrow = W + (size_t)(m + 8 * p + gid) * q;
-            const bool live = gid < nvalid;
-            if (live) {
-              if (col < q) __stcg(wrow + col, __ldcg(wrow + col) - (acc[o][0] + acc[o][2]));
-              if (col + 1 < q) __stcg(wrow + col + 1, __ldcg(wrow + col + 1) - (acc[o][1] + acc[o][3]));
-            }
-            __syncwarp();
-            const int colB = own[o] * 8 + gid;
-            const double b0 = (colB < q && tig < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig) * q + colB) : 0.0;
-            const double b1 = (colB < q && tig + 4 < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig + 4) * q + colB) : 0.0;
-            double d0 = 0.0, d1 = 0.0;
-            dmma(d0, d1, a0, b0);
-            dmma(d0, d1, a1, b1);  // mma.sync: every lane's rhs loads have completed
-            if (live) {
-              if (col < q) __stcg(wrow + col, d0);
-              if (col + 1 < q) __stcg(wrow + col + 1, d1);
-            }
-            __syncwarp();
-          }
+        double* wrow = W + (size_t)(m + 8 * p + gid) * q;
+        const bool live = gid < nvalid;
+        if (live) {
+          if (colC < q) __stcg(wrow + colC, __ldcg(wrow + colC) - (acc[0] + acc[2]));
+          if (colC + 1 < q) __stcg(wrow + colC + 1, __ldcg(wrow + colC + 1) - (acc[1] + acc[3]));
         }
+        __syncwarp();
+        const double b0 = (cok && tig < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig) * q + colB) : 0.0;
+        const double b1 = (cok && tig + 4 < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig + 4) * q + colB) : 0.0;
+        double d0 = 0.0, d1 = 0.0;
+        dmma(d0, d1, a0, b0);
+        dmma(d0, d1, a1, b1);  // mma.sync: every lane's rhs loads have completed
+        if (live) {
+          if (colC < q) __stcg(wrow + colC, d0);
+          if (colC + 1 < q) __stcg(wrow + colC + 1, d1);
+        }
+        __syncwarp();
       }
     }
   }
-  __syncthreads();
+}
 
-  // ---- 3: Sigma* (lower triangle) and mean ---------------------------------------------------------------------
-  {
-    const int n4 = (n + 3) >> 2;
-    const int n_tiles = QB * (QB + 1) / 2;
-    for (int tile = warp; tile < n_tiles; tile += nw) {
-      int rb = 0;
-      while ((rb + 1) * (rb + 2) / 2 <= tile) ++rb;
-      const int sb = tile - rb * (rb + 1) / 2;
-      const int ca = rb * 8 + gid, cbb = sb * 8 + gid;
-      const bool oka = ca < q, okb = cbb < q;
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int k = 0; k < n4; k += 2) {
-        const int r0 = 4 * k + tig, r1 = r0 + 4;
-        const double a0 = (oka && r0 < n) ? __ldcg(W + (size_t)r0 * q + ca) : 0.0;
-        const double a1 = (oka && r1 < n) ? __ldcg(W + (size_t)r1 * q + ca) : 0.0;
-        const double b0 = (okb && r0 < n) ? __ldcg(W + (size_t)r0 * q + cbb) : 0.0;
-        const double b1 = (okb && r1 < n) ? __ldcg(W + (size_t)r1 * q + cbb) : 0.0;
-        dmma(acc[0], acc[1], a0, b0);
-        dmma(acc[2], acc[3], a1, b1);
-      }
-      const int r = rb * 8 + gid;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int s = sb * 8 + 2 * tig + hh;
-        if (r < q && s <= r) {
-          const double kss = cov_scalar(xb + (size_t)(r / T) * D, r % T, xb + (size_t)(s / T) * D, s % T,
-                                        st.ls + j * D, os, D);
-          S[(size_t)r * q + s] = kss - (acc[hh] + acc[2 + hh]);
-        }
-      }
-    }
-    const double* beta_o = st.beta_o + (size_t)j * m;
-    const double* beta_h = st.beta_h + (size_t)b * st.c_cap;
-    for (int r = tid; r < q; r += nt) {
+template <int T>
+__global__ void __launch_bounds__(PM_WARPS * 32)
+k_pm_gram(DevState st, const double* __restrict__ x, int H) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int j = b % st.g_ny, d = st.d;
+  const int m = st.m, n = m + st.c, q = H * T;
+  const int QB = (q + 7) >> 3;
+  const double* W = st.W + (size_t)b * st.W_stride;
+  double* S = st.S + (size_t)b * q * q;
+  double* mu = st.mu + (size_t)b * q;
+  const double* xb = x + (size_t)b * H * d;
+  const double os = st.os[j];
+  const int n4 = (n + 3) >> 2;
+  const int n_tiles = QB * (QB + 1) / 2;
+  const int gw = blockIdx.y * nw + warp, gstride = gridDim.y * nw;
+  for (int tile = gw; tile < n_tiles + QB; tile += gstride) {
+    if (tile >= n_tiles) {
+      // mean of column block cb: lanes (gid, tig) take rows 4k + tig, reduced over tig
+      const int col = (tile - n_tiles) * 8 + gid;
+      const double* beta_o = st.beta_o + (size_t)j * m;
+      const double* beta_h = st.beta_h + (size_t)b * st.c_cap;
       double a = 0.0;
-      for (int i = 0; i < m; ++i) a += __ldcg(W + (size_t)i * q + r) * beta_o[i];
-      for (int i = m; i < n; ++i) a += __ldcg(W + (size_t)i * q + r) * beta_h[i - m];
-      mu[r] = a;
+      if (col < q)
+        for (int r = tig; r < n; r += 4) a = fma(__ldcg(W + (size_t)r * q + col), r < m ? beta_o[r] : beta_h[r - m], a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (tig == 0 && col < q) mu[col] = a;
+      continue;
+    }
+    int rb = 0;
+    while ((rb + 1) * (rb + 2) / 2 <= tile) ++rb;
+    const int sb = tile - rb * (rb + 1) / 2;
+    const int ca = rb * 8 + gid, cbb = sb * 8 + gid;
+    const bool oka = ca < q, okb = cbb < q;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < n4; k += 8) {
+      double av[8], bv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = 4 * (k + u) + tig;
+        av[u] = (oka && r < n) ? __ldcg(W + (size_t)r * q + ca) : 0.0;
+        bv[u] = (okb && r < n) ? __ldcg(W + (size_t)r * q + cbb) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dmma(acc[2 * (u & 1)], acc[2 * (u & 1) + 1], av[u], bv[u]);
+    }
+    const int r = rb * 8 + gid;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int s = sb * 8 + 2 * tig + hh;
+      if (r < q && s <= r) {
+        const double kss = cov_scalar(xb + (size_t)(r / T) * d, r % T, xb + (size_t)(s / T) * d, s % T,
+                                      st.ls + j * d, os, d);
+        S[(size_t)r * q + s] = kss - (acc[hh] + acc[2 + hh]);
+      }
     }
   }
-  __syncthreads();
+}
 
-  for (int r = tid; r < q; r += nt) {
+// mean / variance out, then the draw (tri_ok: q(q+1)/2 doubles of dynamic shared memory for the packed Cholesky)
+__global__ void __launch_bounds__(BLK_THREADS)
+k_pm_finish(DevState st, int H, double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ eps,
+            gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level, int tri_ok) {
+  extern __shared__ __align__(16) double dyn_tri[];
+  const int b = blockIdx.x, q = H * st.T;
+  const double* S = st.S + (size_t)b * q * q;
+  const double* mu = st.mu + (size_t)b * q;
+  for (int r = threadIdx.x; r < q; r += blockDim.x) {
     if (mean) mean[(size_t)b * q + r] = mu[r];
     if (var) var[(size_t)b * q + r] = fmax(S[(size_t)r * q + r], GP_MIN_VARIANCE);
   }
-  if (eps) block_sample(st, b, H, eps, opts, y, jitter_level);
+  if (eps) block_sample(st, b, H, eps, opts, y, jitter_level, tri_ok ? dyn_tri : nullptr);
 }
