@@ -198,6 +198,39 @@ def extras(torch, device, cpu_leg=True):
                                    "device_ms": float(np.median(dev_times[2:])),
                                    "shape": "pendulum1D: ns=70, H=17, T=3 (q=51), n_obs=87",
                                    "calls": "train_hallucinated_dynGP + dyn_fg_jacobians (solver.py:84-94)"}
+    # SQP mode at the car-residual shape (BASELINE configs[2]): q = 150 joint scalars per call, +150 factor rows per iteration
+    try:
+        from sampling_gpmpc_b200.agent import gp_hypers_from_params
+        from sampling_gpmpc_b200.engine import GPEngine
+        from sampling_gpmpc_b200.envs import make_env_spec as _mk
+        cp = configs.car_residual_fs(20, 50, with_derivatives=True)
+        sp = _mk(cp)
+        Xc, Yc = sp.initial_training_data(cp)
+        Hc, its = 50, 6
+        eng = GPEngine(20, 3, 2, 3, Xc.shape[0], cap_points=Hc * its, device=device)
+        ls, os_, nz = gp_hypers_from_params(cp, 3, 2, use_grad=True)
+        eng.set_hypers(ls, os_, nz, 1e-9)
+        eng.set_real_data(Xc, Yc)
+        gd = torch.Generator(device=device).manual_seed(0)
+        base = torch.stack([torch.linspace(-0.9, 0.9, Hc), torch.linspace(-0.5, 0.5, Hc)], 1).to(device, torch.float64)
+        xq = (base[None, None] + 0.05 * torch.randn(20, 1, Hc, 2, generator=gd, dtype=torch.float64, device=device)).expand(20, 3, Hc, 2).contiguous()
+        per_it = []
+        for it in range(its):
+            ee = torch.randn(20, 3, Hc, 3, generator=gd, dtype=torch.float64, device=device).clamp(-3, 3)
+            torch.cuda.synchronize()
+            e0.record()
+            _, _, yq, _ = eng.posterior(xq, ee, eng.opts(beta=3.0))
+            eng.append(xq, yq)
+            e1.record()
+            torch.cuda.synchronize()
+            per_it.append(round(e0.elapsed_time(e1), 3))
+            xq = (xq + 0.03 * torch.randn(20, 1, Hc, 2, generator=gd, dtype=torch.float64, device=device)).contiguous()
+        out["sqp_linearisation_car_ms"] = {"device_ms_by_sqp_iteration": per_it, "factor_rows_before_call": [150 * i for i in range(its)],
+                                           "shape": "car residual: ns=20, g_ny=3, H=50, T=3 (q=150), m=45; model call + conditioning",
+                                           "engine_status": eng.status()}
+        del eng
+    except Exception as exc:  # noqa: BLE001
+        out["sqp_linearisation_car_ms"] = {"error": repr(exc)}
     if cpu_leg:
         # the same calls through the oracle's Agent restatement (full re-fit per call, all host threads)
         from oracle.agent_ref import RefAgent

@@ -140,7 +140,9 @@ static int ensure_workspace(gpmpc_handle* h, int H) {
   DevState& st = h->st;
   const int n = st.m + st.c, q = H * st.T;
   if (n <= h->ws_n && q <= h->ws_q && H <= h->ws_H && st.W) return GPMPC_OK;
-  const int new_n = std::max(n + n / 2, h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
+  // sized for the reserved capacity where one is known (gpmpc_reserve / Agent: H * max_sqp_iter), so that the SQP loop never
+  // re-allocates (cudaFree / cudaMalloc synchronise the device: 10-20 ms spikes otherwise)
+  const int new_n = std::max(std::max(n + n / 2, st.m + st.c_cap), h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
   st.W = st.S = st.C = st.mu = st.xc = nullptr;
   const size_t B = (size_t)st.B;
@@ -190,7 +192,7 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   auto solve = k_pm_solve<D, T>;
   auto gram = k_pm_gram<T>;
   const int q = H * st.T, QB = (q + 7) / 8;
-  const size_t slab = (size_t)PM_SLAB * 8 * sizeof(double);
+  const size_t slab = (size_t)2 * PM_SLAB * 8 * sizeof(double);
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
@@ -199,7 +201,7 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   }
   // the column blocks of one element over ceil(QB / 4) CTAs; the Gram tiles over enough CTAs to fill the GPU
   dim3 gs(st.B, (QB + PM_WARPS - 1) / PM_WARPS);
-  solve<<<gs, PM_WARPS * 32, slab, stream>>>(st, x, H);
+  solve<<<gs, PM_WARPS * PM_KS * 32, slab, stream>>>(st, x, H);
   const int tiles = QB * (QB + 1) / 2 + QB;
   const int want = std::max(1, std::min((tiles + PM_WARPS - 1) / PM_WARPS, (4 * h->num_sms + st.B - 1) / st.B));
   dim3 gg(st.B, want);

@@ -23,14 +23,15 @@
 #include "gpmpc_block.cuh"
 #include "gpmpc_step.cuh"
 
-#define PM_WARPS 4       // warps per CTA = column blocks per CTA of k_pm_solve
-#define PM_SLAB 1024     // storage columns of a sub-panel staged per pass (64 KB of shared memory)
+#define PM_WARPS 4       // column blocks per CTA of k_pm_solve
+#define PM_KS 2          // warps per column block: the k-range of every sub-panel product is split over them
+#define PM_SLAB 512      // storage columns of a sub-panel per slab; two slabs (2 x 32 KB) are resident
 #define PM_MAX_Q 2048    // test scalars per call served by this path (QB <= 256 column blocks)
 
 template <int D, int T>
-__global__ void __launch_bounds__(PM_WARPS * 32, 3)
+__global__ void __launch_bounds__(PM_WARPS * PM_KS * 32, 2)
 k_pm_solve(DevState st, const double* __restrict__ x, int H) {
-  extern __shared__ __align__(128) double sA[];  // [PM_SLAB * 8] one slab of a sub-panel (k-block layout)
+  extern __shared__ __align__(128) double sA[];  // [2][PM_SLAB * 8] two slabs of the factor stream (k-block layout)
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
@@ -85,14 +86,15 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
   __syncthreads();
 
   const uint32_t a_lane = a_lane_off(gid, tig);
-  const int cb = blockIdx.y * PM_WARPS + warp;   // this warp's column block
+  const int cbl = warp % PM_WARPS, ksp = warp / PM_WARPS;  // column block within the CTA, k-split of this warp
+  const int cb = blockIdx.y * PM_WARPS + cbl;    // this warp's column block
   const bool has = cb < QB;                      // (idle warps still take part in the CTA barriers below)
   const int colB = cb * 8 + gid;                 // B-fragment column of this lane
   const bool cok = has && colB < q;
   const int colC = cb * 8 + 2 * tig;             // C-fragment columns colC, colC + 1
 
-  // ---- 1: shared rows ------------------------------------------------------------------------------------------
-  if (has) {
+  // ---- 1: shared rows (split 0 of every column block) ---------------------------------------------------------
+  if (has && ksp == 0) {
     const int Pm = (m + 7) >> 3;
     const double* gL = st.LooP + (size_t)j * subpanel_off(Pm, 0);
     for (int p8 = Pm - 1; p8 >= 0; --p8) {
@@ -116,7 +118,12 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
     }
   }
 
+  __syncthreads();  // the other splits read these rows
+
   // ---- 2: own rows ----------------------------------------------------------------------------------------------
+  // Rounds of 8 k-steps alternate between the PM_KS warps of a column block (more W loads in flight per SM: the loop is
+  // bound by the L2 round trip of W, not by the tensor pipe); the partial sums meet in shared memory at the sub-panel's end.
+  __shared__ double red[PM_KS - 1][PM_WARPS][32][4];
   const int P8 = (c + 7) >> 3;
   const double* Le = st.Lh + (size_t)b * st.elem_stride;
   const uint32_t sA_s = smem_u32(sA);
@@ -129,37 +136,69 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
       bv[u] = (cok && r >= 0 && k + u < k_end) ? __ldcg(W + (size_t)r * q + colB) : 0.0;
     }
   };
+  // The element's factor stream is consumed slab by slab (<= PM_SLAB storage columns of one sub-panel); slab i + 1 is
+  // pulled into the other half of sA by ONE TMA bulk copy while the warps work on slab i.
+  __shared__ uint64_t bars[2];
+  uint64_t l2_stream;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  auto issue = [&](int p, int s0, int buf) {  // thread 0 only
+    const int ncol = mo + 8 * p + 8, s1 = min(ncol, s0 + PM_SLAB);
+    const uint32_t bytes = (uint32_t)(s1 - s0) * 64u;
+    mbar_expect_tx(&bars[buf], bytes);
+    // L2 evict-first: the factor passes through once per CTA and must not push W (re-read by every sub-panel) out of L2
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(sA + (size_t)buf * PM_SLAB * 8)), "l"(Le + subpanel_off(p, mo) + (size_t)s0 * 8), "r"(bytes),
+                   "r"(smem_u32(&bars[buf])), "l"(l2_stream) : "memory");
+  };
+  if (tid == 0 && P8 > 0) issue(0, 0, 0);
+  int it = 0;  // slab counter: buffer it & 1, barrier phase (it >> 1) & 1
   for (int p = 0; p < P8; ++p) {
     const int n_off = mo + 8 * p;           // off-diagonal storage columns of this sub-panel
     const int ncol = n_off + 8;             // + its diagonal block
-    const double* gp = Le + subpanel_off(p, mo);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int s0 = 0; s0 < ncol; s0 += PM_SLAB) {
+    for (int s0 = 0; s0 < ncol; s0 += PM_SLAB, ++it) {
       const int s1 = min(ncol, s0 + PM_SLAB);
       const int k_end = (min(s1, n_off) - s0) >> 2;  // k-steps of off-diagonal columns in this slab
+      __syncthreads();           // every warp is done with slab it - 1 (its buffer may be overwritten) and sees the W
+                                 // rows the previous sub-panel's finish wrote
       double bn[8];
-      load_b(bn, s0, 0, k_end);  // W rows of earlier sub-panels: independent of the staging below
-      __syncthreads();  // the previous slab is no longer read
-      {
-        const double2* src = (const double2*)(gp + (size_t)s0 * 8);
-        double2* dst = (double2*)sA;
-        for (int idx = tid; idx < (s1 - s0) * 4; idx += nt) dst[idx] = __ldcg(src + idx);
+      load_b(bn, s0, 8 * ksp, k_end);  // in flight while the slab arrives
+      if (tid == 0) {
+        if (s1 < ncol) issue(p, s1, (it + 1) & 1);
+        else if (p + 1 < P8) issue(p + 1, 0, (it + 1) & 1);
       }
-      __syncthreads();
-      // 8 k-steps per round; the W loads (L2 round trips) of the NEXT round are in flight during this round's chain
-      for (int k = 0; k < k_end; k += 8) {
+      mbar_wait(&bars[it & 1], (it >> 1) & 1);
+      const uint32_t buf_s = sA_s + (uint32_t)(it & 1) * PM_SLAB * 64;
+      // this warp's rounds: k = 8 ksp, 8 ksp + 8 PM_KS, ...; the W loads of its next round are in flight during the chain
+      for (int k = 8 * ksp; k < k_end; k += 8 * PM_KS) {
         double av[8], bv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) bv[u] = bn[u];
-        if (k + 8 < k_end) load_b(bn, s0, k + 8, k_end);
+        if (k + 8 * PM_KS < k_end) load_b(bn, s0, k + 8 * PM_KS, k_end);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = k + u < k_end ? lds(sA_s + (k + u) * 256 + a_lane) : 0.0;
+        for (int u = 0; u < 8; ++u) av[u] = k + u < k_end ? lds(buf_s + (k + u) * 256 + a_lane) : 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) dmma(acc[2 * (u & 1)], acc[2 * (u & 1) + 1], av[u], bv[u]);
       }
-      if (s1 == ncol && has) {
+      if (s1 == ncol) {  // last slab of the sub-panel: gather the partial sums of the other splits
+        if (ksp > 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) red[ksp - 1][cbl][lane][e] = acc[e];
+        }
+        __syncthreads();
+        if (ksp == 0) {
+#pragma unroll
+          for (int s2 = 0; s2 < PM_KS - 1; ++s2)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] += red[s2][cbl][lane][e];
+        }
+      }
+      if (s1 == ncol && has && ksp == 0) {
         // the slab ends with the diagonal block: rhs = K - dot, w_blk = inv(D) rhs
-        const uint32_t dblk = sA_s + (uint32_t)(n_off - s0) * 64;
+        const uint32_t dblk = buf_s + (uint32_t)(n_off - s0) * 64;
         const int nvalid = min(8, c - 8 * p);
         double a0 = 0.0, a1 = 0.0;
         if (tig <= gid) a0 = lds(dblk + (uint32_t)sp_idx(gid, tig) * 8);
