@@ -192,7 +192,7 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   auto solve = k_pm_solve<D, T>;
   auto gram = k_pm_gram<T>;
   const int q = H * st.T, QB = (q + 7) / 8;
-  const size_t slab = (size_t)2 * PM_SLAB * 8 * sizeof(double);
+  const size_t slab = (size_t)2 * PM_NSP * PM_SLABC * 8 * sizeof(double);
   static bool configured = false;  // per instantiation
   if (!configured) {
     CUDA_TRY(h, cudaFuncSetAttribute(solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
@@ -201,7 +201,7 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   }
   // the column blocks of one element over ceil(QB / 4) CTAs; the Gram tiles over enough CTAs to fill the GPU
   dim3 gs(st.B, (QB + PM_WARPS - 1) / PM_WARPS);
-  solve<<<gs, PM_WARPS * PM_KS * 32, slab, stream>>>(st, x, H);
+  solve<<<gs, PM_WARPS * 32, slab, stream>>>(st, x, H);
   const int tiles = QB * (QB + 1) / 2 + QB;
   const int want = std::max(1, std::min((tiles + PM_WARPS - 1) / PM_WARPS, (4 * h->num_sms + st.B - 1) / st.B));
   dim3 gg(st.B, want);

@@ -23,15 +23,15 @@
 #include "gpmpc_block.cuh"
 #include "gpmpc_step.cuh"
 
-#define PM_WARPS 4       // column blocks per CTA of k_pm_solve
-#define PM_KS 2          // warps per column block: the k-range of every sub-panel product is split over them
-#define PM_SLAB 512      // storage columns of a sub-panel per slab; two slabs (2 x 32 KB) are resident
+#define PM_WARPS 4       // warps = column blocks per CTA of k_pm_solve
+#define PM_NSP 8         // sub-panels per row block of the solve (64 rows share every W fragment)
+#define PM_SLABC 64      // storage columns per sub-panel per stage: a buffer is PM_NSP x PM_SLABC x 64 B = 32 KB, two resident
 #define PM_MAX_Q 2048    // test scalars per call served by this path (QB <= 256 column blocks)
 
 template <int D, int T>
-__global__ void __launch_bounds__(PM_WARPS * PM_KS * 32, 2)
+__global__ void __launch_bounds__(PM_WARPS * 32, 3)
 k_pm_solve(DevState st, const double* __restrict__ x, int H) {
-  extern __shared__ __align__(128) double sA[];  // [2][PM_SLAB * 8] two slabs of the factor stream (k-block layout)
+  extern __shared__ __align__(128) double sA[];  // [2][PM_NSP][PM_SLABC * 8] two stages of the factor stream (k-block layout)
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tig = lane & 3;
@@ -86,15 +86,14 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
   __syncthreads();
 
   const uint32_t a_lane = a_lane_off(gid, tig);
-  const int cbl = warp % PM_WARPS, ksp = warp / PM_WARPS;  // column block within the CTA, k-split of this warp
-  const int cb = blockIdx.y * PM_WARPS + cbl;    // this warp's column block
+  const int cb = blockIdx.y * PM_WARPS + warp;   // this warp's column block
   const bool has = cb < QB;                      // (idle warps still take part in the CTA barriers below)
   const int colB = cb * 8 + gid;                 // B-fragment column of this lane
   const bool cok = has && colB < q;
   const int colC = cb * 8 + 2 * tig;             // C-fragment columns colC, colC + 1
 
-  // ---- 1: shared rows (split 0 of every column block) ---------------------------------------------------------
-  if (has && ksp == 0) {
+  // ---- 1: shared rows ------------------------------------------------------------------------------------------
+  if (has) {
     const int Pm = (m + 7) >> 3;
     const double* gL = st.LooP + (size_t)j * subpanel_off(Pm, 0);
     for (int p8 = Pm - 1; p8 >= 0; --p8) {
@@ -118,108 +117,129 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
     }
   }
 
-  __syncthreads();  // the other splits read these rows
-
   // ---- 2: own rows ----------------------------------------------------------------------------------------------
-  // Rounds of 8 k-steps alternate between the PM_KS warps of a column block (more W loads in flight per SM: the loop is
-  // bound by the L2 round trip of W, not by the tensor pipe); the partial sums meet in shared memory at the sub-panel's end.
-  __shared__ double red[PM_KS - 1][PM_WARPS][32][4];
+  // Left-looking over ROW BLOCKS of PM_NSP sub-panels (64 rows): for the columns left of the block every k-step loads ONE
+  // B fragment of W (an L2 round trip) and feeds PM_NSP tensor-core products, one per sub-panel of the block -- W is
+  // re-read once per 64 rows instead of once per 8 (the 8-row version was bound by exactly these re-reads:
+  // profiles/r1_sqp_growth.txt).  The block's own triangle is then solved sub-panel by sub-panel.
+  // The factor stream arrives through two 32 KB buffers: a "stage" is either the same <= PM_SLABC columns of all the
+  // block's sub-panels (PM_NSP TMA bulk copies on one mbarrier) or the block's triangle; stage i + 1 is in flight while
+  // the warps work on stage i.  A warp owns its column block for the whole solve, so W needs no CTA-wide barrier.
   const int P8 = (c + 7) >> 3;
+  const int NBLK = (P8 + PM_NSP - 1) / PM_NSP;
   const double* Le = st.Lh + (size_t)b * st.elem_stride;
   const uint32_t sA_s = smem_u32(sA);
   // W row of storage column t (the factor's column order): t < m shared, [m, mo) padding (none), t >= mo own
-  auto load_b = [&](double (&bv)[8], int s0, int k, int k_end) {
+  auto load_b = [&](double (&bv)[8], int kk0, int kk_end) {  // k-steps kk0 .. kk0+7 (global, 4 storage columns each)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int t = s0 + 4 * (k + u) + tig;
+      const int t = 4 * (kk0 + u) + tig;
       const int r = t < m ? t : (t >= mo ? t - mo + m : -1);
-      bv[u] = (cok && r >= 0 && k + u < k_end) ? __ldcg(W + (size_t)r * q + colB) : 0.0;
+      bv[u] = (cok && r >= 0 && kk0 + u < kk_end) ? __ldcg(W + (size_t)r * q + colB) : 0.0;
     }
   };
-  // The element's factor stream is consumed slab by slab (<= PM_SLAB storage columns of one sub-panel); slab i + 1 is
-  // pulled into the other half of sA by ONE TMA bulk copy while the warps work on slab i.
   __shared__ uint64_t bars[2];
   uint64_t l2_stream;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_stream));
   if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  auto issue = [&](int p, int s0, int buf) {  // thread 0 only
-    const int ncol = mo + 8 * p + 8, s1 = min(ncol, s0 + PM_SLAB);
-    const uint32_t bytes = (uint32_t)(s1 - s0) * 64u;
-    mbar_expect_tx(&bars[buf], bytes);
-    // L2 evict-first: the factor passes through once per CTA and must not push W (re-read by every sub-panel) out of L2
+  auto bulk = [&](double* dst, const double* src, uint32_t bytes, uint64_t* bar) {
+    // L2 evict-first: the factor passes through once per CTA and must not push W out of L2
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(sA + (size_t)buf * PM_SLAB * 8)), "l"(Le + subpanel_off(p, mo) + (size_t)s0 * 8), "r"(bytes),
-                   "r"(smem_u32(&bars[buf])), "l"(l2_stream) : "memory");
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(l2_stream) : "memory");
   };
-  if (tid == 0 && P8 > 0) issue(0, 0, 0);
-  int it = 0;  // slab counter: buffer it & 1, barrier phase (it >> 1) & 1
-  for (int p = 0; p < P8; ++p) {
-    const int n_off = mo + 8 * p;           // off-diagonal storage columns of this sub-panel
-    const int ncol = n_off + 8;             // + its diagonal block
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int s0 = 0; s0 < ncol; s0 += PM_SLAB, ++it) {
-      const int s1 = min(ncol, s0 + PM_SLAB);
-      const int k_end = (min(s1, n_off) - s0) >> 2;  // k-steps of off-diagonal columns in this slab
-      __syncthreads();           // every warp is done with slab it - 1 (its buffer may be overwritten) and sees the W
-                                 // rows the previous sub-panel's finish wrote
-      double bn[8];
-      load_b(bn, s0, 8 * ksp, k_end);  // in flight while the slab arrives
-      if (tid == 0) {
-        if (s1 < ncol) issue(p, s1, (it + 1) & 1);
-        else if (p + 1 < P8) issue(p + 1, 0, (it + 1) & 1);
+  auto n_part1 = [&](int blk) { return (mo + 8 * PM_NSP * blk + PM_SLABC - 1) / PM_SLABC; };  // stages before the triangle
+  auto issue = [&](int blk, int stg, int buf) {  // thread 0 only
+    const int p0 = blk * PM_NSP, nsp = min(PM_NSP, P8 - p0), base = mo + 8 * p0;
+    double* dst = sA + (size_t)buf * PM_NSP * PM_SLABC * 8;
+    if (stg < n_part1(blk)) {
+      const int s0 = stg * PM_SLABC, s1 = min(base, s0 + PM_SLABC);
+      const uint32_t each = (uint32_t)(s1 - s0) * 64u;
+      mbar_expect_tx(&bars[buf], each * nsp);
+      for (int jj = 0; jj < nsp; ++jj)
+        bulk(dst + (size_t)jj * PM_SLABC * 8, Le + subpanel_off(p0 + jj, mo) + (size_t)s0 * 8, each, &bars[buf]);
+    } else {  // triangle: sub-panel jj contributes its columns [base, base + 8 jj + 8), packed one after the other
+      mbar_expect_tx(&bars[buf], 256u * nsp * (nsp + 1));
+      for (int jj = 0; jj < nsp; ++jj)
+        bulk(dst + 32 * jj * (jj + 1), Le + subpanel_off(p0 + jj, mo) + (size_t)base * 8, (uint32_t)(8 * jj + 8) * 64u, &bars[buf]);
+    }
+  };
+  if (tid == 0 && NBLK > 0) issue(0, 0, 0);
+  int it = 0;  // stage counter: buffer it & 1, barrier phase (it >> 1) & 1
+  uint32_t buf_s = sA_s;
+  auto next_stage = [&](int blk, int stg) {  // all threads: hand over to stage (blk, stg), start the copy of its successor
+    __syncthreads();  // every warp is done with the previous stage's buffer
+    if (tid == 0) {
+      if (stg < n_part1(blk)) issue(blk, stg + 1, (it + 1) & 1);
+      else if (blk + 1 < NBLK) issue(blk + 1, 0, (it + 1) & 1);
+    }
+    mbar_wait(&bars[it & 1], (it >> 1) & 1);
+    buf_s = sA_s + (uint32_t)(it & 1) * PM_NSP * PM_SLABC * 64;
+    ++it;
+  };
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int p0 = blk * PM_NSP, nsp = min(PM_NSP, P8 - p0), base = mo + 8 * p0;
+    const int kk_end = base >> 2, rounds = (kk_end + 7) >> 3, n1 = n_part1(blk);
+    double acc[PM_NSP][4];
+#pragma unroll
+    for (int jj = 0; jj < PM_NSP; ++jj) acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = 0.0;
+    // -- columns left of the block: one W fragment per k-step, PM_NSP products
+    double bn[8];
+    load_b(bn, 0, kk_end);
+    for (int r = 0; r < rounds; ++r) {
+      if ((r & (PM_SLABC / 32 - 1)) == 0) next_stage(blk, r / (PM_SLABC / 32));
+      double bv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bv[u] = bn[u];
+      if (r + 1 < rounds) load_b(bn, 8 * (r + 1), kk_end);
+      const uint32_t ab = buf_s + (uint32_t)((8 * r) & (PM_SLABC / 4 - 1)) * 256 + a_lane;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (8 * r + u < kk_end) {
+#pragma unroll
+          for (int jj = 0; jj < PM_NSP; ++jj)
+            if (jj < nsp) dmma(acc[jj][2 * (u & 1)], acc[jj][2 * (u & 1) + 1], lds(ab + jj * PM_SLABC * 64 + u * 256), bv[u]);
+        }
       }
-      mbar_wait(&bars[it & 1], (it >> 1) & 1);
-      const uint32_t buf_s = sA_s + (uint32_t)(it & 1) * PM_SLAB * 64;
-      // this warp's rounds: k = 8 ksp, 8 ksp + 8 PM_KS, ...; the W loads of its next round are in flight during the chain
-      for (int k = 8 * ksp; k < k_end; k += 8 * PM_KS) {
-        double av[8], bv[8];
+    }
+    // -- the block's triangle, sub-panel by sub-panel
+    next_stage(blk, n1);
+    if (has) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bv[u] = bn[u];
-        if (k + 8 * PM_KS < k_end) load_b(bn, s0, k + 8 * PM_KS, k_end);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = k + u < k_end ? lds(buf_s + (k + u) * 256 + a_lane) : 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) dmma(acc[2 * (u & 1)], acc[2 * (u & 1) + 1], av[u], bv[u]);
-      }
-      if (s1 == ncol) {  // last slab of the sub-panel: gather the partial sums of the other splits
-        if (ksp > 0) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) red[ksp - 1][cbl][lane][e] = acc[e];
+      for (int jj = 0; jj < PM_NSP; ++jj) {
+        if (jj < nsp) {
+          const int p = p0 + jj;
+          const uint32_t tri = buf_s + (uint32_t)(32 * jj * (jj + 1)) * 8;
+          for (int kk = 0; kk < 2 * jj; ++kk) {  // in-block columns base .. base + 8 jj: W rows of this block, just written
+            const int row = m + 8 * p0 + 4 * kk + tig;
+            const double bq = cok ? __ldcg(W + (size_t)row * q + colB) : 0.0;
+            dmma(acc[jj][2 * (kk & 1)], acc[jj][2 * (kk & 1) + 1], lds(tri + kk * 256 + a_lane), bq);
+          }
+          // rhs = K - dot, w_blk = inv(D) rhs (diagonal block = the last 8 columns of this sub-panel's part)
+          const uint32_t dblk = tri + (uint32_t)(8 * jj) * 64;
+          const int nvalid = min(8, c - 8 * p);
+          double a0 = 0.0, a1 = 0.0;
+          if (tig <= gid) a0 = lds(dblk + (uint32_t)sp_idx(gid, tig) * 8);
+          if (tig + 4 <= gid) a1 = lds(dblk + (uint32_t)sp_idx(gid, tig + 4) * 8);
+          double* wrow = W + (size_t)(m + 8 * p + gid) * q;
+          const bool live = gid < nvalid;
+          if (live) {
+            if (colC < q) __stcg(wrow + colC, __ldcg(wrow + colC) - (acc[jj][0] + acc[jj][2]));
+            if (colC + 1 < q) __stcg(wrow + colC + 1, __ldcg(wrow + colC + 1) - (acc[jj][1] + acc[jj][3]));
+          }
+          __syncwarp();
+          const double b0 = (cok && tig < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig) * q + colB) : 0.0;
+          const double b1 = (cok && tig + 4 < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig + 4) * q + colB) : 0.0;
+          double d0 = 0.0, d1 = 0.0;
+          dmma(d0, d1, a0, b0);
+          dmma(d0, d1, a1, b1);  // mma.sync: every lane's rhs loads have completed
+          if (live) {
+            if (colC < q) __stcg(wrow + colC, d0);
+            if (colC + 1 < q) __stcg(wrow + colC + 1, d1);
+          }
+          __syncwarp();
         }
-        __syncthreads();
-        if (ksp == 0) {
-#pragma unroll
-          for (int s2 = 0; s2 < PM_KS - 1; ++s2)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] += red[s2][cbl][lane][e];
-        }
-      }
-      if (s1 == ncol && has && ksp == 0) {
-        // the slab ends with the diagonal block: rhs = K - dot, w_blk = inv(D) rhs
-        const uint32_t dblk = buf_s + (uint32_t)(n_off - s0) * 64;
-        const int nvalid = min(8, c - 8 * p);
-        double a0 = 0.0, a1 = 0.0;
-        if (tig <= gid) a0 = lds(dblk + (uint32_t)sp_idx(gid, tig) * 8);
-        if (tig + 4 <= gid) a1 = lds(dblk + (uint32_t)sp_idx(gid, tig + 4) * 8);
-        double* wrow = W + (size_t)(m + 8 * p + gid) * q;
-        const bool live = gid < nvalid;
-        if (live) {
-          if (colC < q) __stcg(wrow + colC, __ldcg(wrow + colC) - (acc[0] + acc[2]));
-          if (colC + 1 < q) __stcg(wrow + colC + 1, __ldcg(wrow + colC + 1) - (acc[1] + acc[3]));
-        }
-        __syncwarp();
-        const double b0 = (cok && tig < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig) * q + colB) : 0.0;
-        const double b1 = (cok && tig + 4 < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig + 4) * q + colB) : 0.0;
-        double d0 = 0.0, d1 = 0.0;
-        dmma(d0, d1, a0, b0);
-        dmma(d0, d1, a1, b1);  // mma.sync: every lane's rhs loads have completed
-        if (live) {
-          if (colC < q) __stcg(wrow + colC, d0);
-          if (colC + 1 < q) __stcg(wrow + colC + 1, d1);
-        }
-        __syncwarp();
       }
     }
   }
