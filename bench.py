@@ -57,11 +57,13 @@ def workload_config(ns_per_gpu, n_gpus):
 def synthetic_inputs(ns, horizon, T, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
-    eps = torch.empty(horizon, ns, 3, 1, T, dtype=torch.float64).pin_memory()
+    pin = torch.cuda.is_available()  # the CPU legs must run without a GPU too
+    eps = torch.empty(horizon, ns, 3, 1, T, dtype=torch.float64, pin_memory=pin)
     torch.randn(eps.shape, generator=g, dtype=torch.float64, out=eps)
     eps.clamp_(-3.0, 3.0)
     t = torch.linspace(0, 1, horizon, dtype=torch.float64)
-    u = torch.stack([0.05 * torch.sin(6.0 * t), 0.3 * torch.cos(4.0 * t)], 1).contiguous().pin_memory()
+    u = torch.stack([0.05 * torch.sin(6.0 * t), 0.3 * torch.cos(4.0 * t)], 1).contiguous()
+    u = u.pin_memory() if pin else u
     return u, eps
 
 
