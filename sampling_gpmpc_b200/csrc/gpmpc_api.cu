@@ -494,7 +494,17 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
   }
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
-  const int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
+  int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
+  if (grow && !reuse && h->block_mma && H * st.T <= PM_MAX_Q) {
+    // the factor changed since the last model call (e.g. the reset of agent.py:261-272 between the model call and the
+    // conditioning): W, Sigma*, mean for these points against the CURRENT factor, on the tensor-core kernels
+    rc = dispatch_posterior_mma(h, st, x, H, nullptr, nullptr, nullptr, gpmpc_sample_opts{-1.0, -1.0, 0, 0}, nullptr, nullptr, stream);
+    if (rc) return rc;
+    h->launches++;
+    h->cache_version = h->factor_version;
+    h->cache_H = H;
+    reuse = 1;
+  }
   rc = configure_block_smem(h);
   if (rc) return rc;
   size_t tri = grow ? tri_bytes(h, H * st.T) : 0;

@@ -359,11 +359,7 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     for (int rr = tid; rr < qa; rr += nt)
       for (int ss = 0; ss <= rr; ++ss)
         dyn_tri[rr * (rr + 1) / 2 + ss] = S[(size_t)sh_act[rr] * q + sh_act[ss]] + (ss == rr ? noise[sh_act[rr] % T] : 0.0);
-    info = block_cholesky_packed(dyn_tri, qa);
-    if (info == 0)  // the rest of the kernel reads the factor from C (row-major, leading dim qa)
-      for (int rr = tid; rr < qa; rr += nt)
-        for (int ss = 0; ss <= rr; ++ss) C[(size_t)rr * qa + ss] = dyn_tri[rr * (rr + 1) / 2 + ss];
-    __syncthreads();
+    info = block_cholesky_packed(dyn_tri, qa);  // the rest of the kernel reads the factor straight from shared memory
   } else {
     for (int idx = tid; idx < qa * qa; idx += nt) {
       int rr = idx / qa, ss = idx % qa;
@@ -387,20 +383,32 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   }
   for (int idx = tid; idx < qa * qa; idx += nt) {
     int ss = idx / qa, rr = idx % qa;
-    if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = C[(size_t)rr * qa + ss];
-    else if (ss == rr) *own_entry(st, b, st.c + rr, n + rr) = 1.0 / C[(size_t)rr * qa + rr];
+    if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = tri_ok ? dyn_tri[rr * (rr + 1) / 2 + ss] : C[(size_t)rr * qa + ss];
+    else if (ss == rr)
+      *own_entry(st, b, st.c + rr, n + rr) = 1.0 / (tri_ok ? dyn_tri[rr * (rr + 1) / 2 + rr] : C[(size_t)rr * qa + rr]);
   }
-  // beta_new = L_nn^{-1} (y - mu)
+  // beta_new = L_nn^{-1} (y - mu): forward substitution by one warp, the partial solution kept in shared memory
+  // (sh_beta aliases nothing: 512 doubles) so that a row costs a shared-memory round trip, not an L2 one
+  __shared__ double sh_beta[512];
   if (tid < 32) {
     double* beta = st.beta_h + (size_t)b * st.c_cap + st.c;
     const double* yb = ylab + (size_t)b * q;
+    for (int rr = tid; rr < qa; rr += 32) sh_beta[rr] = yb[sh_act[rr]] - mu[sh_act[rr]];
+    __syncwarp();
     for (int rr = 0; rr < qa; ++rr) {
       double acc = 0.0;
-      for (int ss = tid; ss < rr; ss += 32) acc += C[(size_t)rr * qa + ss] * beta[ss];
+      if (tri_ok)
+        for (int ss = tid; ss < rr; ss += 32) acc += dyn_tri[rr * (rr + 1) / 2 + ss] * sh_beta[ss];
+      else
+        for (int ss = tid; ss < rr; ss += 32) acc += C[(size_t)rr * qa + ss] * sh_beta[ss];
       acc = warp_sum(acc);
-      if (tid == 0) beta[rr] = (yb[sh_act[rr]] - mu[sh_act[rr]] - acc) / C[(size_t)rr * qa + rr];
+      if (tid == 0) {
+        const double lrr = tri_ok ? dyn_tri[rr * (rr + 1) / 2 + rr] : C[(size_t)rr * qa + rr];
+        sh_beta[rr] = (sh_beta[rr] - acc) / lrr;
+      }
       __syncwarp();
     }
+    for (int rr = tid; rr < qa; rr += 32) beta[rr] = sh_beta[rr];
   }
   __syncthreads();
   // transposed inverses of the 8 x 8 diagonal blocks the new rows touch: the blocks are independent, one warp each
