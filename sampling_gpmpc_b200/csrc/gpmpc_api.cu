@@ -206,10 +206,12 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   const int want = std::max(1, std::min((tiles + PM_WARPS - 1) / PM_WARPS, (4 * h->num_sms + st.B - 1) / st.B));
   dim3 gg(st.B, want);
   gram<<<gg, PM_WARPS * 32, 0, stream>>>(st, x, H);
+  h->launches += 1;
+  if (!mean && !var && !eps) return GPMPC_OK;  // W, Sigma*, mean stay in the workspace (recompute before an append)
   size_t tri = eps ? tri_bytes(h, q) : 0;
   if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;
   k_pm_finish<<<st.B, BLK_THREADS, tri, stream>>>(st, H, mean, var, eps, o, y, jl, tri ? 1 : 0);
-  h->launches += 2;
+  h->launches += 1;
   return GPMPC_OK;
 }
 
