@@ -188,10 +188,15 @@ __device__ __forceinline__ uint32_t a_lane_off(int gid, int tig) { return (uint3
 template <int T>
 __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint32_t wa, int n4) {
   constexpr int WSTEP = 4 * T * 8;  // bytes of w per 4 columns
+  // B fragments: only T < 8 of the 8 columns are live; the dead ones belong to the lanes with gid >= T -- for T <= 4 the
+  // whole upper half-warp -- which issue no shared-memory access at all (their wavefront disappears; stale register
+  // values only ever reach accumulator columns nobody reads)
+  const bool live = T >= 8 || ((threadIdx.x & 31) >> 2) < T;
+  double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
   int it = 0;
   for (; it + 4 <= n4; it += 4) {
     const double a0 = lds<0>(la), a1 = lds<256>(la), a2 = lds<512>(la), a3 = lds<768>(la);
-    const double b0 = lds<0>(wa), b1 = lds<WSTEP>(wa), b2 = lds<2 * WSTEP>(wa), b3 = lds<3 * WSTEP>(wa);
+    if (live) { b0 = lds<0>(wa); b1 = lds<WSTEP>(wa); b2 = lds<2 * WSTEP>(wa); b3 = lds<3 * WSTEP>(wa); }
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
     dmma(c[0], c[1], a2, b2);
@@ -201,7 +206,7 @@ __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint
   }
   if (it < n4) {
     const double a0 = lds<0>(la), a1 = lds<256>(la);
-    const double b0 = lds<0>(wa), b1 = lds<WSTEP>(wa);
+    if (live) { b0 = lds<0>(wa); b1 = lds<WSTEP>(wa); }
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
   }
