@@ -10,10 +10,11 @@
 //  k_pm_solve (grid B x ceil(QB / 4), 4 warps):
 //   0  K_{o*}: one exp per (training point, test point) pair, the T x T derivative block from it
 //   1  shared rows: W_o = inv(L_oo) K_o, tile-rows last to first, in place (as K1 phase B)
-//   2  own rows, left-looking over the 8-row sub-panels of the element's factor stream: the sub-panel's k-blocks are
-//      staged in shared memory once (all column blocks need the same A operand), every warp runs the DMMA chain
-//      dot = L[rows][cols < n_off] W over its column blocks with W read back through L2, rhs = K - dot, and the 8 x 8
-//      diagonal block is applied as inv(D) rhs (two more DMMAs; inverse kept in the block's upper triangle)
+//   2  own rows, left-looking over ROW BLOCKS of 8 sub-panels (64 rows) of the element's factor stream: the stream is
+//      staged in shared memory by TMA bulk copies (all column blocks need the same A operand); for the columns left of
+//      the block every k-step reads one W fragment back through L2 and feeds 8 DMMA chains (one per sub-panel), then the
+//      block's triangle is solved sub-panel by sub-panel: rhs = K - dot, and the 8 x 8 diagonal block is applied as
+//      inv(D) rhs (two more DMMAs; inverse kept in the block's upper triangle)
 //  k_pm_gram (grid B x splits, 4 warps):
 //   3  Sigma* = K** - W^T W by 8 x 8 output tiles (A and B fragments are the same access pattern on W), mean = W^T beta
 //  k_pm_finish (grid B): mean / variance out, then the draw / post-processing of gpmpc_block.cuh (block_sample, packed
