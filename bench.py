@@ -172,6 +172,31 @@ def extras(torch, device, cpu_leg=True):
     del fr, eps
     torch.cuda.empty_cache()
 
+    # the other large-batch rollout of the reference: benchmarking/simulate_true_reachable_set.py (2-D pendulum, real data WITH
+    # derivative observations: m = 180, g_ny = 2, d = 3, T = 4, 30 steps; 20 samples x 10^4 repeats = 2e5 samples)
+    try:
+        ns2, st2 = 200_000, 30
+        fr = ForwardRollout(configs.pendulum2D_rollout(ns2, st2), condition=True, device=device)
+        g2 = torch.Generator().manual_seed(5)
+        eps2 = torch.randn(st2, ns2, 2, 1, 4, generator=g2, dtype=torch.float64).clamp_(-2.5, 2.5).to(device)
+        u2 = (2.0 * torch.sin(torch.linspace(0, 3, st2, dtype=torch.float64))).reshape(st2, 1).to(device)
+        fr.run(u2, eps2)
+        torch.cuda.synchronize()
+        e0.record()
+        fr.run(u2, eps2)
+        e1.record()
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1)
+        wb, wf = fr.engine.last_launch_work()
+        out["pendulum_true_reachable_set"] = {
+            "sample_steps_per_sec": ns2 * st2 / (ms2 * 1e-3), "ms_per_rollout": ms2, "ns": ns2, "steps": st2,
+            "algorithmic_GBps": wb / ms2 / 1e6, "algorithmic_GFLOPs": wf / ms2 / 1e6, "engine_status": fr.engine.status(),
+            "shape": "g_ny=2, d=3, T=4, m=180 (derivative observations), conditioning on; shared rows by the batched GEMM (K1a)"}
+        del fr, eps2
+    except Exception as exc:  # noqa: BLE001
+        out["pendulum_true_reachable_set"] = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+
     params = configs.pendulum1D_sqp()
     agent = Agent(params, generate_base_samples=False, device=device)
     g = torch.Generator().manual_seed(0)
