@@ -548,8 +548,12 @@ static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double*
   }
   const size_t smem = ((size_t)st.mo * 8 * NB + ((E * D + 1) & ~1)) * 8;
   const int n_tiles = (st.ns + E - 1) / E;
-  dim3 grid(std::min(n_tiles, std::max(1, h->num_sms / st.g_ny)), st.g_ny);
-  kern<<<grid, SR_THREADS, smem, stream>>>(st, x);
+  // few row panels (m of a few hundred): 8 warps per CTA balance them better than 16 and two CTAs share an SM
+  const int Pm = st.mo / 8;
+  const int threads = Pm <= 32 ? 256 : SR_THREADS;
+  const int per_sm = threads == 256 && 2 * (smem + 1024) <= (size_t)h->max_dyn_smem ? 2 : 1;
+  dim3 grid(std::min(n_tiles, std::max(1, h->num_sms * per_sm / st.g_ny)), st.g_ny);
+  kern<<<grid, threads, smem, stream>>>(st, x);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
