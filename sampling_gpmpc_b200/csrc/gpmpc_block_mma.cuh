@@ -55,14 +55,31 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
   }
   for (int idx = tid; idx < m * h_n; idx += nt) {
     const int i = idx / h_n, h = h_lo + idx - i * h_n;
-    double xs[D], out[T];
+    double xs[D];
 #pragma unroll
     for (int a = 0; a < D; ++a) xs[a] = xb[h * D + a];
-    kernel_row<D, T>(st.Xr + (size_t)st.obs_pt[i] * D, st.obs_task[i], xs, il, os, out);
+    const int pt = st.obs_pt[i], ta = st.obs_task[i];
+    if (real_point_full<T>(st, i, pt, ta, m)) {  // one exp for the point's T x T block (thread of its task-0 row)
+      if (ta != 0) continue;
+      double xa[D], kb[T][T];
 #pragma unroll
-    for (int tb = 0; tb < T; ++tb) {
-      const int col = h * T + tb;
-      if (col >= c_lo && col < c_hi) W[(size_t)i * q + col] = out[tb];
+      for (int a = 0; a < D; ++a) xa[a] = st.Xr[(size_t)pt * D + a];
+      kernel_block<D, T>(xa, xs, il, os, kb);
+#pragma unroll
+      for (int t2 = 0; t2 < T; ++t2)
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) {
+          const int col = h * T + tb;
+          if (col >= c_lo && col < c_hi) W[(size_t)(i + t2) * q + col] = kb[t2][tb];
+        }
+    } else {
+      double out[T];
+      kernel_row<D, T>(st.Xr + (size_t)pt * D, ta, xs, il, os, out);
+#pragma unroll
+      for (int tb = 0; tb < T; ++tb) {
+        const int col = h * T + tb;
+        if (col >= c_lo && col < c_hi) W[(size_t)i * q + col] = out[tb];
+      }
     }
   }
   for (int idx = tid; idx < st.np * h_n; idx += nt) {

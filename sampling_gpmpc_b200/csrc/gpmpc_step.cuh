@@ -543,6 +543,16 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   }
 }
 
+// Observed real scalars are ordered point-major, task-minor.  True iff all T tasks of scalar i's point are observed
+// (their rows are then the consecutive rows i - ta .. i - ta + T - 1): such a point needs one exp for its T x T block.
+template <int T>
+__device__ __forceinline__ bool real_point_full(const DevState& st, int i, int pt, int ta, int m) {
+  if (T == 1) return false;
+  const int i0 = i - ta;
+  return i0 >= 0 && i0 + T - 1 < m && st.obs_pt[i0] == pt && st.obs_task[i0] == 0 && st.obs_pt[i0 + T - 1] == pt &&
+         st.obs_task[i0 + T - 1] == T - 1;
+}
+
 // K1a: the shared rows of EVERY element as one batched tensor-core product ("Regime A"): for large m
 // the per-element product with inv(L_oo) is FP64-contraction bound and, done one element at a time, re-streams the
 // m x m factor from L2 for every element.  Here a CTA takes a TILE of E = 8 NB / T consecutive samples of output j:
@@ -592,13 +602,31 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < m * E; idx += blockDim.x) {
       const int i = idx / E, e = idx - i * E;
-      double xs[D], out[T];
+      double xs[D];
 #pragma unroll
       for (int a = 0; a < D; ++a) xs[a] = sx[e * D + a];
-      kernel_row<D, T>(st.Xr + (size_t)st.obs_pt[i] * D, st.obs_task[i], xs, il, os, out);
-      const int rot = sr_rot<NC>(i);
+      const int pt = st.obs_pt[i], ta = st.obs_task[i];
+      if (real_point_full<T>(st, i, pt, ta, m)) {
+        // all T tasks of the point are observed (rows i - ta .. i - ta + T - 1): ONE exp for its T x T block, by the
+        // thread of its task-0 row
+        if (ta != 0) continue;
+        double xa[D], kb[T][T];
 #pragma unroll
-      for (int tb = 0; tb < T; ++tb) sK[i * NC + (e * T + tb + rot) % NC] = out[tb];
+        for (int a = 0; a < D; ++a) xa[a] = st.Xr[(size_t)pt * D + a];
+        kernel_block<D, T>(xa, xs, il, os, kb);
+#pragma unroll
+        for (int t2 = 0; t2 < T; ++t2) {
+          const int rot = sr_rot<NC>(i + t2);
+#pragma unroll
+          for (int tb = 0; tb < T; ++tb) sK[(i + t2) * NC + (e * T + tb + rot) % NC] = kb[t2][tb];
+        }
+      } else {
+        double out[T];
+        kernel_row<D, T>(st.Xr + (size_t)pt * D, ta, xs, il, os, out);
+        const int rot = sr_rot<NC>(i);
+#pragma unroll
+        for (int tb = 0; tb < T; ++tb) sK[i * NC + (e * T + tb + rot) % NC] = out[tb];
+      }
     }
     __syncthreads();
 
