@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0, "/root/repo")
+"""One conditioned pendulum true-reachable-set rollout (m = 180, 2e5 samples x 30 steps), for ncu launch lists."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sampling_gpmpc_b200 import configs
 from sampling_gpmpc_b200.rollout import ForwardRollout
