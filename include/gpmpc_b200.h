@@ -140,6 +140,14 @@ int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* op
 int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_t* point_active,
                  int32_t H, void* stream);
 
+/* The same with one flag per new SCALAR: scalar_active HOST uint8[H*T] (point h, task t -> [h*T + t]; NULL = all).
+ * observation_nan_policy("mask") drops single label slots, e.g. the derivative slots prepare_dynamics_set NaNs
+ * (src/agent.py:402): a point may then enter the factor with some of its T rows only.  While such a point is in the
+ * factor, model calls are served by the row-by-row kernels (k_posterior) instead of the fused / tensor-core ones, which
+ * assume T consecutive rows per point; gpmpc_reset_hallucinated clears the condition. */
+int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const uint8_t* scalar_active,
+                        int32_t H, void* stream);
+
 /* Fused rollout step (H = 1): posterior + draw + post-processing + append in ONE launch, one warp per
  * batch element, the element's factor rows streamed once from HBM.  Same outputs as gpmpc_posterior.
  * Replaces one iteration of the loops at benchmarking/simulate_true_reachable_set.py:179-259 and

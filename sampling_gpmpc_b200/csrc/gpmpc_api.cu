@@ -47,10 +47,13 @@ struct gpmpc_handle {
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
   // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
   int wo_min_m = 1;
-  int wo_max_nb = 3;
+  int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   // SQP-mode model call: tensor-core kernel k_posterior_mma (default) or the scalar substitution kernel k_posterior
   // (gpmpc_set_block_kernels / GPMPC_BLOCK_SCALAR=1: the independent reference semantics the parity tests compare with)
-  bool block_mma = true;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
+  bool block_mma = true;
+  // a hallucinated point with only SOME of its T scalars in the factor exists (gpmpc_append_masked; agent.py:402): the
+  // kernels that find a point's rows through hrow0 (K1, K2m) are bypassed for the scalar kernels until the next reset
+  bool has_partial = false;
   size_t wo_count = 0;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
@@ -371,6 +374,7 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   st.m = m;
   st.mo = (m + 7) & ~7;
   st.c = 0; st.np = 0;
+  h->has_partial = false;
   if (m_changed || !st.Lh) {
     // the slab height depends on m: (re)allocate the per-element state from scratch
     free_factor_state(h);
@@ -391,6 +395,7 @@ int gpmpc_reset_hallucinated(gpmpc_handle* h) {
   if (!h) return GPMPC_ERR_ARG;
   h->st.c = 0;
   h->st.np = 0;
+  h->has_partial = false;
   h->factor_version++;
   return GPMPC_OK;
 }
@@ -432,7 +437,7 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
-  if (h->block_mma && H * st.T <= PM_MAX_Q) {
+  if (h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q) {
     rc = dispatch_posterior_mma(h, st, x, H, mean, var, eps, o, y, jitter_level, (cudaStream_t)stream);
     if (rc) return rc;
   } else {
@@ -467,14 +472,30 @@ int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* op
 
 int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_t* point_active, int32_t H,
                  void* stream_) {
+  if (!h || H < 1 || !point_active) return gpmpc_append_masked(h, x, y, nullptr, H, stream_);
+  std::vector<uint8_t> sc((size_t)H * h->st.T);
+  for (int i = 0; i < H; ++i)
+    for (int t = 0; t < h->st.T; ++t) sc[(size_t)i * h->st.T + t] = point_active[i] ? 1 : 0;
+  return gpmpc_append_masked(h, x, y, sc.data(), H, stream_);
+}
+
+int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const uint8_t* scalar_active, int32_t H,
+                        void* stream_) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || !y || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / H");
   cudaStream_t stream = (cudaStream_t)stream_;
   DevState& hst = h->st;
-  if (H * hst.T > 512) return fail(h, GPMPC_ERR_ARG, "gpmpc_append supports at most 512 new scalars per call");
-  int n_active = 0;
-  for (int i = 0; i < H; ++i) n_active += (!point_active || point_active[i]) ? 1 : 0;
+  const int T = hst.T;
+  if (H * T > 512) return fail(h, GPMPC_ERR_ARG, "gpmpc_append supports at most 512 new scalars per call");
+  int n_active = 0;  // scalars entering the factor
+  bool partial = false;
+  for (int i = 0; i < H; ++i) {
+    int mine = 0;
+    for (int t = 0; t < T; ++t) mine += (!scalar_active || scalar_active[(size_t)i * T + t]) ? 1 : 0;
+    n_active += mine;
+    partial = partial || (mine != 0 && mine != T);
+  }
   if (hst.np + H > hst.cap_points) {
     rc = alloc_factor_state(h, std::max(hst.np + H, hst.cap_points * 2), stream);
     if (rc) return rc;
@@ -484,20 +505,20 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
   if (grow) {
     rc = ensure_workspace(h, H);
     if (rc) return rc;
-    if (point_active && n_active < H) {
-      if (h->d_active_cap < H) {
+    if (scalar_active && n_active < H * T) {
+      if (h->d_active_cap < H * T) {
         cudaFree(h->d_active);
-        CUDA_TRY(h, dev_alloc(&h->d_active, (size_t)H));
-        h->d_active_cap = H;
+        CUDA_TRY(h, dev_alloc(&h->d_active, (size_t)H * T));
+        h->d_active_cap = H * T;
       }
-      CUDA_TRY(h, cudaMemcpyAsync(h->d_active, point_active, (size_t)H, cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->d_active, scalar_active, (size_t)H * T, cudaMemcpyHostToDevice, stream));
       d_act = h->d_active;
     }
   }
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
-  if (grow && !reuse && h->block_mma && H * st.T <= PM_MAX_Q) {
+  if (grow && !reuse && h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q) {
     // the factor changed since the last model call (e.g. the reset of agent.py:261-272 between the model call and the
     // conditioning): W, Sigma*, mean for these points against the CURRENT factor, on the tensor-core kernels
     rc = dispatch_posterior_mma(h, st, x, H, nullptr, nullptr, nullptr, gpmpc_sample_opts{-1.0, -1.0, 0, 0}, nullptr, nullptr, stream);
@@ -518,8 +539,9 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
   count_work(h, H, grow);
   hst.np += H;
   if (grow) {
-    hst.c += n_active * hst.T;
+    hst.c += n_active;
     h->factor_version++;
+    h->has_partial = h->has_partial || partial;
   }
   return GPMPC_OK;
 }
@@ -708,8 +730,10 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
   count_work(h, 1, grow);
   bool handled = false;
-  rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream, &handled);
-  if (rc) return rc;
+  if (!h->has_partial) {  // the fused kernel finds a point's factor rows through hrow0: whole points only
+    rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream, &handled);
+    if (rc) return rc;
+  }
   if (!handled) {
     // factor too tall for the register-resident sweep: same recursion through the general block kernels
     const double w_bytes = h->last_bytes, w_flops = h->last_flops;

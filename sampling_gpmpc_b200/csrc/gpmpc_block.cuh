@@ -299,7 +299,7 @@ k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts o
 // ------------------------------------------------------------------------------------------------
 // Conditioning: append the active points' T scalars each to element b's factor.
 //   reuse != 0 : the workspace may hold W, S, mu for exactly these x (checked per element on device)
-//   active     : DEVICE uint8[H] or NULL; pt_base = index of the first new point in Xh/Yh
+//   active     : DEVICE uint8[H*T] (per test scalar) or NULL; pt_base = index of the first new point in Xh/Yh
 // New rows k = c + r':  L[m+k][0..n) = W[:, act(r')],  L[m+k][n + s'] = chol(S_act + noise)[r'][s'].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK_THREADS)
@@ -313,14 +313,17 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   __shared__ int sh_act[512];  // active test scalars (q' <= 512 checked by the host)
   __shared__ int sh_qa;
 
-  // record the points (labels keep their NaNs); a point's T factor rows are consecutive
+  // record the points (labels keep their NaNs); `active` flags SCALARS (point h, task t) -> active[h * T + t].  A fully
+  // active point's T factor rows are consecutive from hrow0; a point with no or only some active scalars gets
+  // hrow0 = -1 (the host then routes model calls to the kernels that walk hobs_pt / hobs_task row by row)
   if (b == 0)
     for (int h = tid; h < H; h += nt) {
       int row = -1;
-      if (grow_factor && (!active || active[h])) {
-        int before = 0;
-        for (int hh = 0; hh < h; ++hh) before += (!active || active[hh]) ? 1 : 0;
-        row = st.c + before * T;
+      if (grow_factor) {
+        int mine = 0, before = 0;
+        for (int t = 0; t < T; ++t) mine += (!active || active[h * T + t]) ? 1 : 0;
+        for (int s2 = 0; s2 < h * T; ++s2) before += (!active || active[s2]) ? 1 : 0;
+        if (mine == T) row = st.c + before;
       }
       st.hrow0[pt_base + h] = row;
     }
@@ -333,9 +336,8 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   if (tid == 0) {
     sh_same = reuse;
     int qa = 0;
-    for (int h = 0; h < H; ++h)
-      if (!active || active[h])
-        for (int t = 0; t < T; ++t) sh_act[qa++] = h * T + t;
+    for (int s2 = 0; s2 < H * T; ++s2)
+      if (!active || active[s2]) sh_act[qa++] = s2;
     sh_qa = qa;
   }
   __syncthreads();

@@ -53,6 +53,7 @@ ABI = {
     "gpmpc_posterior": (C.c_int, [_P, _D, _I, _D, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _P]),
     "gpmpc_sample": (C.c_int, [_P, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _P]),
     "gpmpc_append": (C.c_int, [_P, _D, _D, C.POINTER(C.c_uint8), _I, _P]),
+    "gpmpc_append_masked": (C.c_int, [_P, _D, _D, C.POINTER(C.c_uint8), _I, _P]),
     "gpmpc_step": (C.c_int, [_P, _D, _D, C.POINTER(GpmpcSampleOpts), _D, _D, _D, _D, _P]),
     "gpmpc_assemble": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _I, _D, _P]),
     "gpmpc_rollout": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _P]),
@@ -250,6 +251,15 @@ class GPEngine:
             pa = np.ascontiguousarray(np.asarray(point_active, dtype=np.uint8).reshape(H))
             act = pa.ctypes.data_as(C.POINTER(C.c_uint8))
         self._check(self.lib.gpmpc_append(self.h, _ptr(xx), _ptr(yy), act, H, _stream()), "gpmpc_append")
+
+    def append_masked(self, x: torch.Tensor, y: torch.Tensor, scalar_active: np.ndarray):
+        """append with one flag per new scalar: scalar_active (H, T) bool / uint8 (a point may enter with some tasks only)."""
+        H = x.shape[-2]
+        xx = self._x(x, H)
+        yy = y.to(self.device, torch.float64).reshape(self.B, H * self.T).contiguous()
+        sa = np.ascontiguousarray(np.asarray(scalar_active, dtype=np.uint8).reshape(H * self.T))
+        self._check(self.lib.gpmpc_append_masked(self.h, _ptr(xx), _ptr(yy), sa.ctypes.data_as(C.POINTER(C.c_uint8)), H,
+                                                 _stream()), "gpmpc_append_masked")
 
     def step(self, x: torch.Tensor, eps: Optional[torch.Tensor], opts: Optional[GpmpcSampleOpts] = None,
              want_moments: bool = True):

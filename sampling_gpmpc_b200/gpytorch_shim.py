@@ -287,15 +287,13 @@ class ExactGP(_Module):
             old = 0
         if nh > old:
             newX, newY = Xh[:, :, old:].contiguous(), Yh[:, :, old:].contiguous()
-            nan_pt = newY.isnan().any(3)
-            if bool((newY.isnan().all(3) != nan_pt).any()):
-                raise NotImplementedError("partially observed hallucinated points (agent.py:402) are not on the hot path")
-            # observation_nan_policy('mask'): a slot is dropped for every element if it is NaN in any
-            active = (~nan_pt.any(1).any(0)).cpu().numpy().astype(np.uint8)
+            # observation_nan_policy('mask'): a label slot is dropped for every element if it is NaN in any;
+            # slots are (point, task): a point may keep its value and lose its derivative slots (agent.py:402)
+            active = (~newY.isnan().any(1).any(0)).cpu().numpy().astype(np.uint8)  # (n_new, T)
             step = max(1, 512 // T)
             for p0 in range(0, nh - old, step):
                 p1 = min(nh - old, p0 + step)
-                eng.append(newX[:, :, p0:p1].contiguous(), newY[:, :, p0:p1].contiguous(), active[p0:p1])
+                eng.append_masked(newX[:, :, p0:p1].contiguous(), newY[:, :, p0:p1].contiguous(), active[p0:p1])
             be.Xh = newX if be.Xh is None else torch.cat([be.Xh, newX], 2)
             be.Yh = newY if be.Yh is None else torch.cat([be.Yh, newY], 2)
             be.version += 1

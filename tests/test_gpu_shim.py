@@ -200,6 +200,42 @@ def test_shim_incremental_append_reset_and_nan_mask():
     shim.reset_backends()
 
 
+def test_shim_partially_observed_points_match_the_oracle():
+    """observation_nan_policy('mask') per label SLOT: hallucinated points whose derivative slots are NaN (what
+    prepare_dynamics_set does, src/agent.py:402) keep their value row only; a slot NaN for one sample is masked for all.
+    The shim (gpmpc_append_masked; model calls then go through the row-by-row kernels) against the CPU oracle on the same
+    data, through three model rebuilds (partial points first, whole points after them, then a reset)."""
+    from oracle import gp_ref
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200 import gpytorch_shim as shim
+    from sampling_gpmpc_b200.envs import make_env_spec
+    shim.reset_backends()
+    G = shim.namespace()
+    params = configs.pendulum1D_sqp(num_dyn_samples=5, n_mpc=1)
+    X, Y = make_env_spec(params).initial_training_data(params)
+    ns, g_ny, d, T, H = 5, 1, 2, 3, 6
+    bs = torch.Size([ns, g_ny])
+    g = torch.Generator().manual_seed(9)
+    Xr, Yr = torch.tile(X, (ns, g_ny, 1, 1)), torch.tile(Y, (ns, 1, 1, 1))
+    xs = [2.2 + torch.rand(ns, g_ny, H, d, generator=g, dtype=torch.float64) for _ in range(3)]
+    ys = [0.01 * torch.randn(ns, g_ny, H, T, generator=g, dtype=torch.float64) for _ in range(2)]
+    ys[0][:, :, 1, 1:] = float("nan")     # point 1: value only (both derivative slots dropped)
+    ys[0][3, 0, 4, 2] = float("nan")      # point 4: one derivative slot NaN for ONE sample -> dropped for all
+    ys[0][:, :, 5, :] = float("nan")      # point 5: not in the factor at all
+    os_ = float(params["agent"]["Dyn_gp_outputscale"]["both"][0])
+    xq = xs[2]
+    for k, want_rows in ((1, 6 * T - 2 - 1 - 3), (2, 6 * T - 6 + 6 * T), (0, 0)):
+        Xa, Ya = torch.cat([Xr] + xs[:k], 2), torch.cat([Yr] + ys[:k], 2)
+        with G.settings.cholesky_jitter(double_value=1e-6):
+            post = _build(G, params, Xa, Ya, bs, True)(xq.cuda())
+        ref = gp_ref.make_gp_from_params(params, Xa, Ya, bs, use_grad=True)(xq)
+        (be,) = shim._BACKENDS.values()
+        assert be.eng.num_factor_rows == want_rows
+        assert scaled_close(post.mean.cpu(), ref.mean, np.sqrt(os_), RTOL) <= 1.0
+        assert scaled_close(post.variance.cpu(), ref.variance, os_, RTOL) <= 1.0
+    shim.reset_backends()
+
+
 def test_shim_installs_as_gpytorch():
     """`import gpytorch` resolves to the shim after install(); the census of SURVEY.md 8(b) is complete."""
     from sampling_gpmpc_b200 import gpytorch_shim as shim
