@@ -32,7 +32,6 @@
 #ifndef STEP_MAX_WARPS
 #define STEP_MAX_WARPS 16  // warps per CTA are chosen per launch (shared-memory budget), one CTA per SM
 #endif
-#define FULL_MASK 0xffffffffu
 #ifndef STEP_SEG
 #define STEP_SEG 64  // 8-row column groups per TMA chunk / ring slot (64 * 64 B = 4 KB); multiple of 8
 #endif
@@ -48,10 +47,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
