@@ -69,3 +69,14 @@ def test_create_fails_loudly_without_device(lib):
     assert rc == -3 and b"no CPU fallback" in lib.gpmpc_last_error(None)
     bad = engine.GpmpcDims(4, 1, 9, 3, 10, 0)
     assert lib.gpmpc_create(C.byref(bad), C.byref(h)) == -1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the engine (and with it every product path) refuses to run instead of falling back."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sampling_gpmpc_b200.engine import GPEngine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        GPEngine(2, 1, 2, 3, 5)
