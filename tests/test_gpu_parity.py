@@ -378,6 +378,32 @@ def test_rollout_properties_at_scale():
     assert fr.engine.status() == 0
 
 
+def test_full_size_rollout_is_batch_independent():
+    """At the bench's own size (125 000 samples x 3 outputs x 50 steps, 59 GB of factor state) the oracle cannot run; the
+    size-independent property that ties it to the sizes the oracle CAN check: a sample's trajectory depends only on its own
+    base samples, so two 1000-sample slices rolled out on their own (the sizes of the oracle-checked tests) must be
+    BIT-IDENTICAL to the same samples inside the full batch.  Also finite, status clean."""
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    if torch.cuda.mem_get_info()[0] < 100e9:
+        pytest.skip("needs ~95 GB of free device memory")
+    ns, steps = 125_000, 50
+    g = torch.Generator(device="cuda").manual_seed(7)
+    eps = torch.randn(steps, ns, 3, 1, 3, generator=g, dtype=torch.float64, device="cuda").clamp_(-3, 3)
+    t = torch.linspace(0, 1, steps, dtype=torch.float64)
+    u = torch.stack([0.05 * torch.sin(6.0 * t), 0.3 * torch.cos(4.0 * t)], 1).cuda()
+    full = ForwardRollout(configs.car_residual_fs(ns, steps, with_derivatives=True), condition=True)
+    traj = full.run(u, eps)
+    assert full.engine.status() == 0 and bool(torch.isfinite(traj).all())
+    assert full.engine.num_factor_rows == steps * 3
+    small = ForwardRollout(configs.car_residual_fs(1000, steps, with_derivatives=True), condition=True)
+    for lo in (0, ns - 1000):
+        part = small.run(u, eps[:, lo:lo + 1000].contiguous())
+        assert torch.equal(part, traj[lo:lo + 1000]), f"samples {lo}..{lo + 1000} differ from their stand-alone rollout"
+    del full, small, traj, eps
+    torch.cuda.empty_cache()
+
+
 def _root_sensitivity(S, level, jitter, eps, os_j, draws=6, rel=1e-15):
     """How far the ORACLE's own draw moves when Sigma* is perturbed at its rounding level (rel * outputscale,
     the size of the cancellation error in K** - W^T W), and whether its jitter decision survives that.
