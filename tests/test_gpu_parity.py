@@ -404,6 +404,28 @@ def test_full_size_rollout_is_batch_independent():
     torch.cuda.empty_cache()
 
 
+def test_large_batch_pendulum_rollout_is_batch_independent():
+    """The same property on the pendulum true-reachable-set shape (m = 180 with derivative observations: shared rows by
+    the batched GEMM K1a, tiles of 6 samples) at 100 000 samples x 30 steps: slices that do not start on a tile boundary."""
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    if torch.cuda.mem_get_info()[0] < 80e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    ns, steps = 100_000, 30
+    g = torch.Generator(device="cuda").manual_seed(8)
+    eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64, device="cuda").clamp_(-2.5, 2.5)
+    u = (2.0 * torch.sin(torch.linspace(0, 3, steps, dtype=torch.float64))).reshape(steps, 1).cuda()
+    full = ForwardRollout(configs.pendulum2D_rollout(ns, steps), condition=True)
+    traj = full.run(u, eps)
+    assert full.engine.status() == 0 and bool(torch.isfinite(traj).all())
+    small = ForwardRollout(configs.pendulum2D_rollout(500, steps), condition=True)
+    for lo in (1, ns - 503):
+        part = small.run(u, eps[:, lo:lo + 500].contiguous())
+        assert torch.equal(part, traj[lo:lo + 500]), f"samples {lo}..{lo + 500} differ from their stand-alone rollout"
+    del full, small, traj, eps
+    torch.cuda.empty_cache()
+
+
 def _root_sensitivity(S, level, jitter, eps, os_j, draws=6, rel=1e-15):
     """How far the ORACLE's own draw moves when Sigma* is perturbed at its rounding level (rel * outputscale,
     the size of the cancellation error in K** - W^T W), and whether its jitter decision survives that.
