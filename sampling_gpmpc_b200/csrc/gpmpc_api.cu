@@ -552,7 +552,7 @@ template <int T>
 static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                               const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                               cudaStream_t stream) {
-  k_step_finish<T><<<(st.B + 127) / 128, 128, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
+  k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;

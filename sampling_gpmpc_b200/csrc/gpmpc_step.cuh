@@ -787,8 +787,11 @@ k_step_shared(DevState st, const double* __restrict__ x) {
 // arithmetic 32-fold redundantly): Sigma* = K** - W^T W, T x T Cholesky with GPyTorch's jitter ladder, y = mean +
 // L eps, zero-variance / truncation (src/agent.py:646-708), then the diagonal-block part of the rank-T append:
 // chol(Sigma* + noise), 1/L_kk, beta_new and the transposed block inverses (gpmpc_state.cuh).
+#ifndef FIN_THREADS
+#define FIN_THREADS 128
+#endif
 template <int T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FIN_THREADS)
 k_step_finish(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
               double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
               int* __restrict__ jitter_level, int grow_factor) {
