@@ -381,7 +381,19 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     int rc = alloc_factor_state(h, st.cap_points, stream);
     if (rc) return rc;
   }
-  k_factor_real<<<g_ny, BLK_THREADS, 0, stream>>>(st);
+  {
+    static bool configured = false;
+    if (!configured) {
+      CUDA_TRY(h, cudaFuncSetAttribute(k_factor_real, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+      CUDA_TRY(h, cudaFuncSetAttribute(k_invert_real, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+      configured = true;
+    }
+    if ((size_t)m * 8 * K0B_WARPS > (size_t)h->max_dyn_smem)
+      return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~7000)");
+    k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
+    k_invert_real<<<dim3((m + K0B_WARPS - 1) / K0B_WARPS, g_ny), K0B_WARPS * 32, (size_t)m * 8 * K0B_WARPS, stream>>>(st);
+    h->launches++;
+  }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaStreamSynchronize(stream));  // host staging vectors go out of scope

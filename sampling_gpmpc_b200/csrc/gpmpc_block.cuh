@@ -36,6 +36,34 @@ __device__ int block_cholesky(double* A, int n, int ld) {
   return 0;
 }
 
+// The same factorisation for the m x m real-data block (K0; m up to a few thousand, A in global memory / L2): the scaled
+// pivot column is cached in shared memory (scol, n doubles) so that the rank-1 update reads A[i][cc] once, coalesced over
+// cc, and nothing else from global memory; rows over the warps, columns over the lanes, no index divisions.
+__device__ int block_cholesky_wide(double* A, int n, int ld, double* scol) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    const double akk = A[(size_t)k * ld + k];
+    if (!(akk > 0.0)) return k + 1;  // uniform: every thread reads the same value
+    const double lkk = sqrt(akk);
+    __syncthreads();
+    if (tid == 0) A[(size_t)k * ld + k] = lkk;
+    for (int i = k + 1 + tid; i < n; i += nt) {
+      const double v = A[(size_t)i * ld + k] / lkk;
+      A[(size_t)i * ld + k] = v;
+      scol[i] = v;
+    }
+    __syncthreads();
+    for (int i = k + 1 + wid; i < n; i += nw) {
+      const double lik = scol[i];
+      double* row = A + (size_t)i * ld;
+      for (int cc = k + 1 + lane; cc <= i; cc += 32) row[cc] -= lik * scol[cc];
+    }
+  }
+  __syncthreads();
+  return 0;
+}
+
 // The same factorisation on a PACKED lower triangle in shared memory (P[r(r+1)/2 + s], s <= r): the q x q matrices of
 // the SQP-mode draw / append are latency bound in global memory (three L2 round trips per pivot); in shared memory a
 // pivot step costs a few hundred cycles.  Same pivot test, same return value.
@@ -64,7 +92,9 @@ __device__ int block_cholesky_packed(double* P, int n) {
 // ------------------------------------------------------------------------------------------------
 // K0: shared real-data block.  grid = g_ny, block = BLK_THREADS.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
+#define K0_THREADS 1024
+__global__ void __launch_bounds__(K0_THREADS) k_factor_real(DevState st) {
+  extern __shared__ __align__(16) double k0_col[];  // [m] pivot column of the factorisation
   const int j = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int m = st.m, d = st.d;
   double* A = st.Loo + (size_t)j * m * m;
@@ -85,7 +115,7 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
       }
       A[idx] = v;
     }
-    int info = block_cholesky(A, m, m);
+    int info = block_cholesky_wide(A, m, m, k0_col);
     if (info == 0) break;
     if (level == GP_MAX_TRIES) {
       if (tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_NOT_PD);
@@ -95,22 +125,10 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
     __syncthreads();
   }
   if (level > 0 && tid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_JITTER | ((unsigned)level << 8));
-  // explicit inverse of L_oo in sub-panel layout for the fused rollout kernel (gpmpc_state.cuh): w_o = inv(L_oo) k_o
-  // is then a plain tensor-core product.  cond(L_oo) ~ 1e3 at the reference's configurations: the inverse costs
-  // ~1e-14 relative accuracy in the posterior variance, 5 orders below the parity tolerance.
-  // Thread jj solves L x = e_jj by forward substitution and scatters column jj; padding rows / upper part are 0.
+  // inv(L_oo) is filled in by k_invert_real (next launch); padding rows / the upper part stay 0
   const int Pm = (m + 7) >> 3;
   double* LP = st.LooP + (size_t)j * subpanel_off(Pm, 0);
   for (int idx = tid; idx < (int)subpanel_off(Pm, 0); idx += nt) LP[idx] = 0.0;
-  __syncthreads();
-  for (int jj = tid; jj < m; jj += nt) {
-    for (int i = jj; i < m; ++i) {
-      double acc = (i == jj) ? 1.0 : 0.0;
-      for (int k = jj; k < i; ++k) acc -= A[(size_t)i * m + k] * LP[subpanel_off(k >> 3, 0) + sp_idx(jj, k & 7)];
-      LP[subpanel_off(i >> 3, 0) + sp_idx(jj, i & 7)] = acc / A[(size_t)i * m + i];
-    }
-  }
-  __syncthreads();
   // beta_o = L^{-1} y_o : forward substitution, one warp, lanes over the row's dot product
   if (tid < 32) {
     const double* y = st.y_obs + (size_t)j * m;
@@ -123,6 +141,32 @@ __global__ void __launch_bounds__(BLK_THREADS) k_factor_real(DevState st) {
       __syncwarp();
     }
   }
+}
+
+// K0b: explicit inverse of L_oo in sub-panel layout (gpmpc_state.cuh) for the fused / tensor-core kernels: w_o = inv(L_oo) k_o
+// is then a plain product.  cond(L_oo) ~ 1e3 at the reference's configurations: the inverse costs ~1e-14 relative accuracy
+// in the posterior variance, 5 orders below the parity tolerance.  The columns of the inverse are independent:
+// one WARP per column jj solves L x = e_jj by forward substitution, lanes over the row's dot product, the solution kept
+// in shared memory; grid = (ceil(m / warps), g_ny), so the whole GPU works on it (one thread per column in one CTA took
+// more than half of K0's 9 s at m = 3000).
+#define K0B_WARPS 4
+__global__ void __launch_bounds__(K0B_WARPS * 32) k_invert_real(DevState st) {
+  extern __shared__ __align__(16) double k0b_x[];  // [K0B_WARPS][m]
+  const int j = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int m = st.m, jj = blockIdx.x * K0B_WARPS + wid;
+  if (jj >= m) return;
+  const double* A = st.Loo + (size_t)j * m * m;
+  double* LP = st.LooP + (size_t)j * subpanel_off((m + 7) >> 3, 0);
+  double* xs = k0b_x + (size_t)wid * m;
+  for (int i = jj; i < m; ++i) {
+    const double* row = A + (size_t)i * m;
+    double acc = 0.0;
+    for (int k = jj + lane; k < i; k += 32) acc += row[k] * xs[k];
+    acc = warp_sum(acc);
+    if (lane == 0) xs[i] = ((i == jj ? 1.0 : 0.0) - acc) / row[i];
+    __syncwarp();
+  }
+  for (int i = jj + lane; i < m; i += 32) LP[subpanel_off(i >> 3, 0) + sp_idx(jj, i & 7)] = xs[i];
 }
 
 // ------------------------------------------------------------------------------------------------
