@@ -101,7 +101,8 @@ def main():
         est_flop = ns * a.g_ny * steps * (d + 1) * (m * m + m * steps * (d + 1) + (steps * (d + 1)) ** 2 / 3.0)
         if m > 4000:
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d,
-                            "why": "K0 (k_factor_real) is a one-CTA factorisation sized for m <= ~2000; m = 1e4 not run"})
+                            "why": "m = 1e4: neither K1a's kernel tile (mo x 8 doubles of shared memory) nor K1's per-warp w array holds such an "
+                                   "m (DESIGN.md 7); not run"})
             continue
         if need > HBM_BUDGET:
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d, "why": f"factor state {need / 1e9:.0f} GB > HBM"})
