@@ -390,7 +390,23 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     }
     if ((size_t)m * 8 * K0B_WARPS > (size_t)h->max_dyn_smem)
       return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~7000)");
-    k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
+    // m in the thousands: the factorisation cooperatively over all SMs (one grid barrier per pivot); GPMPC_K0_COOP_MIN_M
+    int coop_min_m = 768;
+    if (const char* e = getenv("GPMPC_K0_COOP_MIN_M")) coop_min_m = atoi(e);
+    int coop_ok = 0;
+    cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, h->device);
+    if (coop_ok && m >= coop_min_m && (size_t)m * 16 + 1024 <= (size_t)h->max_dyn_smem) {
+      static bool coop_configured = false;
+      if (!coop_configured) {
+        CUDA_TRY(h, cudaFuncSetAttribute(k_factor_real_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
+        coop_configured = true;
+      }
+      void* args[] = {(void*)&st};
+      CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)k_factor_real_coop, dim3(h->num_sms), dim3(K0_THREADS), args,
+                                              (size_t)m * 16, stream));
+    } else {
+      k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
+    }
     k_invert_real<<<dim3((m + K0B_WARPS - 1) / K0B_WARPS, g_ny), K0B_WARPS * 32, (size_t)m * 8 * K0B_WARPS, stream>>>(st);
     h->launches++;
   }

@@ -143,6 +143,94 @@ __global__ void __launch_bounds__(K0_THREADS) k_factor_real(DevState st) {
   }
 }
 
+// K0c: the same factorisation for m in the thousands, COOPERATIVE over the whole GPU (cudaLaunchCooperativeKernel, one CTA
+// per SM, one grid barrier per pivot): every CTA keeps its own copy of the scaled pivot column in shared memory (double
+// buffered), the rows of the trailing update are spread over all warps of the grid, and the scaled column of pivot k is
+// written back by the rows' owners after the barrier that opens pivot k + 1 (nobody reads column k of A after that
+// barrier).  Same pivot test and jitter ladder as K0 (every CTA sees the same pivot value, so the decisions are uniform).
+#include <cooperative_groups.h>
+__global__ void __launch_bounds__(K0_THREADS) k_factor_real_coop(DevState st) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) double k0c_col[];  // [2][m]
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt;
+  const int gw = gtid >> 5, gnw = gnt >> 5;
+  const int m = st.m, d = st.d;
+  for (int j = 0; j < st.g_ny; ++j) {
+    double* A = st.Loo + (size_t)j * m * m;
+    const double* ls = st.ls + j * d;
+    const double os = st.os[j];
+    const double* noise = st.noise + j * st.T;
+    int level = 0;
+    for (;;) {
+      const double add = level == 0 ? 0.0 : st.jitter * pow(10.0, (double)(level - 1));
+      for (int i = gw; i < m; i += gnw) {  // row i of the lower triangle by one warp
+        const double* xi = st.Xr + (size_t)st.obs_pt[i] * d;
+        const int ti = st.obs_task[i];
+        for (int cc = lane; cc < m; cc += 32) {
+          double v = 0.0;
+          if (cc <= i) {
+            v = cov_scalar(xi, ti, st.Xr + (size_t)st.obs_pt[cc] * d, st.obs_task[cc], ls, os, d);
+            if (cc == i) v += noise[ti] + add;
+          }
+          A[(size_t)i * m + cc] = v;
+        }
+      }
+      int info = 0;
+      double lkk_prev = 0.0;
+      for (int k = 0; k < m; ++k) {
+        grid.sync();  // the trailing update of pivot k - 1 is complete everywhere
+        double* scol = k0c_col + (size_t)(k & 1) * m;
+        const double* prev = k0c_col + (size_t)((k + 1) & 1) * m;
+        const double akk = A[(size_t)k * m + k];
+        if (!(akk > 0.0)) { info = k + 1; break; }  // uniform over the grid: nobody writes a(k,k) during pivot k
+        const double lkk = sqrt(akk);
+        for (int i = k + 1 + tid; i < m; i += nt) scol[i] = A[(size_t)i * m + k] / lkk;
+        __syncthreads();
+        for (int i = k + 1 + gw; i < m; i += gnw) {
+          double* row = A + (size_t)i * m;
+          const double lik = scol[i];
+          for (int cc = k + 1 + lane; cc <= i; cc += 32) row[cc] -= lik * scol[cc];
+        }
+        // column k - 1 (scaled, from the other buffer) and its diagonal go back to A now: every CTA has left pivot k - 1,
+        // and pivot k reads column k and touches columns > k only
+        if (k > 0) {
+          for (int i = k + gtid; i < m; i += gnt) A[(size_t)i * m + (k - 1)] = prev[i];
+          if (gtid == 0) A[(size_t)(k - 1) * m + (k - 1)] = lkk_prev;
+        }
+        lkk_prev = lkk;
+      }
+      grid.sync();
+      if (info == 0) {
+        if (gtid == 0) A[(size_t)(m - 1) * m + (m - 1)] = lkk_prev;  // the last pivot has no column below it
+        break;
+      }
+      if (level == GP_MAX_TRIES) {
+        if (gtid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_NOT_PD);
+        break;
+      }
+      ++level;
+    }
+    if (level > 0 && gtid == 0) atomicOr(st.status, GPMPC_ST_TRAIN_JITTER | ((unsigned)level << 8));
+    const int Pm = (m + 7) >> 3;
+    double* LP = st.LooP + (size_t)j * subpanel_off(Pm, 0);
+    for (size_t idx = gtid; idx < subpanel_off(Pm, 0); idx += gnt) LP[idx] = 0.0;
+    grid.sync();
+    if (blockIdx.x == 0 && tid < 32) {  // beta_o = L^{-1} y_o
+      const double* y = st.y_obs + (size_t)j * m;
+      double* beta = st.beta_o + (size_t)j * m;
+      for (int i = 0; i < m; ++i) {
+        double acc = 0.0;
+        for (int k = tid; k < i; k += 32) acc += A[(size_t)i * m + k] * beta[k];
+        acc = warp_sum(acc);
+        if (tid == 0) beta[i] = (y[i] - acc) / A[(size_t)i * m + i];
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // K0b: explicit inverse of L_oo in sub-panel layout (gpmpc_state.cuh) for the fused / tensor-core kernels: w_o = inv(L_oo) k_o
 // is then a plain product.  cond(L_oo) ~ 1e3 at the reference's configurations: the inverse costs ~1e-14 relative accuracy
 // in the posterior variance, 5 orders below the parity tolerance.  The columns of the inverse are independent:

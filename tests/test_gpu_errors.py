@@ -102,3 +102,26 @@ def test_shim_sample_raises_not_psd():
     with pytest.raises(NotPSDError):
         post.sample(base_samples=torch.zeros(ns, g_ny, 3, T, dtype=torch.float64))
     shim.reset_backends()
+
+
+@pytest.mark.parametrize("n_real", [40, 800])
+def test_real_data_factorisation_failure_is_flagged(n_real):
+    """K0's jitter ladder when the real-data block cannot be factorised (a NaN input): all four attempts fail, the status
+    word carries TRAIN_NOT_PD and nothing hangs -- on the one-CTA kernel (n_real = 40) and on the cooperative multi-CTA one
+    (n_real = 800: every CTA must take the same decision at every grid barrier)."""
+    from sampling_gpmpc_b200.engine import GPEngine, ST_TRAIN_NOT_PD
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(n_real, 2, generator=g, dtype=torch.float64)
+    X[n_real // 2, 0] = float("nan")
+    Y = torch.zeros(2, n_real, 1, dtype=torch.float64)
+    eng = GPEngine(2, 2, 2, 1, n_real)
+    eng.set_hypers(np.ones((2, 2)), np.ones(2), np.full((2, 1), 1e-6), 1e-6)
+    eng.set_real_data(X, Y)
+    assert eng.status() & ST_TRAIN_NOT_PD
+    # and a clean factorisation right after it on the same handle
+    X[n_real // 2, 0] = 0.5
+    eng.status(clear=True)
+    eng.set_real_data(X, Y)
+    assert eng.status() & ST_TRAIN_NOT_PD == 0
+    m, v = eng.posterior(torch.rand(2, 2, 3, 2, dtype=torch.float64))
+    assert torch.isfinite(m).all() and (v > 0).all()
