@@ -46,6 +46,8 @@ extern "C" {
 #define GPMPC_ST_SAMPLE_NOT_PD 4u  /* some posterior covariance not PD after the ladder (jitter_level[b] == 4) */
 #define GPMPC_ST_APPEND_NOT_PD 8u  /* a bordered block (Sigma* + noise) was not PD when conditioning */
 #define GPMPC_ST_NAN_INPUT 16u     /* NaN reached a Cholesky (GPyTorch: NanError) */
+#define GPMPC_ST_SAMPLE_EIG 32u    /* a draw fell back to the eigen root for the whole batch (GPyTorch: root_decomposition
+                                      catches the NotPSDError and uses symeig; jitter_level[b] == 4 for every b) */
 
 typedef struct gpmpc_handle gpmpc_handle;
 
@@ -63,8 +65,12 @@ typedef struct {
   double beta;              /* Dyn_gp_beta: truncate to mean +- beta*sqrt(variance); <0 = no truncation */
   double variance_is_zero;  /* Dyn_gp_variance_is_zero */
   int32_t unclamped_sqrt_1x1; /* 1 = GPyTorch's no-base-samples 1x1 path (sqrt without clamp), else 0 */
-  int32_t reserved;
+  int32_t flags;            /* GPMPC_OPT_* */
 } gpmpc_sample_opts;
+/* Without this flag a joint Cholesky that still fails after the jitter ladder makes the WHOLE batch draw through the
+ * eigen root evecs*sqrt(clamp(evals,0)), like GPyTorch's root_decomposition (src/agent.py:641); with it the failing
+ * elements return NaN and GPMPC_ST_SAMPLE_NOT_PD is the caller's to raise (psd_safe_cholesky's NotPSDError). */
+#define GPMPC_OPT_NO_EIG_FALLBACK 1
 
 /* env hooks of Agent.dyn_fg_jacobians as plain data (src/agent.py:532-564, src/environments/*.py) */
 typedef struct {

@@ -201,7 +201,16 @@ class RefPosterior:
         return res.reshape(*res.shape[:-1], self.H, self.T)
 
     def _root(self):
-        return psd_safe_cholesky(self.covariance_matrix, self.jitter)
+        """linear_operator root_decomposition(method="cholesky"): psd_safe_cholesky, and on ANY RuntimeError (NotPSDError
+        after the ladder, NanError) "Using symeig method": evals, evecs = torch.linalg.eigh(dense) for the WHOLE batch,
+        evals.clamp_min(0), root = evecs * evals.sqrt().unsqueeze(-2) (LinearOperator._symeig / root_decomposition).
+        jitter_level 4 marks that branch (every batch element)."""
+        try:
+            return psd_safe_cholesky(self.covariance_matrix, self.jitter)
+        except RuntimeError:
+            evals, evecs = torch.linalg.eigh(self.covariance_matrix)
+            root = evecs * evals.clamp_min(0.0).sqrt().unsqueeze(-2)
+            return root, torch.full(self.covariance_matrix.shape[:-2], 4, dtype=torch.int32)
 
 
 class RefExactGP:

@@ -104,7 +104,7 @@ class MultitaskMultivariateNormal:
         self.covar_prior = covar
 
 
-_SETTINGS = {"jitter": 1e-6}
+_SETTINGS = {"jitter": 1e-8}  # gpytorch.settings.cholesky_jitter default for float64
 
 
 class ExactGP(_Module):

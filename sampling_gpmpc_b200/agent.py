@@ -328,7 +328,9 @@ class Agent:
         y = self.dyn_fg_jacobians_device(xu_hat, sqp_iter)
         host = torch.empty(y.shape, dtype=F64, pin_memory=True)
         host.copy_(y, non_blocking=True)  # ONE device->host copy (the reference does three, agent.py:555-557)
-        torch.cuda.current_stream().synchronize()
+        # once per SQP iteration, behind the same stream sync: NotPSDError where psd_safe_cholesky would raise it (a failed
+        # conditioning block leaves the factor without the new rows -- never carry on silently)
+        self.engine.raise_on_status()
         h = host.numpy()
         return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]
 

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "gpmpc_assemble.cuh"
@@ -14,10 +16,30 @@
 #include "gpmpc_post.cuh"
 #include "gpmpc_step.cuh"
 #include "gpmpc_block_mma.cuh"
+#include "gpmpc_eig.cuh"
+
+// static shared memory of k_sample_eig (rotation tables + coefficients), rounded up
+#define EIG_STATIC_SMEM (44 * 1024)
 
 namespace {
 std::string g_create_error;
-}
+
+// cudaFuncSetAttribute is per DEVICE: remember (kernel, device) pairs, not one process-wide flag per kernel
+std::set<std::pair<const void*, int>> g_func_configured;
+
+// Every entry point runs on the handle's device whatever the caller's current device is (restored on return).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+}  // namespace
+#define ON_HANDLE_DEVICE(h) DeviceGuard dev_guard_((h) ? (h)->device : -1)
 
 struct gpmpc_handle {
   DevState st{};
@@ -43,6 +65,7 @@ struct gpmpc_handle {
   void* c_scratch = nullptr;
   size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
+  int eig_epoch = 0;  // draw launches so far (gpmpc_eig.cuh: a failing element publishes the epoch of its launch)
   // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) whenever inv(L_oo) does not fit in
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
   // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
@@ -74,6 +97,18 @@ static int fail(gpmpc_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   else g_create_error = msg;
   return code;
+}
+
+// opt a kernel in to `bytes` of dynamic shared memory on the handle's device (once per kernel and device)
+template <typename F>
+static cudaError_t opt_in_smem(gpmpc_handle* h, F func, int bytes, bool prefer_shared = false) {
+  const auto key = std::make_pair((const void*)func, h->device);
+  if (g_func_configured.count(key)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && prefer_shared)
+    e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) g_func_configured.insert(key);
+  return e;
 }
 
 template <typename Tp>
@@ -113,6 +148,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
   CUDA_TRY(h, dev_alloc(&hr, (size_t)cap_points));
   // padding columns [m, mo) must read as 0; rows not yet appended are never used but kept finite
   CUDA_TRY(h, cudaMemsetAsync(Lh, 0, lh_count * sizeof(double), stream));
+  CUDA_TRY(h, cudaMemsetAsync(beta_h, 0, std::max<size_t>(1, B * c_cap) * sizeof(double), stream));
   if (old.Xh && old.np > 0) {
     CUDA_TRY(h, cudaMemcpy2DAsync(Xh, (size_t)cap_points * st.d * 8, old.Xh, (size_t)old.cap_points * st.d * 8,
                                   (size_t)old.np * st.d * 8, B, cudaMemcpyDeviceToDevice, stream));
@@ -146,14 +182,17 @@ static int ensure_workspace(gpmpc_handle* h, int H) {
   // sized for the reserved capacity where one is known (gpmpc_reserve / Agent: H * max_sqp_iter), so that the SQP loop never
   // re-allocates (cudaFree / cudaMalloc synchronise the device: 10-20 ms spikes otherwise)
   const int new_n = std::max(std::max(n + n / 2, st.m + st.c_cap), h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
-  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
-  st.W = st.S = st.C = st.mu = st.xc = nullptr;
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E);
+  st.W = st.S = st.C = st.mu = st.xc = st.E = nullptr;
   const size_t B = (size_t)st.B;
   CUDA_TRY(h, dev_alloc(&st.W, B * new_n * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&st.S, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&st.C, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&st.mu, B * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&st.xc, B * (size_t)new_H * st.d));
+  // iteration matrix of the eigen-root fallback, only where it does not fit in shared memory
+  const bool e_global = (size_t)new_q * new_q * 8 > (size_t)(h->max_dyn_smem - EIG_STATIC_SMEM);
+  CUDA_TRY(h, dev_alloc(&st.E, e_global ? B * (size_t)new_q * new_q : 1));
   h->ws_n = new_n; h->ws_q = new_q; h->ws_H = new_H;
   h->cache_version = -1;
   return GPMPC_OK;
@@ -180,12 +219,25 @@ static size_t tri_bytes(gpmpc_handle* h, int q) {
 }
 
 static int configure_block_smem(gpmpc_handle* h) {
-  static bool configured = false;
-  if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_append, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
-    configured = true;
-  }
+  CUDA_TRY(h, opt_in_smem(h, k_sample, h->max_dyn_smem - 8192));
+  CUDA_TRY(h, opt_in_smem(h, k_append, h->max_dyn_smem - 8192));
+  return GPMPC_OK;
+}
+
+// The eigen-root redo of a draw, queued right behind it; returns at once on the device unless an element of THIS draw
+// (st.eig_epoch) failed its jitter ladder.  `st` must be the DevState the draw kernel was launched with.
+static int launch_sample_eig(gpmpc_handle* h, const DevState& st, int H, const double* eps, const gpmpc_sample_opts& o,
+                             double* y, int* jl, cudaStream_t stream) {
+  if (!eps || (o.flags & GPMPC_OPT_NO_EIG_FALLBACK) || H * st.T == 1) return GPMPC_OK;
+  const int q = H * st.T;
+  if (q > 2 * EIG_MAX_PAIRS) return GPMPC_OK;  // beyond the fallback's tables: the NotPD status stands
+  const int dyn_max = h->max_dyn_smem - EIG_STATIC_SMEM;
+  CUDA_TRY(h, opt_in_smem(h, k_sample_eig, dyn_max));
+  const size_t a_bytes = (size_t)q * q * sizeof(double);
+  const int in_smem = a_bytes <= (size_t)dyn_max ? 1 : 0;
+  k_sample_eig<<<st.B, EIG_THREADS, in_smem ? a_bytes : 0, stream>>>(st, H, eps, o, y, jl, in_smem);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
 }
 
@@ -196,12 +248,8 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   auto gram = k_pm_gram<T>;
   const int q = H * st.T, QB = (q + 7) / 8;
   const size_t slab = (size_t)2 * PM_NSP * PM_SLABC * 8 * sizeof(double);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_pm_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem - 8192));
-    configured = true;
-  }
+  CUDA_TRY(h, opt_in_smem(h, solve, (int)slab));
+  CUDA_TRY(h, opt_in_smem(h, k_pm_finish, h->max_dyn_smem - 8192));
   // the column blocks of one element over ceil(QB / 4) CTAs; the Gram tiles over enough CTAs to fill the GPU
   dim3 gs(st.B, (QB + PM_WARPS - 1) / PM_WARPS);
   solve<<<gs, PM_WARPS * 32, slab, stream>>>(st, x, H);
@@ -215,7 +263,7 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;
   k_pm_finish<<<st.B, BLK_THREADS, tri, stream>>>(st, H, mean, var, eps, o, y, jl, tri ? 1 : 0);
   h->launches += 1;
-  return GPMPC_OK;
+  return launch_sample_eig(h, st, H, eps, o, y, jl, stream);
 }
 
 static int dispatch_posterior_mma(gpmpc_handle* h, const DevState& st, const double* x, int H, double* mean,
@@ -266,6 +314,11 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
     return fail(nullptr, GPMPC_ERR_CUDA, "cudaMalloc(status) failed");
   }
   st.status = status;
+  if (dev_alloc(&st.eig_flag, 1) != cudaSuccess || cudaMemset(st.eig_flag, 0, 4) != cudaSuccess) {
+    cudaFree(status);
+    delete h;
+    return fail(nullptr, GPMPC_ERR_CUDA, "cudaMalloc(eig_flag) failed");
+  }
   if (dev_alloc(&st.fin, (size_t)st.B * (st.T + st.T * (st.T + 1) / 2)) != cudaSuccess) {
     cudaFree(status);
     delete h;
@@ -276,13 +329,14 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
 }
 
 int gpmpc_destroy(gpmpc_handle* h) {
+  ON_HANDLE_DEVICE(h);
   if (!h) return GPMPC_OK;
   DevState& st = h->st;
   free_factor_state(h);
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin); cudaFree(st.Wo);
-  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc);
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.eig_flag);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -292,6 +346,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
 
 int gpmpc_set_hypers(gpmpc_handle* h, const double* lengthscale, const double* outputscale,
                      const double* noise, double jitter) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !lengthscale || !outputscale || !noise) return fail(h, GPMPC_ERR_ARG, "null argument");
   DevState& st = h->st;
   for (int i = 0; i < st.g_ny * st.d; ++i)
@@ -318,6 +373,7 @@ int gpmpc_set_hypers(gpmpc_handle* h, const double* lengthscale, const double* o
 }
 
 int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void* stream_) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !X || !Y) return fail(h, GPMPC_ERR_ARG, "null argument");
   if (!h->have_hypers) return fail(h, GPMPC_ERR_STATE, "call gpmpc_set_hypers first");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -340,9 +396,13 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   for (int j = 0; j < g_ny; ++j)
     for (int i = 0; i < m; ++i) yobs[(size_t)j * m + i] = hy[((size_t)j * n + pt[i]) * T + task[i]];
 
+  h->have_real = false;  // until every allocation and the factorisation below have succeeded
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
+  st.Xr = st.y_obs = st.Yr = nullptr;
+  st.obs_pt = st.obs_task = st.real_full = nullptr;
+  st.Loo = st.LooP = st.beta_o = nullptr;
   // per output: is every task of real point p observed?  (sample_gp's y_train_isnan, src/agent.py:674-679)
   std::vector<int> full((size_t)g_ny * n);
   for (int j = 0; j < g_ny; ++j)
@@ -382,12 +442,8 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     if (rc) return rc;
   }
   {
-    static bool configured = false;
-    if (!configured) {
-      CUDA_TRY(h, cudaFuncSetAttribute(k_factor_real, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-      CUDA_TRY(h, cudaFuncSetAttribute(k_invert_real, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-      configured = true;
-    }
+    CUDA_TRY(h, opt_in_smem(h, k_factor_real, h->max_dyn_smem));
+    CUDA_TRY(h, opt_in_smem(h, k_invert_real, h->max_dyn_smem));
     if ((size_t)m * 8 * K0B_WARPS > (size_t)h->max_dyn_smem)
       return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~7000)");
     // m in the thousands: the factorisation cooperatively over all SMs (one grid barrier per pivot); GPMPC_K0_COOP_MIN_M
@@ -396,11 +452,7 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     int coop_ok = 0;
     cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, h->device);
     if (coop_ok && m >= coop_min_m && (size_t)m * 16 + 1024 <= (size_t)h->max_dyn_smem) {
-      static bool coop_configured = false;
-      if (!coop_configured) {
-        CUDA_TRY(h, cudaFuncSetAttribute(k_factor_real_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-        coop_configured = true;
-      }
+      CUDA_TRY(h, opt_in_smem(h, k_factor_real_coop, h->max_dyn_smem));
       void* args[] = {(void*)&st};
       CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)k_factor_real_coop, dim3(h->num_sms), dim3(K0_THREADS), args,
                                               (size_t)m * 16, stream));
@@ -429,6 +481,7 @@ int gpmpc_reset_hallucinated(gpmpc_handle* h) {
 }
 
 int gpmpc_reserve(gpmpc_handle* h, int32_t cap_points, void* stream) {
+  ON_HANDLE_DEVICE(h);
   if (!h || cap_points < 0) return fail(h, GPMPC_ERR_ARG, "bad capacity");
   if (!h->have_real) { h->st.cap_points = std::max(h->st.cap_points, cap_points); return GPMPC_OK; }
   if (cap_points <= h->st.cap_points) return GPMPC_OK;
@@ -436,6 +489,7 @@ int gpmpc_reserve(gpmpc_handle* h, int32_t cap_points, void* stream) {
 }
 
 int gpmpc_set_condition_on_hallucinated(gpmpc_handle* h, int32_t on) {
+  ON_HANDLE_DEVICE(h);
   if (!h) return GPMPC_ERR_ARG;
   const bool was = h->condition;
   h->condition = on != 0;
@@ -456,12 +510,14 @@ static int check_ready(gpmpc_handle* h) {
 int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, double* var,
                     const double* eps, const gpmpc_sample_opts* opts, double* y, int32_t* jitter_level,
                     void* stream) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / H");
   if (eps && (!opts || !y)) return fail(h, GPMPC_ERR_ARG, "eps given without opts / y");
   rc = ensure_workspace(h, H);
   if (rc) return rc;
+  if (eps) h->st.eig_epoch = ++h->eig_epoch;
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
@@ -470,6 +526,8 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
     if (rc) return rc;
   } else {
     k_posterior<<<st.B, BLK_THREADS, 0, (cudaStream_t)stream>>>(st, x, H, mean, var, eps, o, y, jitter_level);
+    rc = launch_sample_eig(h, st, H, eps, o, y, jitter_level, (cudaStream_t)stream);
+    if (rc) return rc;
   }
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
@@ -481,11 +539,13 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
 
 int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* opts, double* y,
                  int32_t* jitter_level, void* stream) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!eps || !opts || !y) return fail(h, GPMPC_ERR_ARG, "null argument");
   if (h->cache_version != h->factor_version || h->cache_H < 1)
     return fail(h, GPMPC_ERR_STATE, "gpmpc_sample needs a preceding gpmpc_posterior on the current factor");
+  h->st.eig_epoch = ++h->eig_epoch;
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (h->cache_H * st.T);
   rc = configure_block_smem(h);
@@ -495,7 +555,7 @@ int gpmpc_sample(gpmpc_handle* h, const double* eps, const gpmpc_sample_opts* op
   k_sample<<<st.B, BLK_THREADS, tri, (cudaStream_t)stream>>>(st, h->cache_H, eps, *opts, y, jitter_level, tri ? 1 : 0);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
-  return GPMPC_OK;
+  return launch_sample_eig(h, st, h->cache_H, eps, *opts, y, jitter_level, (cudaStream_t)stream);
 }
 
 int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_t* point_active, int32_t H,
@@ -509,6 +569,7 @@ int gpmpc_append(gpmpc_handle* h, const double* x, const double* y, const uint8_
 
 int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const uint8_t* scalar_active, int32_t H,
                         void* stream_) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || !y || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / H");
@@ -580,8 +641,13 @@ template <int T>
 static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                               const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                               cudaStream_t stream) {
-  k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow);
+  k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, 0);
   h->launches++;
+  if (eps && T > 1 && !(o.flags & GPMPC_OPT_NO_EIG_FALLBACK)) {
+    // GPyTorch's batch-wide eigen-root fallback: exits on the device unless an element of this step failed its ladder
+    k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, 1);
+    h->launches++;
+  }
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
 }
@@ -591,11 +657,7 @@ template <int D, int T, int NB>
 static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double* x, cudaStream_t stream) {
   constexpr int E = 8 * NB / T;
   auto kern = k_shared_rows<D, T, NB>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-    configured = true;
-  }
+  CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem));
   const size_t smem = ((size_t)st.mo * 8 * NB + ((E * D + 1) & ~1)) * 8;
   const int n_tiles = (st.ns + E - 1) / E;
   // few row panels (m of a few hundred): 8 warps per CTA balance them better than 16 and two CTAs share an SM
@@ -614,13 +676,7 @@ static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x
                             const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                             int warps, size_t smem, cudaStream_t stream) {
   auto kern = k_step<D, T, LOO_SMEM, WO>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-    configured = true;
-  }
+  CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem, true));
   // persistent CTAs, one per SM, split over the g_ny outputs; each warp loops over samples
   const int want = (st.ns + warps - 1) / warps;
   const int resident = std::max(1, h->num_sms / st.g_ny);
@@ -650,11 +706,7 @@ static int launch_step_shared(gpmpc_handle* h, const DevState& st, const double*
   const int per_cta_need = (groups * st.g_ny + h->num_sms - 1) / h->num_sms;
   warps = std::max(1, std::min(warps, per_cta_need));
   auto kern = k_step_shared<D, T>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_dyn_smem));
-    configured = true;
-  }
+  CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem));
   const int want = (groups + warps - 1) / warps;
   const int resident = std::max(1, h->num_sms / st.g_ny);
   dim3 grid(std::min(want, resident), st.g_ny);
@@ -744,6 +796,7 @@ extern "C" {
 
 int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_sample_opts* opts,
                double* mean, double* var, double* y, int32_t* jitter_level, void* stream_) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x) return fail(h, GPMPC_ERR_ARG, "null x");
@@ -756,6 +809,7 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
   }
   const int grow = (eps && h->condition) ? 1 : 0;
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
+  if (eps) hst.eig_epoch = ++h->eig_epoch;
   count_work(h, 1, grow);
   bool handled = false;
   if (!h->has_partial) {  // the fused kernel finds a point's factor rows through hrow0: whole points only
@@ -784,6 +838,7 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
 
 int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, const double* y_gp, int32_t H,
                    double* out, void* stream) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !env || !xu || !y_gp || !out || H < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
   if (env->nx > GPMPC_MAX_NX || env->nx + env->nu > 2 * GPMPC_MAX_NX || env->g_ny != h->st.g_ny)
     return fail(h, GPMPC_ERR_ARG, "bad env dims");
@@ -805,6 +860,7 @@ int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const
 int gpmpc_rollout_gated(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
                         const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
                         void* const* eps_ready, void* stream_) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!env || !x0 || !u_ff || !eps || !opts || !traj || n_steps < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
@@ -875,6 +931,7 @@ static int ensure_scratch(gpmpc_handle* h, size_t bytes) {
 
 int gpmpc_min_dist_overwrite(gpmpc_handle* h, const double* x, int32_t H, const double* mean, const double* var,
                              double min_dist, double beta, double* y, void* stream) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || !y || H < 1 || (beta >= 0.0 && (!mean || !var))) return fail(h, GPMPC_ERR_ARG, "bad x / y / H / moments");
@@ -889,6 +946,7 @@ int gpmpc_min_dist_overwrite(gpmpc_handle* h, const double* x, int32_t H, const 
 
 int gpmpc_filter_new_points(gpmpc_handle* h, const double* x, int32_t H, double min_dist, int32_t use_hallucinated,
                             double* y, int32_t* counts, void* stream) {
+  ON_HANDLE_DEVICE(h);
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || !y || !counts || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / counts / H");
@@ -904,6 +962,7 @@ int gpmpc_filter_new_points(gpmpc_handle* h, const double* x, int32_t H, double 
 
 int gpmpc_pack_plin(gpmpc_handle* h, const gpmpc_env* env, const double* lin, const double* x_h, const double* tail,
                     int32_t n_tail, int32_t H, int32_t use_feedback_K, double* out, void* stream) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !env || !lin || !x_h || !out || H < 1 || n_tail < 0 || (n_tail > 0 && !tail))
     return fail(h, GPMPC_ERR_ARG, "null argument");
   if (env->nx < 1 || env->nx > GPMPC_MAX_NX || env->nu < 1 || env->nu > GPMPC_MAX_NX)
@@ -921,6 +980,7 @@ int gpmpc_pack_plin(gpmpc_handle* h, const gpmpc_env* env, const double* lin, co
 
 int gpmpc_traj_stats(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, const double* ref,
                      double* box_min, double* box_max, double* max_dev, void* stream_) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !traj || ns < 1 || nx < 1 || H1 < 1) return fail(h, GPMPC_ERR_ARG, "bad traj / dims");
   if (max_dev && !ref) return fail(h, GPMPC_ERR_ARG, "max_dev needs a reference trajectory");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -987,6 +1047,7 @@ int gpmpc_hull2d(const double* xy, int32_t n, int32_t* hull_pos, int32_t* hull_n
 
 int gpmpc_stage_hulls(gpmpc_handle* h, const double* traj, int32_t ns, int32_t nx, int32_t H1, int32_t i0, int32_t i1,
                       int32_t max_vertices, int32_t* hull_idx, int32_t* hull_n, void* stream_) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !traj || !hull_idx || !hull_n || ns < 1 || nx < 1 || H1 < 1 || max_vertices < 1 || i0 < 0 || i1 < 0 ||
       i0 >= nx || i1 >= nx || i0 == i1)
     return fail(h, GPMPC_ERR_ARG, "bad traj / dims / coordinate pair");
@@ -1068,6 +1129,7 @@ int32_t gpmpc_num_factor_rows(const gpmpc_handle* h) { return h ? h->st.c : -1; 
 int32_t gpmpc_num_real_observed(const gpmpc_handle* h) { return h ? h->st.m : -1; }
 
 int gpmpc_export_hallucinated(const gpmpc_handle* h_, double* X, double* Y, void* stream) {
+  ON_HANDLE_DEVICE(h_);
   gpmpc_handle* h = const_cast<gpmpc_handle*>(h_);
   if (!h || !X || !Y) return fail(h, GPMPC_ERR_ARG, "null argument");
   const DevState& st = h->st;
@@ -1080,6 +1142,7 @@ int gpmpc_export_hallucinated(const gpmpc_handle* h_, double* X, double* Y, void
 }
 
 int gpmpc_status(gpmpc_handle* h, uint32_t* status, int32_t clear, void* stream) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !status) return fail(h, GPMPC_ERR_ARG, "null argument");
   CUDA_TRY(h, cudaMemcpyAsync(status, h->st.status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   if (clear) CUDA_TRY(h, cudaMemsetAsync(h->st.status, 0, 4, (cudaStream_t)stream));
@@ -1117,6 +1180,7 @@ int gpmpc_set_timing(gpmpc_handle* h, int32_t on) {
 }
 
 int gpmpc_rollout_kernel_ms(gpmpc_handle* h, double* total_ms, int32_t* launches) {
+  ON_HANDLE_DEVICE(h);
   if (!h || !total_ms || !launches) return fail(h, GPMPC_ERR_ARG, "null argument");
   *total_ms = 0.0;
   *launches = h->ev_used / 2;

@@ -326,6 +326,8 @@ __device__ void block_posterior(const DevState& st, int b, const double* __restr
   __syncthreads();
 }
 
+__device__ void block_postprocess(const DevState& st, int b, int H, gpmpc_sample_opts opts, double* __restrict__ yb);
+
 // chol(Sigma*) with the psd_safe_cholesky ladder, y = mu + L eps, then sample_gp's post-processing
 // (zero-variance -> mean, truncation to mean +- beta sqrt(var); src/agent.py:646-663,701-708).
 // tri != NULL: shared-memory scratch of at least q(q+1)/2 doubles for the factorisation (packed lower triangle).
@@ -366,7 +368,15 @@ __device__ void block_sample(const DevState& st, int b, int H, const double* __r
       // NaN anywhere makes GPyTorch raise NanError instead of climbing the ladder
       if (level == GP_MAX_TRIES) {
         level = 4;
-        if (tid == 0) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+        // a NaN in the matrix is GPyTorch's NanError (and eigh of a NaN matrix raises too): no eigen fallback for that
+        int nan_here = 0;
+        for (int idx = tid; idx < q * q; idx += nt) nan_here |= (idx % q <= idx / q && isnan(S[idx])) ? 1 : 0;
+        const int has_nan = __syncthreads_or(nan_here);
+        if (tid == 0) {
+          atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD | (has_nan ? GPMPC_ST_NAN_INPUT : 0u));
+          // GPyTorch: the whole batch falls back to the eigen root (gpmpc_eig.cuh) -- tell the kernel queued behind this one
+          if (!has_nan && !(opts.flags & GPMPC_OPT_NO_EIG_FALLBACK)) atomicMax(st.eig_flag, st.eig_epoch);
+        }
         break;
       }
       ++level;
@@ -385,6 +395,15 @@ __device__ void block_sample(const DevState& st, int b, int H, const double* __r
     yb[r] = acc;
   }
   __syncthreads();
+  block_postprocess(st, b, H, opts, yb);
+}
+
+// sample_gp's post-processing of a draw yb [q] (zero-variance -> mean, truncation; src/agent.py:646-663,701-708)
+__device__ void block_postprocess(const DevState& st, int b, int H, gpmpc_sample_opts opts, double* __restrict__ yb) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int T = st.T, q = H * T;
+  const double* S = st.S + (size_t)b * q * q;
+  const double* mu = st.mu + (size_t)b * q;
   for (int h = tid; h < H; h += nt) {
     bool zero = opts.variance_is_zero >= 0.0;
     if (zero)

@@ -70,6 +70,8 @@ struct DevState {
   double* Wo;           // [B][mo][T]  shared rows inv(L_oo) k_o of the current step (k_shared_rows -> k_step<WO>), large m only
   double* fin;          // [B][T + T(T+1)/2]  W^T beta and lower(W^T W) of the last fused step (k_step -> k_step_finish)
   unsigned* status;     // device status word (GPMPC_ST_*)
+  int* eig_flag;        // epoch of the last draw in which some element's jitter ladder failed (gpmpc_eig.cuh)
+  int eig_epoch;        // epoch of the current draw launch
   // workspace of the block kernels ---------------------------------------------------------
   double* W;            // [B][n_ws][q]   L^{-1} K_{o*}
   long long W_stride;   // n_ws * q
@@ -77,6 +79,7 @@ struct DevState {
   double* C;            // [B][q][q]  scratch for Cholesky
   double* mu;           // [B][q]
   double* xc;           // [B][H][d]  test points the cache was built for
+  double* E;            // [B][q][q]  iteration matrix of the eigen-root fallback when it does not fit in shared memory
 };
 
 // cov( task ta of f at xa , task tb of f at xb ) for the scaled SE kernel with derivative tasks

@@ -28,6 +28,7 @@
 // inputs: HBM-bound by design (DESIGN.md "Roofline"); the host counts the algorithmic bytes per launch.
 #pragma once
 #include "gpmpc_state.cuh"
+#include "gpmpc_eig.cuh"
 
 #ifndef STEP_MAX_WARPS
 #define STEP_MAX_WARPS 16  // warps per CTA are chosen per launch (shared-memory budget), one CTA per SM
@@ -794,10 +795,14 @@ template <int T>
 __global__ void __launch_bounds__(FIN_THREADS)
 k_step_finish(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
               double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-              int* __restrict__ jitter_level, int grow_factor) {
+              int* __restrict__ jitter_level, int grow_factor, int eig_redo) {
   constexpr int FS = T + T * (T + 1) / 2;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= st.B) return;
+  // eig_redo: the launch queued behind the regular one; it repeats the draw and the append of EVERY element through the
+  // eigen root iff some element's jitter ladder failed in this step (GPyTorch's batch-wide symeig fallback, gpmpc_eig.cuh).
+  // Everything this kernel writes depends only on st.fin, eps and the old factor rows, so the repeat simply overwrites.
+  if (eig_redo && (T == 1 || *(volatile int*)st.eig_flag != st.eig_epoch)) return;
   const int j_out = b % st.g_ny, d = st.d, c = st.c, mo = st.mo;
   const double* fi = st.fin + (size_t)b * FS;
   const double os = st.os[j_out];
@@ -828,25 +833,44 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
   // ---- E: draw ------------------------------------------------------------------------------------
   TriT<T> Lc;
   int level = 0;
-  if (T == 1) {
-    Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
-  } else {
-    bool ok = chol_T<T>(S, 0.0, Lc);
-    double jit = st.jitter;
-    while (!ok && level < GP_MAX_TRIES) {
-      ++level;
-      ok = chol_T<T>(S, jit, Lc);
-      jit *= 10.0;
-    }
-    if (!ok) level = 4;
-  }
   double yv[T];
+  if (eig_redo) {
+    double R[T * T];
+    eig_root_T<T>(S.v, R);
+    level = 4;
+    for (int r = 0; r < T; ++r) {
+      double acc = macc[r];
+      for (int s = 0; s < T; ++s) acc += R[r * T + s] * eps[(size_t)b * T + s];
+      yv[r] = acc;
+    }
+    if (b == 0) atomicOr(st.status, GPMPC_ST_SAMPLE_EIG);
+  } else {
+    if (T == 1) {
+      Lc.v[0] = opts.unclamped_sqrt_1x1 ? sqrt(S.v[0]) : sqrt(fmax(S.v[0], 0.0));
+    } else {
+      bool ok = chol_T<T>(S, 0.0, Lc);
+      double jit = st.jitter;
+      while (!ok && level < GP_MAX_TRIES) {
+        ++level;
+        ok = chol_T<T>(S, jit, Lc);
+        jit *= 10.0;
+      }
+      if (!ok) {
+        level = 4;
+        bool has_nan = false;  // NaN in the matrix: GPyTorch's NanError, no eigen fallback
 #pragma unroll
-  for (int r = 0; r < T; ++r) {
-    double acc = macc[r];
+        for (int i = 0; i < T * (T + 1) / 2; ++i) has_nan = has_nan || isnan(S.v[i]);
+        if (has_nan) atomicOr(st.status, GPMPC_ST_NAN_INPUT);
+        else if (!(opts.flags & GPMPC_OPT_NO_EIG_FALLBACK)) atomicMax(st.eig_flag, st.eig_epoch);
+      }
+    }
 #pragma unroll
-    for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
-    yv[r] = level < 4 ? acc : nan("");
+    for (int r = 0; r < T; ++r) {
+      double acc = macc[r];
+#pragma unroll
+      for (int s = 0; s <= r; ++s) acc += Lc.at(r, s) * eps[(size_t)b * T + s];
+      yv[r] = level < 4 ? acc : nan("");
+    }
   }
   bool zero = opts.variance_is_zero >= 0.0;
 #pragma unroll
@@ -861,7 +885,7 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
     y[(size_t)b * T + r] = yv[r];
   }
   if (jitter_level) jitter_level[b] = level;
-  if (level == 4) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+  if (level == 4 && !eig_redo) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
 
   // ---- F (second half): condition on (x*, y) --------------------------------------------------------
   for (int a = 0; a < d; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * d + a] = x[(size_t)b * d + a];

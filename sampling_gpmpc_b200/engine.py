@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("GPMPC_B200_LIB", os.path.join(_HERE, "libgpmpc_b200.s
 
 MAX_D, MAX_T, MAX_NX = 6, 7, 8
 
-ST_TRAIN_JITTER, ST_TRAIN_NOT_PD, ST_SAMPLE_NOT_PD, ST_APPEND_NOT_PD, ST_NAN_INPUT = 1, 2, 4, 8, 16
+ST_TRAIN_JITTER, ST_TRAIN_NOT_PD, ST_SAMPLE_NOT_PD, ST_APPEND_NOT_PD, ST_NAN_INPUT, ST_SAMPLE_EIG = 1, 2, 4, 8, 16, 32
+OPT_NO_EIG_FALLBACK = 1
 
 
 class GpmpcDims(C.Structure):
@@ -28,7 +29,7 @@ class GpmpcDims(C.Structure):
 
 class GpmpcSampleOpts(C.Structure):
     _fields_ = [("beta", C.c_double), ("variance_is_zero", C.c_double),
-                ("unclamped_sqrt_1x1", C.c_int32), ("reserved", C.c_int32)]
+                ("unclamped_sqrt_1x1", C.c_int32), ("flags", C.c_int32)]
 
 
 class GpmpcEnv(C.Structure):
@@ -107,6 +108,10 @@ class NotPSDError(GPEngineError):
     """Counterpart of linear_operator's NotPSDError (posterior covariance not PD after the jitter ladder)."""
 
 
+class NanError(GPEngineError):
+    """Counterpart of linear_operator's NanError (a NaN reached a Cholesky factorisation)."""
+
+
 def _ptr(t: Optional[torch.Tensor]):
     if t is None:
         return None
@@ -115,8 +120,8 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def make_env_struct(spec, feedback_K=None, x_equi=None) -> GpmpcEnv:
@@ -196,21 +201,24 @@ class GPEngine:
         X = X.to(self.device, torch.float64).contiguous()
         Y = Y.to(self.device, torch.float64).contiguous()
         assert X.shape == (self.n_real, self.d) and Y.shape == (self.g_ny, self.n_real, self.T)
-        self._check(self.lib.gpmpc_set_real_data(self.h, _ptr(X), _ptr(Y), _stream()), "gpmpc_set_real_data")
+        self._check(self.lib.gpmpc_set_real_data(self.h, _ptr(X), _ptr(Y), _stream(self.device)), "gpmpc_set_real_data")
 
     def reset_hallucinated(self):
         self._check(self.lib.gpmpc_reset_hallucinated(self.h), "gpmpc_reset_hallucinated")
 
     def reserve(self, cap_points: int):
-        self._check(self.lib.gpmpc_reserve(self.h, int(cap_points), _stream()), "gpmpc_reserve")
+        self._check(self.lib.gpmpc_reserve(self.h, int(cap_points), _stream(self.device)), "gpmpc_reserve")
 
     def set_condition_on_hallucinated(self, on: bool):
         self._check(self.lib.gpmpc_set_condition_on_hallucinated(self.h, int(on)), "gpmpc_set_condition")
 
     # ---- hot path ------------------------------------------------------------------------------
     @staticmethod
-    def opts(beta=-1.0, variance_is_zero=-1.0, unclamped_sqrt_1x1=False) -> GpmpcSampleOpts:
-        return GpmpcSampleOpts(float(beta), float(variance_is_zero), int(unclamped_sqrt_1x1), 0)
+    def opts(beta=-1.0, variance_is_zero=-1.0, unclamped_sqrt_1x1=False, eig_fallback=True) -> GpmpcSampleOpts:
+        """eig_fallback (default, GPyTorch's behaviour): a joint Cholesky that fails after the jitter ladder makes the
+        whole batch draw through the eigen root; off: failing elements return NaN and raise_on_status raises."""
+        return GpmpcSampleOpts(float(beta), float(variance_is_zero), int(unclamped_sqrt_1x1),
+                               0 if eig_fallback else OPT_NO_EIG_FALLBACK)
 
     def _x(self, x: torch.Tensor, H: int) -> torch.Tensor:
         x = x.to(self.device, torch.float64).reshape(self.B, H, self.d)
@@ -230,7 +238,7 @@ class GPEngine:
             jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
             opts = opts or self.opts()
         rc = self.lib.gpmpc_posterior(self.h, _ptr(xx), H, _ptr(mean), _ptr(var), _ptr(eps),
-                                      C.byref(opts) if opts is not None else None, _ptr(y), _ptr(jl), _stream())
+                                      C.byref(opts) if opts is not None else None, _ptr(y), _ptr(jl), _stream(self.device))
         self._check(rc, "gpmpc_posterior")
         return (mean, var) if eps is None else (mean, var, y, jl)
 
@@ -239,7 +247,7 @@ class GPEngine:
         y = torch.empty((self.ns, self.g_ny, H, self.T), dtype=torch.float64, device=self.device)
         jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
         opts = opts or self.opts()
-        self._check(self.lib.gpmpc_sample(self.h, _ptr(eps), C.byref(opts), _ptr(y), _ptr(jl), _stream()), "gpmpc_sample")
+        self._check(self.lib.gpmpc_sample(self.h, _ptr(eps), C.byref(opts), _ptr(y), _ptr(jl), _stream(self.device)), "gpmpc_sample")
         return y, jl
 
     def append(self, x: torch.Tensor, y: torch.Tensor, point_active: Optional[np.ndarray] = None):
@@ -250,7 +258,7 @@ class GPEngine:
         if point_active is not None:
             pa = np.ascontiguousarray(np.asarray(point_active, dtype=np.uint8).reshape(H))
             act = pa.ctypes.data_as(C.POINTER(C.c_uint8))
-        self._check(self.lib.gpmpc_append(self.h, _ptr(xx), _ptr(yy), act, H, _stream()), "gpmpc_append")
+        self._check(self.lib.gpmpc_append(self.h, _ptr(xx), _ptr(yy), act, H, _stream(self.device)), "gpmpc_append")
 
     def append_masked(self, x: torch.Tensor, y: torch.Tensor, scalar_active: np.ndarray):
         """append with one flag per new scalar: scalar_active (H, T) bool / uint8 (a point may enter with some tasks only)."""
@@ -259,7 +267,7 @@ class GPEngine:
         yy = y.to(self.device, torch.float64).reshape(self.B, H * self.T).contiguous()
         sa = np.ascontiguousarray(np.asarray(scalar_active, dtype=np.uint8).reshape(H * self.T))
         self._check(self.lib.gpmpc_append_masked(self.h, _ptr(xx), _ptr(yy), sa.ctypes.data_as(C.POINTER(C.c_uint8)), H,
-                                                 _stream()), "gpmpc_append_masked")
+                                                 _stream(self.device)), "gpmpc_append_masked")
 
     def step(self, x: torch.Tensor, eps: Optional[torch.Tensor], opts: Optional[GpmpcSampleOpts] = None,
              want_moments: bool = True):
@@ -275,7 +283,7 @@ class GPEngine:
             jl = torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device)
             opts = opts or self.opts()
         rc = self.lib.gpmpc_step(self.h, _ptr(xx), _ptr(eps), C.byref(opts) if opts is not None else None,
-                                 _ptr(mean), _ptr(var), _ptr(y), _ptr(jl), _stream())
+                                 _ptr(mean), _ptr(var), _ptr(y), _ptr(jl), _stream(self.device))
         self._check(rc, "gpmpc_step")
         return (mean, var) if eps is None else (mean, var, y, jl)
 
@@ -285,7 +293,7 @@ class GPEngine:
         xu = xu.to(self.device, torch.float64).contiguous()
         y_gp = y_gp.to(self.device, torch.float64).contiguous()
         out = torch.empty((ns, nx, H, 1 + nz), dtype=torch.float64, device=self.device)
-        self._check(self.lib.gpmpc_assemble(self.h, C.byref(env), _ptr(xu), _ptr(y_gp), H, _ptr(out), _stream()),
+        self._check(self.lib.gpmpc_assemble(self.h, C.byref(env), _ptr(xu), _ptr(y_gp), H, _ptr(out), _stream(self.device)),
                     "gpmpc_assemble")
         return out
 
@@ -299,7 +307,7 @@ class GPEngine:
         if traj is None:
             traj = torch.empty((self.ns, env.nx, n_steps + 1), dtype=torch.float64, device=self.device)
         rc = self.lib.gpmpc_rollout(self.h, C.byref(env), _ptr(x0), _ptr(u_ff), _ptr(eps), C.byref(opts), n_steps,
-                                    _ptr(traj), _stream())
+                                    _ptr(traj), _stream(self.device))
         self._check(rc, "gpmpc_rollout")
         return traj
 
@@ -328,7 +336,7 @@ class GPEngine:
                 events.append(ev)
                 ready[t0] = ev.cuda_event
         rc = self.lib.gpmpc_rollout_gated(self.h, C.byref(env), _ptr(x0), _ptr(u_ff), _ptr(eps_dev), C.byref(opts),
-                                          n_steps, _ptr(traj), ready, _stream())
+                                          n_steps, _ptr(traj), ready, _stream(self.device))
         self._check(rc, "gpmpc_rollout_gated")
         self._keep_events = events  # alive until the next call (the waits are already queued)
         return traj
@@ -340,7 +348,7 @@ class GPEngine:
         H = x.shape[-2]
         assert y.is_contiguous() and y.shape == (self.ns, self.g_ny, H, self.T)
         rc = self.lib.gpmpc_min_dist_overwrite(self.h, _ptr(self._x(x, H)), H, _ptr(mean), _ptr(var), float(min_dist),
-                                               float(beta), _ptr(y), _stream())
+                                               float(beta), _ptr(y), _stream(self.device))
         self._check(rc, "gpmpc_min_dist_overwrite")
         return y
 
@@ -351,7 +359,7 @@ class GPEngine:
         assert y.is_contiguous() and y.shape == (self.ns, self.g_ny, H, self.T)
         counts = torch.empty((self.g_ny, H), dtype=torch.int32, device=self.device)
         rc = self.lib.gpmpc_filter_new_points(self.h, _ptr(self._x(x, H)), H, float(min_dist), int(use_hallucinated),
-                                              _ptr(y), _ptr(counts), _stream())
+                                              _ptr(y), _ptr(counts), _stream(self.device))
         self._check(rc, "gpmpc_filter_new_points")
         return counts
 
@@ -368,7 +376,7 @@ class GPEngine:
         if out is None:
             out = torch.empty((H, P), dtype=torch.float64, device=self.device)
         rc = self.lib.gpmpc_pack_plin(self.h, C.byref(env), _ptr(lin), _ptr(x_h), _ptr(tail), n_tail, H,
-                                      int(use_feedback_K), _ptr(out), _stream())
+                                      int(use_feedback_K), _ptr(out), _stream(self.device))
         self._check(rc, "gpmpc_pack_plin")
         return out
 
@@ -380,7 +388,7 @@ class GPEngine:
         lo, hi = mk(), mk()
         dev = mk() if ref is not None else None
         ref = None if ref is None else ref.to(self.device, torch.float64).contiguous()
-        rc = self.lib.gpmpc_traj_stats(self.h, _ptr(traj), ns, nx, H1, _ptr(ref), _ptr(lo), _ptr(hi), _ptr(dev), _stream())
+        rc = self.lib.gpmpc_traj_stats(self.h, _ptr(traj), ns, nx, H1, _ptr(ref), _ptr(lo), _ptr(hi), _ptr(dev), _stream(self.device))
         self._check(rc, "gpmpc_traj_stats")
         return (lo, hi) if ref is None else (lo, hi, dev)
 
@@ -393,7 +401,7 @@ class GPEngine:
         n = np.empty((H1,), dtype=np.int32)
         rc = self.lib.gpmpc_stage_hulls(self.h, _ptr(traj), ns, nx, H1, i0, i1, max_vertices,
                                         idx.ctypes.data_as(C.POINTER(C.c_int32)), n.ctypes.data_as(C.POINTER(C.c_int32)),
-                                        _stream())
+                                        _stream(self.device))
         self._check(rc, "gpmpc_stage_hulls")
         return [idx[t, : n[t]].copy() for t in range(H1)]
 
@@ -415,20 +423,35 @@ class GPEngine:
         X = torch.empty((self.ns, self.g_ny, n, self.d), dtype=torch.float64, device=self.device)
         Y = torch.empty((self.ns, self.g_ny, n, self.T), dtype=torch.float64, device=self.device)
         if n:
-            self._check(self.lib.gpmpc_export_hallucinated(self.h, _ptr(X), _ptr(Y), _stream()), "gpmpc_export")
+            self._check(self.lib.gpmpc_export_hallucinated(self.h, _ptr(X), _ptr(Y), _stream(self.device)), "gpmpc_export")
         return X, Y
 
     def status(self, clear: bool = False) -> int:
         s = C.c_uint32(0)
-        self._check(self.lib.gpmpc_status(self.h, C.byref(s), int(clear), _stream()), "gpmpc_status")
+        self._check(self.lib.gpmpc_status(self.h, C.byref(s), int(clear), _stream(self.device)), "gpmpc_status")
         return int(s.value)
 
     def engine_status_ok(self) -> bool:
-        """True when no Cholesky failed (a jitter-ladder escalation of the real-data block is not a failure)."""
-        return self.status() & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD | ST_NAN_INPUT) == 0
+        """True when no Cholesky failed (a jitter-ladder escalation of the real-data block is not a failure, and neither
+        is a draw that GPyTorch-style fell back to the eigen root)."""
+        s = self.status()
+        if s & ST_SAMPLE_EIG:
+            s &= ~ST_SAMPLE_NOT_PD
+        return s & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD | ST_NAN_INPUT) == 0
 
     def raise_on_status(self):
+        """Reads and clears the device status word (one 4-byte copy + stream sync).  Raises NotPSDError where GPyTorch's
+        psd_safe_cholesky would (real-data block / conditioning block not PD; a draw not PD with the eigen fallback off);
+        warns where linear_operator warns and carries on (draw through the eigen root).  After an ST_APPEND_NOT_PD the
+        failing elements' new factor rows were not written: the handle is unusable until reset_hallucinated()."""
         s = self.status(clear=True)
+        if s & ST_NAN_INPUT:
+            raise NanError(f"NaN in a matrix to be factorised (status {s:#x})")
+        if s & ST_SAMPLE_EIG:
+            import warnings
+            warnings.warn("Cholesky of a posterior covariance failed after the jitter ladder; the batch was drawn "
+                          "through the eigen root (GPyTorch: 'Using symeig method')", RuntimeWarning, stacklevel=2)
+            s &= ~ST_SAMPLE_NOT_PD
         if s & (ST_SAMPLE_NOT_PD | ST_TRAIN_NOT_PD | ST_APPEND_NOT_PD):
             raise NotPSDError(f"matrix not positive definite after the jitter ladder (status {s:#x})")
         return s

@@ -34,7 +34,7 @@ from .engine import GPEngine, NotPSDError
 
 F64 = torch.float64
 _SOFTPLUS_0 = 0.6931471805599453  # value of an untouched GPyTorch raw parameter (softplus(0))
-_SETTINGS = {"jitter": 1e-6, "nan_policy": "ignore"}
+_SETTINGS = {"jitter": 1e-8, "nan_policy": "ignore"}  # gpytorch.settings.cholesky_jitter default for float64
 
 
 class _Module:

@@ -60,13 +60,22 @@ class ForwardRollout:
         self.opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
         self.x0 = torch.tensor(params["env"]["start"], dtype=F64, device=self.device).expand(self.ns, -1).contiguous()
 
-    def run(self, u_ff: torch.Tensor, eps: torch.Tensor, traj: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def run(self, u_ff: torch.Tensor, eps: torch.Tensor, traj: Optional[torch.Tensor] = None,
+            check: bool = False) -> torch.Tensor:
         """u_ff (steps, nu); eps (steps, ns_global or ns, g_ny, 1, T) standard-normal draws (the reference's
-        epistimic_random_vector[:, 1]).  Returns this rank's trajectories (ns, nx, steps+1) on the device."""
+        epistimic_random_vector[:, 1]).  Returns this rank's trajectories (ns, nx, steps+1) on the device.  The call
+        only queues work; `check=True` (or `check()` later) waits for it and raises NotPSDError where GPyTorch would."""
         if eps.shape[1] == self.ns_global and self.world_size > 1:
             eps = eps[:, self.s_lo:self.s_hi]
         self.engine.reset_hallucinated()
-        return self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
+        out = self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
+        if check:
+            self.check()
+        return out
+
+    def check(self) -> int:
+        """Synchronises and turns the device status word into the reference's error behaviour (engine.raise_on_status)."""
+        return self.engine.raise_on_status()
 
     def run_from_host(self, u_ff: torch.Tensor, eps_host: torch.Tensor, traj: Optional[torch.Tensor] = None,
                       traj_host: Optional[torch.Tensor] = None, chunk_steps: int = 5) -> torch.Tensor:

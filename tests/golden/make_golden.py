@@ -39,12 +39,17 @@ CASES = {
     # as shipped: one sample overwritten by the true dynamics, the model is still evaluated (agent.py:583-616)
     "car_residual_truedyn": ("params_car_residual", {"optimizer.H": 10, "optimizer.SEMPC.max_sqp_iter": 2,
                                                      "common.num_MPC_itrs": 2}, 2, 2),
-    # sampling switched on as SURVEY.md 8(d) config 3 suggests; the yaml's jitter 1e-20 makes the joint
-    # q x q Cholesky fail (GPyTorch would fall back to symeig), so the fixture uses 1e-9
+    # sampling switched on as SURVEY.md 8(d) config 3 suggests, at the yaml's own jitter 1e-20 (params_car_residual.yaml:51):
+    # the ladder is a no-op, the joint q x q Cholesky fails on the near-duplicate iterates and the draw goes through
+    # root_decomposition's eigen root for the whole batch (jitter_level 4 in the fixture marks those calls)
     "car_residual_sqp": ("params_car_residual", {"agent.num_dyn_samples": 4, "agent.true_dyn_as_sample": False,
-                                                 "agent.Dyn_gp_jitter": 1.0e-9,
                                                  "optimizer.H": 10, "optimizer.SEMPC.max_sqp_iter": 3,
                                                  "common.num_MPC_itrs": 2}, 2, 3),
+    # the same with a working ladder (1e-9): Cholesky draws, comparable sample by sample
+    "car_residual_sqp_jit": ("params_car_residual", {"agent.num_dyn_samples": 4, "agent.true_dyn_as_sample": False,
+                                                     "agent.Dyn_gp_jitter": 1.0e-9,
+                                                     "optimizer.H": 10, "optimizer.SEMPC.max_sqp_iter": 3,
+                                                     "common.num_MPC_itrs": 2}, 2, 3),
     "car_residual_fs": ("params_car_residual_fs", {"agent.num_dyn_samples": 8, "common.num_MPC_itrs": 6}, 6, 1),
     "pendulum2D_sqp": ("params_pendulum", {"agent.num_dyn_samples": 4, "optimizer.H": 8, "common.num_MPC_itrs": 2}, 2, 3),
     # params_car.yaml is stale w.r.t. src/agent.py:32: supply the missing key

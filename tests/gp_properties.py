@@ -114,3 +114,19 @@ def sequential_draw(mean, cov, eps):
 def rel_err(a, b, scale):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), scale))) if a.size else 0.0
+
+
+def compare_modulo_eigenvector_signs(y, post, eps, scale):
+    """y, eps (q,), post = (mean (q,), cov (q,q)) of ONE batch element.  The draw must be mean + sum_k s_k sqrt(l_k) e_k v_k
+    with s_k = +-1, i.e. |v_k . (y - mean)| = sqrt(l_k) |e_k| for every k (V is orthonormal, so this pins y - mean up to
+    those signs).  Any eigh resolves eigenvalues only to ~eps_machine * l_max absolutely, which moves sqrt(l_k) e_k by up
+    to sqrt(eps_machine * l_max) |e_k| for the (near-)null directions: that floor is added to the 1e-9 tolerance."""
+    mean, cov = post
+    lam, V = torch.linalg.eigh(cov)
+    coef = (V.T @ (y - mean)).abs()
+    want = lam.clamp_min(0.0).sqrt() * eps.abs()
+    # Sigma* = K** - W^T W carries absolute rounding ~eps_machine * outputscale (= scale^2), whatever its own size
+    tol = 1e-9 * scale + 4.0 * float(np.sqrt(2.3e-16 * max(float(lam.max()), scale ** 2))) * float(eps.abs().max())
+    err = float((coef - want).abs().max())
+    assert err <= tol, (err, tol)
+    assert float(want.max()) > 1e3 * tol  # the comparison is not vacuous: the draw is far above the floor

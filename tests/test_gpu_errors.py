@@ -53,8 +53,9 @@ def test_argument_and_state_errors():
 @pytest.mark.parametrize("mma", [True, False])
 def test_not_positive_definite_is_reported_like_gpytorch(mma):
     """A covariance that stays non-PD through the jitter ladder (here: NaN test inputs of one sample): that element gets
-    jitter_level 4 and NaN draws, the others are unaffected, the status word carries the flag and raise_on_status raises."""
-    from sampling_gpmpc_b200.engine import NotPSDError, ST_SAMPLE_NOT_PD
+    jitter_level 4 and NaN draws, the others are unaffected, the status word carries the flags and raise_on_status raises
+    the counterpart of GPyTorch's NanError (a NaN matrix never takes the eigen-root fallback: eigh raises on it too)."""
+    from sampling_gpmpc_b200.engine import NanError, ST_NAN_INPUT, ST_SAMPLE_EIG, ST_SAMPLE_NOT_PD
     eng = _engine()
     eng.set_block_kernels(mma)
     x = torch.rand(3, 2, 4, 2, dtype=torch.float64) - 0.5
@@ -64,15 +65,15 @@ def test_not_positive_definite_is_reported_like_gpytorch(mma):
     jl = jl.cpu().numpy()
     assert (jl[1] == 4).all() and (jl[[0, 2]] < 4).all()
     assert torch.isnan(y[1]).all() and torch.isfinite(y[[0, 2]]).all()
-    assert eng.status() & ST_SAMPLE_NOT_PD
-    with pytest.raises(NotPSDError):
+    assert eng.status() & ST_SAMPLE_NOT_PD and eng.status() & ST_NAN_INPUT and not eng.status() & ST_SAMPLE_EIG
+    with pytest.raises(NanError):
         eng.raise_on_status()
     assert eng.status() == 0  # cleared by raise_on_status
 
 
-def test_shim_sample_raises_not_psd():
+def test_shim_sample_raises_on_nan_like_gpytorch():
     from sampling_gpmpc_b200 import gpytorch_shim as shim
-    from sampling_gpmpc_b200.engine import NotPSDError
+    from sampling_gpmpc_b200.engine import NanError
     shim.reset_backends()
     G = shim.namespace()
     ns, g_ny, n, d, T = 2, 1, 9, 2, 3
@@ -99,7 +100,7 @@ def test_shim_sample_raises_not_psd():
     xq = torch.rand(ns, g_ny, 3, d, generator=g, dtype=torch.float64)
     xq[0] = float("nan")
     post = model(xq.cuda())
-    with pytest.raises(NotPSDError):
+    with pytest.raises(NanError):
         post.sample(base_samples=torch.zeros(ns, g_ny, 3, T, dtype=torch.float64))
     shim.reset_backends()
 

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.replay import CASES, load_case, n_calls, outputscales, replay, scaled_close
+from tests.replay import CASES, EIGEN_ROOT, load_case, n_calls, outputscales, replay, scaled_close
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ def _make_agent(params, z):
 # flip (measured in DESIGN.md "Conditioning").  Free-running replay is only meaningful for the others; the
 # ill-conditioned ones are covered by test_one_step_parity_under_identical_history below.
 ILL_CONDITIONED = ["pendulum2D_sqp", "car_sqp"]
-WELL_CONDITIONED = [c for c in CASES if c not in ILL_CONDITIONED]
+WELL_CONDITIONED = [c for c in CASES if c not in ILL_CONDITIONED + EIGEN_ROOT]
 
 
 @pytest.mark.parametrize("case", WELL_CONDITIONED)
@@ -466,7 +466,7 @@ def test_one_step_parity_under_identical_history(case):
     n_sqp = params["optimizer"]["SEMPC"]["max_sqp_iter"]
     jitter = params["agent"]["Dyn_gp_jitter"]
     worst = {"mean": 0.0, "variance": 0.0, "y_sample_over_allowed": 0.0}
-    flips = marginal_flips = total = 0
+    flips = marginal_flips = total = eig_calls = 0
     for k in range(n_calls(z)):
         mpc, sqp = divmod(k, n_sqp)
         for a in (gpu, ref):
@@ -479,9 +479,29 @@ def test_one_step_parity_under_identical_history(case):
         y_gpu = gpu.sample_gp(g_ref.cuda(), eps.cuda()).cpu()
         mean, var = gpu.model_i_call.mean.cpu().numpy(), gpu.model_i_call.variance.cpu().numpy()
         lvl_g, lvl_r = gpu.model_i_call.jitter_level.cpu(), ref.model_i_call.jitter_level
+        if int(lvl_r.max()) == 4:
+            # GPyTorch's eigen-root fallback (whole batch): same decision, raw draws equal modulo one sign per eigenvector,
+            # and the post-processed sample is the truncation of the GPU's own raw draw
+            from tests import gp_properties as P
+            assert bool((lvl_g == 4).all()), f"{case} call {k}: the GPU did not take the eigen-root fallback"
+            _, _, raw_g, _ = gpu.engine.posterior(g_ref.cuda(), eps.cuda(), gpu.engine.opts())
+            raw_g = raw_g.cpu()
+            cov = ref.model_i_call.covariance_matrix
+            for s_ in range(mean.shape[0]):
+                for j in range(mean.shape[1]):
+                    P.compare_modulo_eigenvector_signs(raw_g[s_, j].reshape(-1), (ref.model_i_call.mean[s_, j].reshape(-1),
+                                                       cov[s_, j]), eps[s_, j].reshape(-1), np.sqrt(os_[j]))
+            beta = params["agent"]["Dyn_gp_beta"]
+            sd = gpu.model_i_call.variance.cpu().sqrt()
+            mg = gpu.model_i_call.mean.cpu()
+            clamped = torch.min(torch.max(raw_g, mg - beta * sd), mg + beta * sd)
+            assert float((y_gpu - clamped).abs().max()) <= 1e-15  # the kernel's bounds are fused multiply-adds
+            eig_calls += 1
         for j in range(mean.shape[1]):
             worst["mean"] = max(worst["mean"], scaled_close(mean[:, j], ref.model_i_call.mean[:, j].numpy(), np.sqrt(os_[j]), RTOL))
             worst["variance"] = max(worst["variance"], scaled_close(var[:, j], ref.model_i_call.variance[:, j].numpy(), os_[j], RTOL))
+            if int(lvl_r.max()) == 4:
+                continue  # draw compared above
             S = ref.model_i_call.covariance_matrix[:, j]
             dy, marginal = _root_sensitivity(S, lvl_r[:, j], jitter, eps[:, j].reshape(S.shape[0], -1), os_[j])
             same = lvl_g[:, j] == lvl_r[:, j]
@@ -498,7 +518,9 @@ def test_one_step_parity_under_identical_history(case):
         ref.update_hallucinated_Dyn_dataset(g_ref, y_ref)
         gpu.update_hallucinated_Dyn_dataset(g_ref.cuda(), y_ref.cuda())
     REPORT[f"one_step/{case}"] = dict(worst, jitter_flips=flips, marginal_flips=marginal_flips, elements=total,
-                                      status=gpu.engine.status())
+                                      eigen_root_calls=eig_calls, status=gpu.engine.status())
+    if case in EIGEN_ROOT:
+        assert eig_calls == n_calls(z)  # at the yaml's jitter every car SQP draw is an eigen-root draw
     _dump_report()
     for q, v in worst.items():
         assert v <= 1.0, f"{case}: {q} off by {v:.3g} x allowed"

@@ -154,3 +154,27 @@ def test_sequential_conditioning_with_noise_equals_refit():
     mean, cov = P.dense_posterior(Xc, Yc, probe, ls, os_, noise)
     assert P.rel_err(refit.mean[0, 0].reshape(-1).numpy(), mean.numpy(), np.sqrt(os_)) < 1e-9
     assert P.rel_err(refit.covariance_matrix[0, 0].numpy(), cov.numpy(), os_) < 1e-9
+
+
+def test_draw_falls_back_to_the_eigen_root_for_the_whole_batch_when_a_cholesky_fails():
+    """root_decomposition: NotPSDError after the ladder => symeig for every batch element (linear_operator);
+    root root^T = the covariance with its negative eigenvalues clamped."""
+    d = 2
+    X, Y, xs, ls, os_, noise = P.random_problem(81, n=9, d=d, H=4)
+    gp = _oracle_gp(X, Y, ls, os_, noise, jitter=1e-20, batch=(2, 1))
+    x = xs.expand(2, 1, *xs.shape).clone()
+    x[1, 0, 2] = x[1, 0, 0]  # sample 1 evaluates one point twice: exactly singular joint covariance
+    x[1, 0, 3] = x[1, 0, 0]
+    post = gp(x)
+    g = torch.Generator().manual_seed(2)
+    eps = torch.randn(2, 1, 4, d + 1, generator=g, dtype=F64)
+    y = post.sample(base_samples=eps)
+    assert (post.jitter_level == 4).all()  # both elements, although only sample 1 is singular
+    lam, V = torch.linalg.eigh(post.covariance_matrix)
+    root = V * lam.clamp_min(0).sqrt().unsqueeze(-2)
+    want = post.mean.reshape(2, 1, -1) + (root @ eps.reshape(2, 1, -1, 1)).squeeze(-1)
+    assert torch.equal(y.reshape(2, 1, -1), want)
+    # with a working ladder (default jitter) the Cholesky draw is kept and only the singular element escalates
+    post2 = _oracle_gp(X, Y, ls, os_, noise, jitter=1e-8, batch=(2, 1))(x)
+    post2.sample(base_samples=eps)
+    assert int(post2.jitter_level[0, 0]) == 0 and 1 <= int(post2.jitter_level[1, 0]) <= 3
