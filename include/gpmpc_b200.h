@@ -87,6 +87,16 @@ typedef struct {
   double x_equi[GPMPC_MAX_NX];
 } gpmpc_env;
 
+/* ---- base samples (host only) -------------------------------------------------------------------- */
+
+/* The truncated standard-normal base samples of Agent.random_vector_within_bounds (src/agent.py:76-104), drawn from
+ * torch's CPU generator stream-identically and without the Python loop: `slots` candidates of `n` float64 scalars each
+ * (slots = n_mpc * n_sqp * ns, n = g_ny * H * T), every candidate one emulated torch.normal(0, 1, size=(1, g_ny, H, T))
+ * call, redrawn until all |w| <= beta.  rng_state: HOST, the bytes of torch.get_rng_state() (CPUGeneratorImplState,
+ * state_bytes must be 5056); advanced in place -- write it back with torch.set_rng_state().  out: HOST [slots * n].
+ * Returns the number of candidates drawn (>= slots), < 0 on a bad argument.  No CUDA involved. */
+int64_t gpmpc_base_samples(uint8_t* rng_state, int64_t state_bytes, int64_t slots, int64_t n, double beta, double* out);
+
 /* ---- lifetime ---------------------------------------------------------------------------------- */
 
 /* Allocates the persistent per-sample state on the current CUDA device.

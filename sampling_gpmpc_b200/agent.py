@@ -168,22 +168,14 @@ class Agent:
     def Hallcinated_Y_train(self):
         return self._hallucinated()[1]
 
-    # ---- a2: agent.py:76-104, same generator stream (one torch.normal per candidate) --------------
+    # ---- a2 / f2: agent.py:76-104, the same generator stream without the Python loop (base_samples.py) ------------
     def random_vector_within_bounds(self) -> torch.Tensor:
-        H = self.params["optimizer"]["H"]
-        n_dyn, beta = self.ns_global, self.params["agent"]["Dyn_gp_beta"]
-        n_mpc = self.params["common"]["num_MPC_itrs"]
-        n_itrs = self.params["optimizer"]["SEMPC"]["max_sqp_iter"]
-        dev = self.torch_device if self.params["common"]["use_cuda"] else torch.device("cpu")
-        out = torch.empty(n_mpc, n_itrs, n_dyn, self.g_ny, H, self.in_dim_y, dtype=F64, device=dev)
-        for j in range(n_mpc):
-            for i in range(n_itrs):
-                k = 0
-                while k < n_dyn:
-                    w = torch.normal(0, 1, size=(1, self.g_ny, H, self.in_dim_y), dtype=F64, device=dev)
-                    if torch.all(w >= -beta) and torch.all(w <= beta):
-                        out[j, i, k] = w[0]
-                        k += 1
+        from .base_samples import truncated_normal_base_samples
+        p = self.params
+        dev = self.torch_device if p["common"]["use_cuda"] else torch.device("cpu")  # the generator the reference uses
+        out = truncated_normal_base_samples(p["common"]["num_MPC_itrs"], p["optimizer"]["SEMPC"]["max_sqp_iter"],
+                                            self.ns_global, self.g_ny, p["optimizer"]["H"], self.in_dim_y,
+                                            p["agent"]["Dyn_gp_beta"], dev)
         return out.to(self.torch_device)
 
     def mpc_iteration(self, i):

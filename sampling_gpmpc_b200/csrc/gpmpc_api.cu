@@ -17,6 +17,7 @@
 #include "gpmpc_step.cuh"
 #include "gpmpc_block_mma.cuh"
 #include "gpmpc_eig.cuh"
+#include "gpmpc_rng.cuh"
 
 // static shared memory of k_sample_eig (rotation tables + coefficients), rounded up
 #define EIG_STATIC_SMEM (44 * 1024)
@@ -282,7 +283,13 @@ static int dispatch_posterior_mma(gpmpc_handle* h, const DevState& st, const dou
 
 extern "C" {
 
-const char* gpmpc_version(void) { return "gpmpc_b200 0.1 (sm_100a)"; }
+const char* gpmpc_version(void) { return "gpmpc_b200 0.2 (sm_100a)"; }
+
+int64_t gpmpc_base_samples(uint8_t* rng_state, int64_t state_bytes, int64_t slots, int64_t n, double beta, double* out) {
+  if (!rng_state || !out || state_bytes != (int64_t)gpmpc_rng::STATE_BYTES || slots < 0 || n < 1 || !(beta > 0.0))
+    return GPMPC_ERR_ARG;
+  return gpmpc_rng::truncated_candidates(rng_state, slots, n, beta, out);
+}
 
 const char* gpmpc_last_error(const gpmpc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 

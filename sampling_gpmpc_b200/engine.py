@@ -78,6 +78,7 @@ ABI = {
     "gpmpc_set_block_kernels": (C.c_int, [_P, _I]),
     "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
+    "gpmpc_base_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
 }
 
 _lib = None

@@ -524,3 +524,21 @@ def test_one_step_parity_under_identical_history(case):
     _dump_report()
     for q, v in worst.items():
         assert v <= 1.0, f"{case}: {q} off by {v:.3g} x allowed"
+
+
+def test_product_agent_generates_the_reference_base_samples():
+    """Agent.random_vector_within_bounds of the PRODUCT (no epistimic_random_vector passed in): the stream-identical
+    generation of sampling_gpmpc_b200/base_samples.py reproduces what the unmodified reference Agent drew from
+    experiment.rnd_seed (the fixture's eps), and the replay on them is the golden one."""
+    from sampling_gpmpc_b200.agent import Agent
+    from sampling_gpmpc_b200.envs import make_env_spec
+    z, params = load_case("pendulum1D_sqp")
+    torch.manual_seed(params["experiment"]["rnd_seed"]["value"])
+    agent = Agent(params, spec=make_env_spec(params), X_real=torch.tensor(z["X_real"]), Y_real=torch.tensor(z["Y_real"]))
+    eps = agent.epistimic_random_vector.cpu().numpy()
+    assert eps.shape[1:] == z["eps"].shape[1:]
+    assert np.array_equal(eps[: z["eps"].shape[0]], z["eps"])
+    outs = replay(agent, z, params)
+    os_ = outputscales(params)
+    for k, (gp_val, y_grad, u_grad) in enumerate(outs):
+        assert scaled_close(gp_val, z[f"gp_val_{k}"], float(np.sqrt(os_.max())) * 4.0, RTOL) <= 1.0
