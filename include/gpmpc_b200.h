@@ -87,6 +87,15 @@ typedef struct {
   double x_equi[GPMPC_MAX_NX];
 } gpmpc_env;
 
+/* ---- tuning switches ------------------------------------------------------------------------------- */
+
+/* name = "rollout_fused"  (0 default: one gpmpc_step per horizon step; 1: gpmpc_rollout runs the whole horizon in ONE launch,
+ *                          csrc/gpmpc_horizon.cuh, where the shape allows -- measured slower at the bench shape, kept as an option),
+ *        "hz_groups"      (cap on the samples one CTA of the fused kernel holds at a time; 0 = as many as fit),
+ *        "hz_stagger_ns"  (spread of the sample groups' start times in the fused kernel; -1 = automatic, 0 = none).
+ * The results do not depend on any of them (bit-identical trajectories). */
+int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value);
+
 /* ---- base samples (host only) -------------------------------------------------------------------- */
 
 /* The truncated standard-normal base samples of Agent.random_vector_within_bounds (src/agent.py:76-104), drawn from

@@ -16,6 +16,7 @@
 #include "gpmpc_post.cuh"
 #include "gpmpc_step.cuh"
 #include "gpmpc_block_mma.cuh"
+#include "gpmpc_horizon.cuh"
 #include "gpmpc_eig.cuh"
 #include "gpmpc_rng.cuh"
 
@@ -66,6 +67,18 @@ struct gpmpc_handle {
   void* c_scratch = nullptr;
   size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
+  // fused-horizon rollout (k_horizon, one launch per rollout): a measured prototype that LOSES to the step-wise path at the
+  // bench shape (254.7 ms vs 220.4 ms per rollout on the same box, profiles/r2_horizon_probe.txt), so it is
+  // opt-in: GPMPC_ROLLOUT_FUSED=1 / gpmpc_set_option("rollout_fused", 1).  GPMPC_HZ_GROUPS caps the sample groups per CTA
+  // (L2 footprint = #SMs x groups x g_ny factors), GPMPC_HZ_STAGGER_NS spreads the groups' starts over the horizon
+  bool fused_rollout = false;
+  int hz_groups_cap = 0;
+  long long hz_stagger_ns = -1;      // < 0: automatic (one sample-horizon of the previous fused rollout)
+  double hz_last_ms = 0.0;           // device time of the previous fused launch (for the automatic stagger)
+  int hz_last_samples_per_group = 0;
+  cudaEvent_t hz_ev[2] = {nullptr, nullptr};
+  bool last_rollout_fused = false;
+  std::vector<cudaEvent_t> slice_ev;
   int eig_epoch = 0;  // draw launches so far (gpmpc_eig.cuh: a failing element publishes the epoch of its launch)
   // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) whenever inv(L_oo) does not fit in
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
@@ -310,6 +323,9 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   if (const char* e = getenv("GPMPC_WO_MIN_M")) h->wo_min_m = atoi(e);
   if (const char* e = getenv("GPMPC_BLOCK_SCALAR")) h->block_mma = atoi(e) == 0;
   if (const char* e = getenv("GPMPC_WO_MAX_NB")) h->wo_max_nb = std::min(3, std::max(1, atoi(e)));
+  if (const char* e = getenv("GPMPC_ROLLOUT_FUSED")) h->fused_rollout = atoi(e) != 0;
+  if (const char* e = getenv("GPMPC_HZ_GROUPS")) h->hz_groups_cap = atoi(e);
+  if (const char* e = getenv("GPMPC_HZ_STAGGER_NS")) h->hz_stagger_ns = atoll(e);
   DevState& st = h->st;
   st.ns = dims->ns; st.g_ny = dims->g_ny; st.d = dims->d; st.T = dims->T; st.n_real = dims->n_real;
   st.B = dims->ns * dims->g_ny;
@@ -347,6 +363,8 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->hz_ev) if (e) cudaEventDestroy(e);
   delete h;
   return GPMPC_OK;
 }
@@ -858,6 +876,74 @@ int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, cons
   return GPMPC_OK;
 }
 
+}  // extern "C"
+
+// ---- fused-horizon rollout (gpmpc_horizon.cuh) ---------------------------------------------------------------------------
+// sample groups per CTA that fit (0: the step-wise path serves this shape)
+static int horizon_groups(const gpmpc_handle* h, int n_steps) {
+  const DevState& st = h->st;
+  if (!h->fused_rollout || !h->condition || h->has_partial || st.T != st.d + 1 || st.c != 0 || st.np != 0) return 0;
+  int groups = std::min(HZ_MAX_WARPS / st.g_ny, 15);
+  if (h->hz_groups_cap > 0) groups = std::min(groups, h->hz_groups_cap);
+  for (; groups >= 1; --groups) {
+    const HzLayout L = hz_layout(st.g_ny, st.n_real, st.m, st.mo, st.d, st.T, n_steps, groups);
+    if ((size_t)L.total * 8 + 256 <= (size_t)h->max_dyn_smem) break;
+  }
+  return std::max(groups, 0);
+}
+
+template <int D, int T>
+static int launch_horizon_impl(gpmpc_handle* h, const gpmpc_env& env, const HorizonArgs& a, cudaStream_t stream) {
+  auto kern = k_horizon<D, T>;
+  CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem, true));
+  const DevState& st = h->st;
+  const HzLayout L = hz_layout(st.g_ny, st.n_real, st.m, st.mo, D, T, a.n_steps, a.groups);
+  const int n = a.s_end - a.s_begin;
+  const int grid = std::max(1, std::min(h->num_sms, (n + a.groups - 1) / a.groups));
+  kern<<<grid, a.groups * st.g_ny * 32, (size_t)L.total * 8, stream>>>(st, env, a);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GPMPC_OK;
+}
+
+static int launch_horizon(gpmpc_handle* h, const gpmpc_env& env, const HorizonArgs& a, cudaStream_t stream) {
+#define HZ_CASE(D_) case D_: return launch_horizon_impl<D_, D_ + 1>(h, env, a, stream);
+  switch (h->st.d) { HZ_CASE(1) HZ_CASE(2) HZ_CASE(3) HZ_CASE(4) HZ_CASE(5) HZ_CASE(6) }
+#undef HZ_CASE
+  return fail(h, GPMPC_ERR_ARG, "unsupported d");
+}
+
+// bookkeeping after the fused launches: every element now holds n_steps fully observed points
+static int horizon_commit(gpmpc_handle* h, int n_steps, cudaStream_t stream) {
+  DevState& hst = h->st;
+  k_fill_row_tables<<<(n_steps * hst.T + 127) / 128, 128, 0, stream>>>(hst, n_steps);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  double bytes = 0.0, flops = 0.0;
+  for (int t = 0; t < n_steps; ++t) {
+    hst.c = hst.T * t;
+    count_work(h, 1, true);
+    bytes += h->last_bytes;
+    flops += h->last_flops;
+  }
+  h->last_bytes = bytes;
+  h->last_flops = flops;
+  hst.np = n_steps;
+  hst.c = hst.T * n_steps;
+  h->factor_version++;
+  h->last_rollout_fused = true;
+  return GPMPC_OK;
+}
+
+static unsigned long long horizon_stagger(const gpmpc_handle* h, int samples_per_group) {
+  if (h->hz_stagger_ns >= 0) return (unsigned long long)h->hz_stagger_ns;
+  // automatic: the duration of one sample's horizon in the previous fused launch (0 on the very first launch)
+  if (h->hz_last_ms <= 0.0 || h->hz_last_samples_per_group <= 0 || samples_per_group < 8) return 0ull;
+  return (unsigned long long)(h->hz_last_ms * 1e6 / h->hz_last_samples_per_group);
+}
+
+extern "C" {
+
 int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
                   const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,
                   void* stream_) {
@@ -889,6 +975,36 @@ int gpmpc_rollout_gated(gpmpc_handle* h, const gpmpc_env* env, const double* x0,
   } else if (!h->condition && hst.np + n_steps > hst.cap_points) {
     rc = alloc_factor_state(h, hst.np + n_steps, stream);
     if (rc) return rc;
+  }
+  h->last_rollout_fused = false;
+  const int hz_groups = horizon_groups(h, n_steps);
+  if (hz_groups > 0) {
+    // ONE launch for the whole horizon (gpmpc_horizon.cuh); base samples still on their way from the host are awaited first
+    if (eps_ready)
+      for (int t = 0; t < n_steps; ++t)
+        if (eps_ready[t]) CUDA_TRY(h, cudaStreamWaitEvent(stream, (cudaEvent_t)eps_ready[t], 0));
+    if (!h->hz_ev[0]) {
+      CUDA_TRY(h, cudaEventCreate(&h->hz_ev[0]));
+      CUDA_TRY(h, cudaEventCreate(&h->hz_ev[1]));
+    } else if (h->hz_last_samples_per_group < 0) {
+      // the previous fused launch was timed: its duration feeds the automatic stagger (the events are long complete when
+      // a caller has read the trajectories; otherwise this waits for that launch)
+      float ms = 0.f;
+      if (cudaEventSynchronize(h->hz_ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, h->hz_ev[0], h->hz_ev[1]) == cudaSuccess)
+        h->hz_last_ms = ms;
+      h->hz_last_samples_per_group = -h->hz_last_samples_per_group;
+    }
+    HorizonArgs a{x0, u_ff, eps, traj, n_steps, 0, ns, hz_groups, 0ull, *opts};
+    const int grid = std::max(1, std::min(h->num_sms, (ns + hz_groups - 1) / hz_groups));
+    const int per_group = (ns + grid * hz_groups - 1) / (grid * hz_groups);
+    a.stagger_ns = horizon_stagger(h, per_group);
+    CUDA_TRY(h, cudaEventRecord(h->hz_ev[0], stream));
+    rc = launch_horizon(h, *env, a, stream);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->hz_ev[1], stream));
+    h->hz_last_samples_per_group = -per_group;  // negative: duration not read yet
+    h->ev_used = 0;
+    return horizon_commit(h, n_steps, stream);
   }
   const int threads = 128, blocks = (ns + threads - 1) / threads;
   const size_t eps_stride = (size_t)hst.B * hst.T;
@@ -1180,6 +1296,16 @@ int gpmpc_set_block_kernels(gpmpc_handle* h, int32_t mma) {
   return GPMPC_OK;
 }
 
+int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(h, GPMPC_ERR_ARG, "null argument");
+  const std::string n(name);
+  if (n == "rollout_fused") h->fused_rollout = value != 0;
+  else if (n == "hz_groups") h->hz_groups_cap = (int)value;
+  else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
+  else return fail(h, GPMPC_ERR_ARG, "unknown option " + n);
+  return GPMPC_OK;
+}
+
 int gpmpc_set_timing(gpmpc_handle* h, int32_t on) {
   if (!h) return GPMPC_ERR_ARG;
   h->timing = on != 0;
@@ -1191,6 +1317,16 @@ int gpmpc_rollout_kernel_ms(gpmpc_handle* h, double* total_ms, int32_t* launches
   if (!h || !total_ms || !launches) return fail(h, GPMPC_ERR_ARG, "null argument");
   *total_ms = 0.0;
   *launches = h->ev_used / 2;
+  if (h->last_rollout_fused && h->hz_ev[1]) {  // the fused-horizon rollout is one launch
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventSynchronize(h->hz_ev[1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->hz_ev[0], h->hz_ev[1]));
+    *total_ms = ms;
+    *launches = 1;
+    h->hz_last_ms = ms;
+    if (h->hz_last_samples_per_group < 0) h->hz_last_samples_per_group = -h->hz_last_samples_per_group;
+    return GPMPC_OK;
+  }
   if (h->ev_used == 0) return GPMPC_OK;
   CUDA_TRY(h, cudaEventSynchronize(h->ev[h->ev_used - 1]));
   for (int i = 0; i < h->ev_used; i += 2) {

@@ -5,7 +5,8 @@
 
 // transform_sensitivity (identity: pendulum1D.py:240-241; residual car: car_model_residual.py:211-224)
 // followed by the scatter into pad_g (src/agent.py:545-550).  Returns entry p of the padded row.
-__device__ __forceinline__ double transformed_entry(const gpmpc_env& env, const double* __restrict__ yg, int T,
+template <typename ENV>
+__device__ __forceinline__ double transformed_entry(const ENV& env, const double* __restrict__ yg, int T,
                                                     double v, int p) {
   if (env.transform == 1) {
     // [v g, v dg/dphi, g, v dg/ddelta]; with T == 1 torch broadcasting copies g into every slot
@@ -46,6 +47,44 @@ __global__ void k_assemble(gpmpc_env env, int ns, int H, int T, const double* __
   }
 }
 
+// Row i of the next state of one sample from z = [x, u] of this step and the g_ny sampled value rows y_of(j)[T]:
+// x+_i = F_known[i] z + sum_j B_d[i][j] pad(transform(y_j))[0]   (k_rollout_state evaluates every row in one thread, the
+// fused-horizon kernel one row per lane: same expression order, bit-identical trajectories)
+template <typename ENV, typename YOF>
+__device__ __forceinline__ double rollout_next_state_row(const ENV& env, int T, const double* z, YOF y_of, int i) {
+  const int nz = env.nx + env.nu;
+  const double v = nz > 3 ? z[3] : 0.0;
+  double f = 0.0;
+  for (int k = 0; k < nz; ++k) f += env.F_known[i * nz + k] * z[k];
+  for (int j = 0; j < env.g_ny; ++j) {
+    const double bij = env.B_d[i * env.g_ny + j];
+    if (bij != 0.0) {
+      const double* yg = y_of(j);
+      for (int p = 0; p < env.n_pad; ++p)
+        if (env.pad_g[p] == 0) f += bij * transformed_entry(env, yg, T, v, p);
+    }
+  }
+  return f;
+}
+template <typename ENV, typename YOF>
+__device__ __forceinline__ void rollout_next_state(const ENV& env, int T, const double* z, YOF y_of, double* xc) {
+  for (int i = 0; i < env.nx; ++i) xc[i] = rollout_next_state_row(env, T, z, y_of, i);
+}
+
+// input k of z = [x, u_t (+ feedback)]  (simulate_forward_sampling_car.py:122: u = u_ff - K (x_equi - x))
+template <typename ENV>
+__device__ __forceinline__ double rollout_input_row(const ENV& env, const double* xc, const double* u_t, int k) {
+  double u = u_t[k];
+  if (env.use_feedback)
+    for (int i = 0; i < env.nx; ++i) u -= env.K_fb[k * env.nx + i] * (env.x_equi[i] - xc[i]);
+  return u;
+}
+template <typename ENV>
+__device__ __forceinline__ void rollout_inputs(const ENV& env, const double* xc, const double* u_t, double* z) {
+  for (int i = 0; i < env.nx; ++i) z[i] = xc[i];
+  for (int k = 0; k < env.nu; ++k) z[env.nx + k] = rollout_input_row(env, xc, u_t, k);
+}
+
 // Rollout bookkeeping, one thread per sample.  phase 0: x_cur = x0.  phase 1: x_cur = F xu + B_d pad(y)[0].
 // Then (if t < n_steps) builds xu_t = [x_cur, u_t (+feedback)], records traj[:, :, t] and gathers the GP input.
 __global__ void k_rollout_state(gpmpc_env env, int ns, int T, int t, int n_steps, int phase,
@@ -60,30 +99,15 @@ __global__ void k_rollout_state(gpmpc_env env, int ns, int T, int t, int n_steps
   if (phase == 0) {
     for (int i = 0; i < nx; ++i) xc[i] = x0[(size_t)s * nx + i];
   } else {
-    const double v = nz > 3 ? z[3] : 0.0;
-    for (int i = 0; i < nx; ++i) {
-      double f = 0.0;
-      for (int k = 0; k < nz; ++k) f += env.F_known[i * nz + k] * z[k];
-      for (int j = 0; j < env.g_ny; ++j) {
-        const double bij = env.B_d[i * env.g_ny + j];
-        if (bij != 0.0) {
-          const double* yg = y_gp + ((size_t)s * env.g_ny + j) * T;
-          for (int p = 0; p < env.n_pad; ++p)
-            if (env.pad_g[p] == 0) f += bij * transformed_entry(env, yg, T, v, p);
-        }
-      }
-      xc[i] = f;
-    }
+    double zl[2 * GPMPC_MAX_NX];
+    for (int k = 0; k < nz; ++k) zl[k] = z[k];
+    rollout_next_state(env, T, zl, [&](int j) { return y_gp + ((size_t)s * env.g_ny + j) * T; }, xc);
   }
   for (int i = 0; i < nx; ++i) traj[((size_t)s * nx + i) * (n_steps + 1) + t] = xc[i];
   if (t >= n_steps) return;
-  for (int i = 0; i < nx; ++i) z[i] = xc[i];
-  for (int k = 0; k < nu; ++k) {
-    double u = u_ff[(size_t)t * nu + k];
-    if (env.use_feedback)
-      for (int i = 0; i < nx; ++i) u -= env.K_fb[k * nx + i] * (env.x_equi[i] - xc[i]);
-    z[nx + k] = u;
-  }
+  double zn[2 * GPMPC_MAX_NX];
+  rollout_inputs(env, xc, u_ff + (size_t)t * nu, zn);
+  for (int k = 0; k < nz; ++k) z[k] = zn[k];
   for (int j = 0; j < env.g_ny; ++j)
-    for (int a = 0; a < env.d; ++a) xstar[((size_t)s * env.g_ny + j) * env.d + a] = z[env.g_idx_inputs[a]];
+    for (int a = 0; a < env.d; ++a) xstar[((size_t)s * env.g_ny + j) * env.d + a] = zn[env.g_idx_inputs[a]];
 }

@@ -40,6 +40,12 @@
 #define STEP_NST 2   // ring slots per warp: one being consumed, the other in flight
 #endif
 #define STEP_SLOT_BYTES (STEP_SEG * 64)
+#ifndef GPMPC_PRED_LOADS
+// B-fragment loads of the hot loops under a predicate (1) or inside a divergent branch (0).  Measured on one B200 box
+// (profiles/r2_horizon_probe.txt): the branch wins -- step-wise rollout 220.4 ms vs 229.8 ms, fused horizon 254.7 vs 276.2 --
+// although it costs a BSSY / BSYNC pair per iteration: the predicated form keeps the dead lanes' loads in the LSU queue
+#define GPMPC_PRED_LOADS 0
+#endif
 
 // ---- TMA bulk copy + mbarrier (one ring per warp; the warp is its own producer and consumer) ----------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,7 +115,7 @@ __device__ __forceinline__ void kernel_row(const double* __restrict__ xa, int ta
     const double t = r * il[a];
     sq = fma(t, t, sq);
     g[a] = t * il[a];  // r_a / l_a^2
-    if (a == ta - 1) { ga = g[a]; il2 = il[a] * il[a]; }
+    if (a == ta - 1) { ga = g[a]; il2 = __dmul_rn(il[a], il[a]); }
   }
   const double k0 = os * exp(-0.5 * sq);
   if (ta == 0) {
@@ -121,8 +127,8 @@ __device__ __forceinline__ void kernel_row(const double* __restrict__ xa, int ta
 #pragma unroll
     for (int tb = 1; tb < T; ++tb) {
       double h = -ga * g[tb - 1];
-      if (tb == ta) h += il2;
-      out[tb] = k0 * h;
+      if (tb == ta) h = __dadd_rn(h, il2);  // explicit: the product 1/l^2 is never fused into this sum (the same entry must
+      out[tb] = k0 * h;                     // come out bit-identical from every kernel that evaluates it)
     }
   }
 }
@@ -151,7 +157,7 @@ __device__ __forceinline__ void kernel_block(const double (&xa)[D], const double
 #pragma unroll
       for (int tb = 1; tb < T; ++tb) {
         double h = -g[ta - 1] * g[tb - 1];
-        if (ta == tb) h += il[ta - 1] * il[ta - 1];
+        if (ta == tb) h = __dadd_rn(h, __dmul_rn(il[ta - 1], il[ta - 1]));  // explicit roundings, see kernel_row
         out[ta][tb] = k0 * h;
       }
   }
@@ -163,6 +169,33 @@ __device__ __forceinline__ double lds(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
   return v;
+}
+// four loads at addr + {0, S, 2S, 3S} under ONE predicate (lanes with live == 0 issue no shared-memory access and keep their
+// register values): predication instead of a divergent branch -- an `if (live)` around the loads costs a BSSY / BSYNC pair and
+// a branch per iteration of the hot loops
+template <int S>
+__device__ __forceinline__ void lds4_if(uint32_t live, uint32_t addr, double& b0, double& b1, double& b2, double& b3) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %4, 0;\n\t"
+      "@p ld.shared.f64 %0, [%5];\n\t"
+      "@p ld.shared.f64 %1, [%5+%6];\n\t"
+      "@p ld.shared.f64 %2, [%5+%7];\n\t"
+      "@p ld.shared.f64 %3, [%5+%8];\n\t}"
+      : "+d"(b0), "+d"(b1), "+d"(b2), "+d"(b3)
+      : "r"(live), "r"(addr), "n"(S), "n"(2 * S), "n"(3 * S)
+      : "memory");
+}
+template <int S>
+__device__ __forceinline__ void lds2_if(uint32_t live, uint32_t addr, double& b0, double& b1) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %2, 0;\n\t"
+      "@p ld.shared.f64 %0, [%3];\n\t"
+      "@p ld.shared.f64 %1, [%3+%4];\n\t}"
+      : "+d"(b0), "+d"(b1)
+      : "r"(live), "r"(addr), "n"(S)
+      : "memory");
 }
 __device__ __forceinline__ void sts(uint32_t addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
@@ -187,12 +220,16 @@ __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint
   // B fragments: only T < 8 of the 8 columns are live; the dead ones belong to the lanes with gid >= T -- for T <= 4 the
   // whole upper half-warp -- which issue no shared-memory access at all (their wavefront disappears; stale register
   // values only ever reach accumulator columns nobody reads)
-  const bool live = T >= 8 || ((threadIdx.x & 31) >> 2) < T;
+  const uint32_t live = (T >= 8 || ((threadIdx.x & 31) >> 2) < T) ? 1u : 0u;
   double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
   int it = 0;
   for (; it + 4 <= n4; it += 4) {
     const double a0 = lds<0>(la), a1 = lds<256>(la), a2 = lds<512>(la), a3 = lds<768>(la);
+#if GPMPC_PRED_LOADS
+    lds4_if<WSTEP>(live, wa, b0, b1, b2, b3);
+#else
     if (live) { b0 = lds<0>(wa); b1 = lds<WSTEP>(wa); b2 = lds<2 * WSTEP>(wa); b3 = lds<3 * WSTEP>(wa); }
+#endif
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
     dmma(c[0], c[1], a2, b2);
@@ -202,7 +239,11 @@ __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint
   }
   if (it < n4) {
     const double a0 = lds<0>(la), a1 = lds<256>(la);
+#if GPMPC_PRED_LOADS
+    lds2_if<WSTEP>(live, wa, b0, b1);
+#else
     if (live) { b0 = lds<0>(wa); b1 = lds<WSTEP>(wa); }
+#endif
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
   }
@@ -817,7 +858,7 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
       double kss = 0.0;
       if (r == s) {
         if (r == 0) kss = os;
-        else { const double il = 1.0 / st.ls[j_out * d + r - 1]; kss = os * (il * il); }
+        else { const double il = 1.0 / st.ls[j_out * d + r - 1]; kss = __dmul_rn(os, __dmul_rn(il, il)); }  // never fused into the subtraction below
       }
       S.at(r, s) = kss - fi[T + r * (r + 1) / 2 + s];
     }

@@ -78,6 +78,7 @@ ABI = {
     "gpmpc_set_block_kernels": (C.c_int, [_P, _I]),
     "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
+    "gpmpc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "gpmpc_base_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
 }
 
@@ -469,6 +470,11 @@ class GPEngine:
     def set_block_kernels(self, mma: bool):
         """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
         self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
+
+    def set_option(self, name: str, value: int):
+        """Tuning switches of the C ABI (gpmpc_set_option): rollout_fused, hz_groups, hz_stagger_ns.  Results do not depend
+        on them."""
+        self._check(self.lib.gpmpc_set_option(self.h, name.encode(), int(value)), "gpmpc_set_option")
 
     def set_timing(self, on: bool):
         self._check(self.lib.gpmpc_set_timing(self.h, int(on)), "gpmpc_set_timing")
