@@ -176,7 +176,7 @@ def extras(torch, device, cpu_leg=True):
     # derivative observations: m = 180, g_ny = 2, d = 3, T = 4, 30 steps; 20 samples x 10^4 repeats = 2e5 samples)
     try:
         ns2, st2 = 200_000, 30
-        fr = ForwardRollout(configs.pendulum2D_rollout(ns2, st2), condition=True, device=device)
+        fr = ForwardRollout(configs.pendulum2D_rollout(ns2, st2), condition=True, device=device, agent_size=20)
         g2 = torch.Generator().manual_seed(5)
         eps2 = torch.randn(st2, ns2, 2, 1, 4, generator=g2, dtype=torch.float64).clamp_(-2.5, 2.5).to(device)
         u2 = (2.0 * torch.sin(torch.linspace(0, 3, st2, dtype=torch.float64))).reshape(st2, 1).to(device)

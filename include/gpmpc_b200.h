@@ -87,6 +87,22 @@ typedef struct {
   double x_equi[GPMPC_MAX_NX];
 } gpmpc_env;
 
+/* ---- several reference Agents in one handle ------------------------------------------------------------- */
+
+/* benchmarking/simulate_true_reachable_set.py:167-259 builds a NEW Agent of num_dyn_samples samples for each of its 10^4
+ * repeats; the B200 path rolls all repeats out as one batch.  With Dyn_gp_min_data_dist >= 0 the Agent's
+ * update_hallucinated_Dyn_dataset (src/agent.py:164-202) couples the samples of ONE Agent: a new point whose label was NaN'd
+ * (closer than min_dist to the element's own data set) for ANY element of the Agent is masked out of the Agent's model by
+ * observation_nan_policy("mask"), and it is not stored at all if it was filtered for ALL samples of some output.
+ * group_size > 0 declares consecutive blocks of group_size samples to be one Agent each: every gpmpc_step / gpmpc_rollout
+ * step then runs that filter and those two reductions PER GROUP (no host round trip) and a masked / dropped point enters the
+ * group's factors as null rows.  group_size = 0 switches it off.  Call on an empty hallucinated set.  While it is on the
+ * block entry points (gpmpc_posterior with hallucinated points, gpmpc_append) refuse the handle. */
+int gpmpc_set_grouping(gpmpc_handle* h, int32_t group_size, double min_dist);
+/* DEVICE out[B * num_hallucinated] uint8: 0 = point in the element's factor, 1 = recorded but masked, 2 = dropped (not part of
+ * the Agent's data set: skip it when reading gpmpc_export_hallucinated).  All 0 without grouping. */
+int gpmpc_export_point_states(const gpmpc_handle* h, uint8_t* out, void* stream);
+
 /* ---- tuning switches ------------------------------------------------------------------------------- */
 
 /* name = "rollout_fused"  (0 default: one gpmpc_step per horizon step; 1: gpmpc_rollout runs the whole horizon in ONE launch,

@@ -48,3 +48,48 @@ def reference_rollout(params: dict, spec, u_ff: torch.Tensor, eps: torch.Tensor,
         x_h = gp_val[:, :, 0, 0].reshape(1, -1)
     X_traj[:, :, steps] = gp_val[:, :, 0, 0]
     return X_traj
+
+
+def reference_true_reachable_set(params: dict, spec, u_ff: torch.Tensor, eps: torch.Tensor, group_size: int,
+                                 X_real=None, Y_real=None, return_datasets: bool = False):
+    """benchmarking/simulate_true_reachable_set.py:152-259 for ns_total / group_size repeats: every repeat is a NEW Agent of
+    ``group_size`` samples (:172); per horizon step a full re-fit on [real || hallucinated] (:182), the posterior at the
+    current state / input of every sample (:208), a joint draw (:209; here with the given base samples eps
+    (steps, ns_total, g_ny, 1, T) instead of the script's internal torch.randn), the zero-variance rule (:213-228), the
+    truncation (:230-236), ``update_hallucinated_Dyn_dataset`` WITH its min-distance filter (:239 -> agent.py:164-202),
+    next state := sampled values (:251-258).  -> X_traj (ns_total, nx, steps+1)."""
+    import copy
+    ag = params["agent"]
+    ns_total, steps = eps.shape[1], u_ff.shape[0]
+    nx, nu, g_ny = ag["dim"]["nx"], ag["dim"]["nu"], ag["g_dim"]["ny"]
+    assert g_ny == nx, "the script feeds the sampled values back as the next state"
+    if X_real is None:
+        X_real, Y_real = spec.initial_training_data(params)
+    beta, var0 = ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"]
+    X_traj = np.empty((ns_total, nx, steps + 1))
+    datasets = []
+    for g0 in range(0, ns_total, group_size):
+        gs = min(group_size, ns_total - g0)
+        p = copy.deepcopy(params)
+        p["agent"]["num_dyn_samples"] = gs
+        agent = RefAgent(p, spec, X_real, Y_real)
+        x = torch.tensor(params["env"]["start"], dtype=F64).expand(gs, nx).clone()
+        for i in range(steps):
+            agent.train_hallucinated_dynGP(i)
+            X_inp = torch.zeros(gs, g_ny, 1, nx + nu, dtype=F64)
+            X_inp[:, :, 0, :nx] = x[:, None, :]
+            X_inp[:, :, 0, nx:] = u_ff[i]
+            post = agent.model_i(X_inp)
+            Y = post.sample(base_samples=eps[i, g0:g0 + gs])
+            zero = (post.variance <= var0).all(dim=-1, keepdim=True).tile(1, 1, 1, nx + nu + 1)
+            num = torch.zeros_like(post.variance)
+            num[zero] = 1
+            Y = num * post.mean + (1 - num) * Y
+            Y = torch.max(Y, post.mean - beta * torch.sqrt(post.variance))
+            Y = torch.min(Y, post.mean + beta * torch.sqrt(post.variance))
+            agent.update_hallucinated_Dyn_dataset(X_inp, Y)
+            X_traj[g0:g0 + gs, :, i] = x.numpy()
+            x = Y[:, :, 0, 0].clone()
+        X_traj[g0:g0 + gs, :, steps] = x.numpy()
+        datasets.append((agent.Hallcinated_X_train.clone(), agent.Hallcinated_Y_train.clone()))
+    return (X_traj, datasets) if return_datasets else X_traj

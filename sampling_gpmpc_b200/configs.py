@@ -61,9 +61,10 @@ def pendulum1D_sqp(num_dyn_samples: int = 70, n_mpc: int = 55) -> dict:
     }
 
 
-def pendulum2D_rollout(num_dyn_samples: int = 20, steps: int = 30) -> dict:
-    """2-D pendulum true-reachable-set rollout (benchmarking/simulate_true_reachable_set.py): real data WITH
-    derivatives (m = 45*4 = 180 observed scalars), T=4, one point per step, zero-variance switch on."""
+def pendulum2D_rollout(num_dyn_samples: int = 20, steps: int = 30, min_data_dist: float = 1.0e-4) -> dict:
+    """2-D pendulum true-reachable-set rollout (benchmarking/simulate_true_reachable_set.py on params_pendulum.yaml): real
+    data WITH derivatives (m = 45*4 = 180 observed scalars), T=4, one point per step, the zero-variance switch
+    (params_pendulum.yaml:45) and the min-distance filter of update_hallucinated_Dyn_dataset (:46, 1e-4) on."""
     return {
         "env": {"start": [0.0, 0.0], "goal_state": [2.5, 0.0], "dynamics": "pendulum", "prior_dyn_meas": True,
                 "train_data_has_derivatives": True, "use_model_without_derivatives": False, "n_data_x": 3,
@@ -74,7 +75,7 @@ def pendulum2D_rollout(num_dyn_samples: int = 20, steps: int = 30) -> dict:
                   "Dyn_gp_task_noises": {"val": [3.8, 1.27, 3.8, 1.27], "multiplier": 1.0e-5}, "Dyn_gp_beta": 2.5,
                   "mean_shift_val": 2, "num_dyn_samples": num_dyn_samples, "mean_as_dyn_sample": False,
                   "true_dyn_as_sample": False, "Dyn_gp_jitter": 1.0e-6, "Dyn_gp_variance_is_zero": 1.1e-6,
-                  "Dyn_gp_min_data_dist": -1, "feedback": {"use": False}},
+                  "Dyn_gp_min_data_dist": min_data_dist, "feedback": {"use": False}},
         "common": {"use_cuda": True, "num_MPC_itrs": steps, "dynamics_rejection": False},
         "optimizer": {"H": 1, "u_min": [-8], "u_max": [8], "x_min": [-2.14, -2.5], "x_max": [2.14, 2.5],
                       "SEMPC": {"max_sqp_iter": 1}, "dt": 0.015, "terminal_tightening": {"K": [[0.0, 0.0]]}},

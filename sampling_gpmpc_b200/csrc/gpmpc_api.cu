@@ -79,6 +79,11 @@ struct gpmpc_handle {
   cudaEvent_t hz_ev[2] = {nullptr, nullptr};
   bool last_rollout_fused = false;
   std::vector<cudaEvent_t> slice_ev;
+  // grouped rollout (gpmpc_set_grouping): consecutive blocks of grp_size samples are one reference Agent each; the min-distance
+  // filter of update_hallucinated_Dyn_dataset (src/agent.py:164-202) reduces its flags per group
+  int grp_size = 0;
+  double grp_min_dist = -1.0;
+  unsigned char *grp_flags = nullptr, *grp_decision = nullptr;
   int eig_epoch = 0;  // draw launches so far (gpmpc_eig.cuh: a failing element publishes the epoch of its launch)
   // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) whenever inv(L_oo) does not fit in
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
@@ -135,8 +140,9 @@ static cudaError_t dev_alloc(Tp** p, size_t count) {
 static void free_factor_state(gpmpc_handle* h) {
   DevState& st = h->st;
   cudaFree(st.Xh); cudaFree(st.Yh); cudaFree(st.hobs_pt); cudaFree(st.hobs_task); cudaFree(st.hrow0);
-  cudaFree(st.Lh); cudaFree(st.beta_h);
+  cudaFree(st.Lh); cudaFree(st.beta_h); cudaFree(st.pstate);
   st.Xh = st.Yh = st.Lh = st.beta_h = nullptr;
+  st.pstate = nullptr;
   st.hobs_pt = st.hobs_task = st.hrow0 = nullptr;
 }
 
@@ -160,6 +166,14 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
   CUDA_TRY(h, dev_alloc(&hp, (size_t)c_cap));
   CUDA_TRY(h, dev_alloc(&ht, (size_t)c_cap));
   CUDA_TRY(h, dev_alloc(&hr, (size_t)cap_points));
+  unsigned char* ps = nullptr;
+  if (h->grp_size > 0) {
+    CUDA_TRY(h, dev_alloc(&ps, B * (size_t)std::max(cap_points, 1)));
+    CUDA_TRY(h, cudaMemsetAsync(ps, 0, B * (size_t)std::max(cap_points, 1), stream));
+    if (old.pstate && old.np > 0)
+      CUDA_TRY(h, cudaMemcpy2DAsync(ps, (size_t)cap_points, old.pstate, (size_t)old.cap_points, (size_t)old.np, B,
+                                    cudaMemcpyDeviceToDevice, stream));
+  }
   // padding columns [m, mo) must read as 0; rows not yet appended are never used but kept finite
   CUDA_TRY(h, cudaMemsetAsync(Lh, 0, lh_count * sizeof(double), stream));
   CUDA_TRY(h, cudaMemsetAsync(beta_h, 0, std::max<size_t>(1, B * c_cap) * sizeof(double), stream));
@@ -184,6 +198,7 @@ static int alloc_factor_state(gpmpc_handle* h, int cap_points, cudaStream_t stre
     free_factor_state(h);
   }
   st.Xh = Xh; st.Yh = Yh; st.Lh = Lh; st.beta_h = beta_h; st.hobs_pt = hp; st.hobs_task = ht; st.hrow0 = hr;
+  st.pstate = ps;
   st.cap_points = cap_points; st.c_cap = c_cap; st.elem_stride = stride;
   h->dims.cap_points = cap_points;
   return GPMPC_OK;
@@ -362,6 +377,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.eig_flag);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
+  cudaFree(h->grp_flags); cudaFree(h->grp_decision);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->hz_ev) if (e) cudaEventDestroy(e);
@@ -498,6 +514,10 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
 
 int gpmpc_reset_hallucinated(gpmpc_handle* h) {
   if (!h) return GPMPC_ERR_ARG;
+  if (h->st.pstate && h->st.np > 0) {
+    ON_HANDLE_DEVICE(h);
+    cudaMemset(h->st.pstate, 0, (size_t)h->st.B * std::max(h->st.cap_points, 1));
+  }
   h->st.c = 0;
   h->st.np = 0;
   h->has_partial = false;
@@ -540,6 +560,8 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   if (rc) return rc;
   if (!x || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / H");
   if (eps && (!opts || !y)) return fail(h, GPMPC_ERR_ARG, "eps given without opts / y");
+  if (h->grp_size > 0 && h->st.np > 0)
+    return fail(h, GPMPC_ERR_STATE, "grouped handle (gpmpc_set_grouping): only gpmpc_step / gpmpc_rollout see the per-Agent point masks");
   rc = ensure_workspace(h, H);
   if (rc) return rc;
   if (eps) h->st.eig_epoch = ++h->eig_epoch;
@@ -598,6 +620,7 @@ int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const
   int rc = check_ready(h);
   if (rc) return rc;
   if (!x || !y || H < 1) return fail(h, GPMPC_ERR_ARG, "bad x / y / H");
+  if (h->grp_size > 0) return fail(h, GPMPC_ERR_STATE, "grouped handle (gpmpc_set_grouping): append through gpmpc_step / gpmpc_rollout");
   cudaStream_t stream = (cudaStream_t)stream_;
   DevState& hst = h->st;
   const int T = hst.T;
@@ -666,11 +689,28 @@ template <int T>
 static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double* x, const double* eps,
                               const gpmpc_sample_opts& o, double* mean, double* var, double* y, int* jl, int grow,
                               cudaStream_t stream) {
-  k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, 0);
+  const int fin_blocks = (st.B + FIN_THREADS - 1) / FIN_THREADS;
+  if (h->grp_size > 0 && eps && grow) {
+    // grouped step: draw, per-element "too close" flags, per-Agent all / any reduction, then the append (null rows for a
+    // masked / dropped point)
+    k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_DRAW);
+    const int warps = 4;
+    k_filter_new_points<<<(st.B + warps - 1) / warps, warps * 32, 0, stream>>>(st, x, 1, h->grp_min_dist, 1, nullptr, nullptr,
+                                                                              h->grp_flags);
+    const int n_groups = (st.ns + h->grp_size - 1) / h->grp_size;
+    k_group_decide<<<(n_groups + warps - 1) / warps, warps * 32, 0, stream>>>(st.ns, st.g_ny, h->grp_size, h->grp_flags,
+                                                                              h->grp_decision);
+    k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, nullptr, nullptr, y, nullptr, grow, FIN_APPEND,
+                                                             GroupArgs{h->grp_flags, h->grp_decision, h->grp_size * st.g_ny});
+    h->launches += 4;
+    CUDA_TRY(h, cudaGetLastError());
+    return GPMPC_OK;
+  }
+  k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_ALL);
   h->launches++;
   if (eps && T > 1 && !(o.flags & GPMPC_OPT_NO_EIG_FALLBACK)) {
     // GPyTorch's batch-wide eigen-root fallback: exits on the device unless an element of this step failed its ladder
-    k_step_finish<T><<<(st.B + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, 1);
+    k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_EIG_REDO);
     h->launches++;
   }
   CUDA_TRY(h, cudaGetLastError());
@@ -841,6 +881,8 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
     rc = dispatch_step(h, h->st, x, eps, o, mean, var, y, jitter_level, grow, stream, &handled);
     if (rc) return rc;
   }
+  if (!handled && h->grp_size > 0)
+    return fail(h, GPMPC_ERR_CAPACITY, "grouped step: the factor does not fit the fused step kernel");
   if (!handled) {
     // factor too tall for the register-resident sweep: same recursion through the general block kernels
     const double w_bytes = h->last_bytes, w_flops = h->last_flops;
@@ -882,7 +924,8 @@ int gpmpc_assemble(gpmpc_handle* h, const gpmpc_env* env, const double* xu, cons
 // sample groups per CTA that fit (0: the step-wise path serves this shape)
 static int horizon_groups(const gpmpc_handle* h, int n_steps) {
   const DevState& st = h->st;
-  if (!h->fused_rollout || !h->condition || h->has_partial || st.T != st.d + 1 || st.c != 0 || st.np != 0) return 0;
+  if (!h->fused_rollout || !h->condition || h->has_partial || h->grp_size > 0 || st.T != st.d + 1 || st.c != 0 || st.np != 0)
+    return 0;
   int groups = std::min(HZ_MAX_WARPS / st.g_ny, 15);
   if (h->hz_groups_cap > 0) groups = std::min(groups, h->hz_groups_cap);
   for (; groups >= 1; --groups) {
@@ -1264,6 +1307,21 @@ int gpmpc_export_hallucinated(const gpmpc_handle* h_, double* X, double* Y, void
   return GPMPC_OK;
 }
 
+int gpmpc_export_point_states(const gpmpc_handle* h_, uint8_t* out, void* stream) {
+  gpmpc_handle* h = const_cast<gpmpc_handle*>(h_);
+  if (!h || !out) return fail(h, GPMPC_ERR_ARG, "null argument");
+  ON_HANDLE_DEVICE(h);
+  const DevState& st = h->st;
+  if (st.np == 0) return GPMPC_OK;
+  if (!st.pstate) {
+    CUDA_TRY(h, cudaMemsetAsync(out, 0, (size_t)st.B * st.np, (cudaStream_t)stream));
+    return GPMPC_OK;
+  }
+  CUDA_TRY(h, cudaMemcpy2DAsync(out, (size_t)st.np, st.pstate, (size_t)st.cap_points, (size_t)st.np, st.B,
+                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return GPMPC_OK;
+}
+
 int gpmpc_status(gpmpc_handle* h, uint32_t* status, int32_t clear, void* stream) {
   ON_HANDLE_DEVICE(h);
   if (!h || !status) return fail(h, GPMPC_ERR_ARG, "null argument");
@@ -1293,6 +1351,27 @@ int64_t gpmpc_launch_count(const gpmpc_handle* h) { return h ? h->launches : -1;
 int gpmpc_set_block_kernels(gpmpc_handle* h, int32_t mma) {
   if (!h) return fail(h, GPMPC_ERR_ARG, "null handle");
   h->block_mma = mma != 0;
+  return GPMPC_OK;
+}
+
+int gpmpc_set_grouping(gpmpc_handle* h, int32_t group_size, double min_dist) {
+  if (!h || group_size < 0) return fail(h, GPMPC_ERR_ARG, "bad group size");
+  ON_HANDLE_DEVICE(h);
+  DevState& st = h->st;
+  if (st.np != 0) return fail(h, GPMPC_ERR_STATE, "set the grouping on an empty hallucinated set (gpmpc_reset_hallucinated first)");
+  if (group_size > 0 && st.T == 1 && !h->condition) return fail(h, GPMPC_ERR_ARG, "grouping needs conditioning");
+  cudaFree(h->grp_flags); cudaFree(h->grp_decision); cudaFree(st.pstate);
+  h->grp_flags = h->grp_decision = nullptr;
+  st.pstate = nullptr;
+  h->grp_size = group_size;
+  h->grp_min_dist = min_dist;
+  if (group_size == 0) return GPMPC_OK;
+  CUDA_TRY(h, dev_alloc(&h->grp_flags, (size_t)st.B));
+  CUDA_TRY(h, dev_alloc(&h->grp_decision, (size_t)(st.ns + group_size - 1) / group_size));
+  if (st.Lh || st.Xh) {  // the per-element state exists already: add the point states
+    CUDA_TRY(h, dev_alloc(&st.pstate, (size_t)st.B * std::max(st.cap_points, 1)));
+    CUDA_TRY(h, cudaMemset(st.pstate, 0, (size_t)st.B * std::max(st.cap_points, 1)));
+  }
   return GPMPC_OK;
 }
 

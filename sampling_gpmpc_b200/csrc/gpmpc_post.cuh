@@ -71,7 +71,8 @@ __global__ void k_min_dist_overwrite(DevState st, const double* __restrict__ x, 
 // number of this handle's samples for which point h of output j was filtered (the host turns it into the
 // reference's all-over-samples / any-over-batch flags, after an all-reduce when the samples are sharded).
 __global__ void k_filter_new_points(DevState st, const double* __restrict__ x, int H, double min_dist,
-                                    int use_hallucinated, double* __restrict__ y, int* __restrict__ counts) {
+                                    int use_hallucinated, double* __restrict__ y, int* __restrict__ counts,
+                                    unsigned char* __restrict__ flags = nullptr) {
   const int lane = threadIdx.x & 31;
   const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pair >= (long long)st.B * H) return;
@@ -80,14 +81,44 @@ __global__ void k_filter_new_points(DevState st, const double* __restrict__ x, i
   const int n = st.n_real + (use_hallucinated ? st.np : 0);
   bool hit = false;
   for (int i = lane; i < n && !hit; i += 32) {
+    if (i >= st.n_real && st.pstate && st.pstate[(size_t)b * st.cap_points + (i - st.n_real)] == 2) continue;  // dropped: never stored
     const double* xt = i < st.n_real ? st.Xr + (size_t)i * d
                                      : st.Xh + ((size_t)b * st.cap_points + (i - st.n_real)) * d;
     hit = point_dist(xs, xt, d) <= min_dist;
   }
   hit = __any_sync(0xffffffffu, hit);
+  if (flags && lane == 0) flags[pair] = hit ? 1 : 0;
   if (!hit) return;
-  if (lane < T) y[pair * T + lane] = nan("");
-  if (lane == 0) atomicAdd(counts + (size_t)j * H + h, 1);
+  if (y && lane < T) y[pair * T + lane] = nan("");
+  if (counts && lane == 0) atomicAdd(counts + (size_t)j * H + h, 1);
+}
+
+// Group-wise reduction of the flags of ONE new point per element (H = 1), groups = consecutive blocks of group_size samples
+// = one reference Agent each (simulate_true_reachable_set.py: a new Agent of num_dyn_samples samples per repeat):
+//   dropped  (2) iff for some output the point is filtered for ALL samples of the group      (src/agent.py:186-191)
+//   masked   (1) iff filtered for ANY batch element of the group (GPyTorch's any-over-batch NaN mask)
+//   appended (0) otherwise.                                              One warp per group.
+__global__ void k_group_decide(int ns, int g_ny, int group_size, const unsigned char* __restrict__ flags,
+                               unsigned char* __restrict__ decision) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_groups = (ns + group_size - 1) / group_size;
+  if (g >= n_groups) return;
+  const int s0 = g * group_size, s1 = min(ns, s0 + group_size);
+  bool any = false, drop = false;
+  for (int j = 0; j < g_ny; ++j) {
+    bool all_j = true, any_j = false;
+    for (int s = s0 + lane; s < s1; s += 32) {
+      const bool f = flags[(size_t)s * g_ny + j] != 0;
+      all_j = all_j && f;
+      any_j = any_j || f;
+    }
+    all_j = __all_sync(0xffffffffu, all_j);
+    any_j = __any_sync(0xffffffffu, any_j);
+    drop = drop || all_j;
+    any = any || any_j;
+  }
+  if (lane == 0) decision[g] = drop ? 2 : (any ? 1 : 0);
 }
 
 // The acados stage parameter p_lin (src/solver.py:98-131; consumed by src/utils/model.py:34-41), all stages at

@@ -67,6 +67,9 @@ struct DevState {
   int* hrow0;           // [cap_points] first factor row of hallucinated point p (its T tasks are consecutive), -1 if not in the factor
   double* Lh;           // [B][elem_stride] own rows L[m+k][0 .. m+k] in sub-panel layout (off = mo)
   double* beta_h;       // [B][c_cap]
+  unsigned char* pstate; // [B][cap_points] grouped rollouts only (else NULL): 0 = point in the factor, 1 = recorded but MASKED
+                        //   (a label of its Agent was NaN: observation_nan_policy("mask") drops the slot for the whole batch),
+                        //   2 = DROPPED (filtered for all samples of an output, src/agent.py:186-191: never recorded)
   double* Wo;           // [B][mo][T]  shared rows inv(L_oo) k_o of the current step (k_shared_rows -> k_step<WO>), large m only
   double* fin;          // [B][T + T(T+1)/2]  W^T beta and lower(W^T W) of the last fused step (k_step -> k_step_finish)
   unsigned* status;     // device status word (GPMPC_ST_*)

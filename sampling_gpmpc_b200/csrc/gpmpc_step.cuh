@@ -430,7 +430,13 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
     // hallucinated points first: their global loads overlap with the real points' arithmetic
     for (int p0 = 0; p0 < np; p0 += 64) {
       const int pa = p0 + lane, pb = pa + 32;
-      const int ra = pa < np ? sHrow[pa] : -1, rb = pb < np ? sHrow[pb] : -1;
+      int ra = pa < np ? sHrow[pa] : -1, rb = pb < np ? sHrow[pb] : -1;
+      if (st.pstate) {
+        // grouped rollout: a masked / dropped point keeps its (null) factor rows but contributes no kernel entries
+        const unsigned char* ps = st.pstate + (size_t)b * st.cap_points;
+        if (ra >= 0 && ps[pa]) ra = -2 - ra;
+        if (rb >= 0 && ps[pb]) rb = -2 - rb;
+      }
       double xa[D], xb[D], ba[T], bb[T];
       if (ra >= 0) {
 #pragma unroll
@@ -462,6 +468,21 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
 #pragma unroll
           for (int tb = 0; tb < T; ++tb) wv[(mo + rb + ta) * T + tb] = kb[ta][tb];
           wb[mo + rb + ta] = bb[ta];
+        }
+      }
+      if (ra <= -2 || rb <= -2) {  // null rows: zero kernel entries, zero beta
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int rr = half ? rb : ra;
+          if (rr <= -2) {
+            const int r0 = -2 - rr;
+#pragma unroll
+            for (int ta = 0; ta < T; ++ta) {
+#pragma unroll
+              for (int tb = 0; tb < T; ++tb) wv[(mo + r0 + ta) * T + tb] = 0.0;
+              wb[mo + r0 + ta] = 0.0;
+            }
+          }
         }
       }
     }
@@ -832,14 +853,28 @@ k_step_shared(DevState st, const double* __restrict__ x) {
 #ifndef FIN_THREADS
 #define FIN_THREADS 128
 #endif
+// modes of k_step_finish: the plain fused step, GPyTorch's eigen-root redo, and the two halves of a GROUPED step (per-Agent
+// filter of update_hallucinated_Dyn_dataset, src/agent.py:164-202): draw only, then -- after the group-wise all / any
+// reduction of the "too close" flags -- the append, which writes NULL rows for a masked / dropped point
+#define FIN_ALL 0
+#define FIN_EIG_REDO 1
+#define FIN_DRAW 2
+#define FIN_APPEND 3
+struct GroupArgs {
+  const unsigned char* flag;  // [B]  1 = this element's new point is within min_dist of its data set (label becomes NaN)
+  const unsigned char* decision;  // [n_groups]  0 append, 1 mask, 2 drop
+  int group_elems;            // batch elements per group = group_size * g_ny
+};
+
 template <int T>
 __global__ void __launch_bounds__(FIN_THREADS)
 k_step_finish(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
               double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
-              int* __restrict__ jitter_level, int grow_factor, int eig_redo) {
+              int* __restrict__ jitter_level, int grow_factor, int mode, GroupArgs ga = GroupArgs{}) {
   constexpr int FS = T + T * (T + 1) / 2;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= st.B) return;
+  const int eig_redo = mode == FIN_EIG_REDO;
   // eig_redo: the launch queued behind the regular one; it repeats the draw and the append of EVERY element through the
   // eigen root iff some element's jitter ladder failed in this step (GPyTorch's batch-wide symeig fallback, gpmpc_eig.cuh).
   // Everything this kernel writes depends only on st.fin, eps and the old factor rows, so the repeat simply overwrites.
@@ -875,7 +910,10 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
   TriT<T> Lc;
   int level = 0;
   double yv[T];
-  if (eig_redo) {
+  if (mode == FIN_APPEND) {
+#pragma unroll
+    for (int r = 0; r < T; ++r) yv[r] = y[(size_t)b * T + r];  // as drawn by the FIN_DRAW launch
+  } else if (eig_redo) {
     double R[T * T];
     eig_root_T<T>(S.v, R);
     level = 4;
@@ -913,27 +951,55 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
       yv[r] = level < 4 ? acc : nan("");
     }
   }
-  bool zero = opts.variance_is_zero >= 0.0;
+  if (mode != FIN_APPEND) {
+    bool zero = opts.variance_is_zero >= 0.0;
 #pragma unroll
-  for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
+    for (int r = 0; r < T; ++r) zero = zero && (vr[r] <= opts.variance_is_zero);
 #pragma unroll
-  for (int r = 0; r < T; ++r) {
-    if (zero) yv[r] = macc[r];
-    if (opts.beta >= 0.0) {
-      const double sd = sqrt(vr[r]);
-      yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
+    for (int r = 0; r < T; ++r) {
+      if (zero) yv[r] = macc[r];
+      if (opts.beta >= 0.0) {
+        const double sd = sqrt(vr[r]);
+        yv[r] = fmin(fmax(yv[r], macc[r] - opts.beta * sd), macc[r] + opts.beta * sd);
+      }
+      y[(size_t)b * T + r] = yv[r];
     }
-    y[(size_t)b * T + r] = yv[r];
+    if (jitter_level) jitter_level[b] = level;
+    if (level == 4 && !eig_redo) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
+    if (mode == FIN_DRAW) return;
   }
-  if (jitter_level) jitter_level[b] = level;
-  if (level == 4 && !eig_redo) atomicOr(st.status, GPMPC_ST_SAMPLE_NOT_PD);
 
   // ---- F (second half): condition on (x*, y) --------------------------------------------------------
+  int decision = 0;
+  bool flagged = false;
+  if (mode == FIN_APPEND) {
+    decision = ga.decision[b / ga.group_elems];
+    flagged = ga.flag[b] != 0;
+    st.pstate[(size_t)b * st.cap_points + st.np] = (unsigned char)decision;
+  }
   for (int a = 0; a < d; ++a) st.Xh[((size_t)b * st.cap_points + st.np) * d + a] = x[(size_t)b * d + a];
 #pragma unroll
-  for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = yv[r];
+  for (int r = 0; r < T; ++r) st.Yh[((size_t)b * st.cap_points + st.np) * T + r] = flagged ? nan("") : yv[r];
   if (b == 0) st.hrow0[st.np] = grow_factor ? c : -1;
   if (!grow_factor) return;
+  if (decision != 0) {
+    // NULL rows: the point stays out of this Agent's model (masked: a label of the Agent is NaN; dropped: filtered for all
+    // samples).  Rows c .. c+T-1 = unit rows (zero off the diagonal, 1 / L_kk = 1, zero inverse entries, beta 0); phase A of
+    // later steps gives them zero kernel entries (st.pstate), so w is 0 there and nothing downstream sees the point.
+    double* Le0 = st.Lh + (size_t)b * st.elem_stride;
+    for (int r = 0; r < T; ++r) {
+      const int k = c + r, i = k & 7, kb = k - i;
+      double* sp = Le0 + subpanel_off(k >> 3, mo);
+      for (int t = 0; t < st.m; ++t) sp[sp_idx(t, i)] = 0.0;
+      for (int t = 0; t < k; ++t) sp[sp_idx(mo + t, i)] = 0.0;
+      sp[sp_idx(mo + k, i)] = 1.0;
+      for (int jc = 0; jc < i; ++jc) sp[sp_idx(mo + kb + i, jc)] = 0.0;  // transposed-inverse slots (row jc, column i)
+      st.beta_h[(size_t)b * st.c_cap + k] = 0.0;
+    }
+    if (b == 0)
+      for (int r = 0; r < T; ++r) { st.hobs_pt[c + r] = st.np; st.hobs_task[c + r] = r; }
+    return;
+  }
   TriT<T> Sn = S, Ln;
 #pragma unroll
   for (int r = 0; r < T; ++r) Sn.at(r, r) += st.noise[j_out * T + r];

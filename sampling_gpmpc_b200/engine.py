@@ -79,6 +79,8 @@ ABI = {
     "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
     "gpmpc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "gpmpc_set_grouping": (C.c_int, [_P, _I, C.c_double]),
+    "gpmpc_export_point_states": (C.c_int, [_P, _D, _P]),
     "gpmpc_base_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
 }
 
@@ -428,6 +430,13 @@ class GPEngine:
             self._check(self.lib.gpmpc_export_hallucinated(self.h, _ptr(X), _ptr(Y), _stream(self.device)), "gpmpc_export")
         return X, Y
 
+    def export_point_states(self) -> torch.Tensor:
+        """(ns, g_ny, num_hallucinated) uint8: 0 in the factor, 1 recorded but masked, 2 dropped (grouped rollouts)."""
+        out = torch.zeros((self.ns, self.g_ny, self.num_hallucinated), dtype=torch.uint8, device=self.device)
+        if self.num_hallucinated:
+            self._check(self.lib.gpmpc_export_point_states(self.h, _ptr(out), _stream(self.device)), "gpmpc_export_point_states")
+        return out
+
     def status(self, clear: bool = False) -> int:
         s = C.c_uint32(0)
         self._check(self.lib.gpmpc_status(self.h, C.byref(s), int(clear), _stream(self.device)), "gpmpc_status")
@@ -470,6 +479,12 @@ class GPEngine:
     def set_block_kernels(self, mma: bool):
         """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
         self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
+
+    def set_grouping(self, group_size: int, min_dist: float):
+        """Consecutive blocks of `group_size` samples are one reference Agent each: the min-distance filter of
+        update_hallucinated_Dyn_dataset (src/agent.py:164-202) and GPyTorch's any-over-batch NaN mask act per group inside
+        gpmpc_step / gpmpc_rollout.  0 switches it off."""
+        self._check(self.lib.gpmpc_set_grouping(self.h, int(group_size), float(min_dist)), "gpmpc_set_grouping")
 
     def set_option(self, name: str, value: int):
         """Tuning switches of the C ABI (gpmpc_set_option): rollout_fused, hz_groups, hz_stagger_ns.  Results do not depend

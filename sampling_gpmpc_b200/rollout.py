@@ -33,7 +33,12 @@ def shard_bounds(ns_global: int, rank: int, world_size: int):
 
 class ForwardRollout:
     def __init__(self, params: dict, condition: bool, rank: int = 0, world_size: int = 1,
-                 device: Optional[torch.device] = None, X_real=None, Y_real=None):
+                 device: Optional[torch.device] = None, X_real=None, Y_real=None, agent_size: Optional[int] = None):
+        """agent_size: benchmarking/simulate_true_reachable_set.py rolls out a NEW Agent of num_dyn_samples samples per
+        repeat; here all repeats are one batch of `num_dyn_samples` samples in total and `agent_size` says how many
+        consecutive samples form one reference Agent.  It matters iff Dyn_gp_min_data_dist >= 0: the min-distance filter of
+        update_hallucinated_Dyn_dataset and GPyTorch's any-over-batch NaN mask couple the samples of one Agent
+        (src/agent.py:164-202); default: the whole batch is one Agent (as in the reference's own single-Agent runs)."""
         self.params = params
         ag = params["agent"]
         self.spec = make_env_spec(params)
@@ -54,6 +59,12 @@ class ForwardRollout:
         self.engine.set_hypers(ls, os_, noise, ag["Dyn_gp_jitter"])
         self.engine.set_real_data(X_real, Y_real.contiguous())
         self.condition = condition
+        self.agent_size = None
+        if condition and ag["Dyn_gp_min_data_dist"] >= 0.0:
+            self.agent_size = int(agent_size) if agent_size else self.ns_global
+            if world_size > 1 and self.s_lo % self.agent_size:
+                raise ValueError("sharding must not cut a reference Agent in two: ceil(ns / world_size) % agent_size != 0")
+            self.engine.set_grouping(self.agent_size, ag["Dyn_gp_min_data_dist"])
         fb = ag.get("feedback", {}).get("use", False)
         K = np.asarray(params["optimizer"]["terminal_tightening"]["K"]) if fb else None
         self.env = make_env_struct(self.spec, K, params["env"]["goal_state"] if fb else None)

@@ -21,7 +21,7 @@ def _car(ns, steps, seed):
 
 def _pendulum(ns, steps, seed):
     from sampling_gpmpc_b200 import configs
-    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps)
+    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps, min_data_dist=-1)  # (the per-Agent filter is step-wise only)
     params["env"]["train_data_has_derivatives"] = False  # m = 45 value observations: inv(L_oo) of both outputs fits in shared memory
     g = torch.Generator().manual_seed(seed)
     eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64).clamp(-2.5, 2.5)

@@ -415,10 +415,10 @@ def test_large_batch_pendulum_rollout_is_batch_independent():
     g = torch.Generator(device="cuda").manual_seed(8)
     eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64, device="cuda").clamp_(-2.5, 2.5)
     u = (2.0 * torch.sin(torch.linspace(0, 3, steps, dtype=torch.float64))).reshape(steps, 1).cuda()
-    full = ForwardRollout(configs.pendulum2D_rollout(ns, steps), condition=True)
+    full = ForwardRollout(configs.pendulum2D_rollout(ns, steps), condition=True, agent_size=20)
     traj = full.run(u, eps)
     assert full.engine.status() == 0 and bool(torch.isfinite(traj).all())
-    small = ForwardRollout(configs.pendulum2D_rollout(500, steps), condition=True)
+    small = ForwardRollout(configs.pendulum2D_rollout(500, steps), condition=True, agent_size=20)
     for lo in (1, ns - 503):
         part = small.run(u, eps[:, lo:lo + 500].contiguous())
         assert torch.equal(part, traj[lo:lo + 500]), f"samples {lo}..{lo + 500} differ from their stand-alone rollout"
