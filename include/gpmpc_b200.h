@@ -87,6 +87,20 @@ typedef struct {
   double x_equi[GPMPC_MAX_NX];
 } gpmpc_env;
 
+/* ---- rejection rollout (Agent.prepare_dynamics_set, src/agent.py:331-443) ------------------------------------ */
+
+/* Forgets every hallucinated point from index n_points on (their factor rows are simply no longer used): the end of
+ * prepare_dynamics_set's forward-sampling data set (FS_*_train_batch, src/agent.py:344-345,399-405), which the reference
+ * drops by re-fitting on [real || hallucinated] (:438-441). */
+int gpmpc_truncate_hallucinated(gpmpc_handle* h, int32_t n_points);
+
+/* One step of the rejection rollout, all DEVICE: xu [ns][nx][1][nx+nu] current [x, u] (tiled over nx as get_batch_x_hat lays
+ * it out), y [B][1][T] the draw at it, x_target [ns][nx] = X_soln[i+1], c_i = ci_list[i];  x_next [ns][nx] = known_dyn(xu) +
+ * B_d g (src/agent.py:381-383), samples_left [ns] int32 *= prod_i(|x_target - x_next| - c_i < 0) (:384-389); with u_next
+ * [nu] also xu_next [ns][nx][1][nx+nu] = [x_next, u_next] (:407-415).  u_next = xu_next = NULL on the last step. */
+int gpmpc_fs_advance(gpmpc_handle* h, const gpmpc_env* env, const double* xu, const double* y, const double* x_target,
+                     double c_i, const double* u_next, int32_t* samples_left, double* x_next, double* xu_next, void* stream);
+
 /* ---- several reference Agents in one handle ------------------------------------------------------------- */
 
 /* benchmarking/simulate_true_reachable_set.py:167-259 builds a NEW Agent of num_dyn_samples samples for each of its 10^4

@@ -43,6 +43,27 @@ def gp_hypers_from_params(params: dict, g_ny: int, d: int, use_grad: bool):
     return ls, os_, noise
 
 
+def reachable_set_ball(params: dict, V_k: np.ndarray):
+    """The epsilon-ball constraint tightenings of src/utils/reachable_set.py:3-39 (host scalar math; prepare_dynamics_set
+    reads ci_list[i] as the acceptance radius of stage i).  Returns (tilde_eps_list, ci_list)."""
+    opt, tight = params["optimizer"], params["agent"]["tight"]
+    H = opt["H"]
+    P = np.array(opt["terminal_tightening"]["P"])
+    L = tight["Lipschitz"]
+    var_eps = tight["dyn_eps"] + tight["w_bound"]
+    B_d_norm = np.sum(np.sqrt(np.diag(P[:3][:3]))) * V_k
+    P_inv = np.linalg.inv(P)
+    K = np.array(opt["terminal_tightening"]["K"])
+    x_t, u_t = np.sqrt(np.diag(P_inv)), np.sqrt(np.diag(K @ P_inv @ K.T))
+    tilde_eps_list = [np.concatenate([(x_t * 0).tolist(), (u_t * 0).tolist(), [0]])]
+    ci_list = []
+    for stage in range(1, H + 1):
+        B_eps_k = var_eps * B_d_norm[stage - 1] * np.sum(np.power(L, np.arange(0, stage)))
+        tilde_eps_list.append(np.concatenate([(x_t * B_eps_k).tolist(), (u_t * B_eps_k).tolist(), [B_eps_k]]))
+        ci_list.append(B_eps_k)
+    return tilde_eps_list, ci_list
+
+
 class _ModelView:
     """What callers read off ``agent.model_i`` (src/visu.py:483-484, src/agent.py:642-643)."""
 
@@ -138,6 +159,9 @@ class Agent:
         self.model_i = None
         self.model_i_call = None
         self.mpc_iter = 0
+        self.tilde_eps_list = self.ci_list = None
+        if "P" in params["optimizer"].get("terminal_tightening", {}) and "Lipschitz" in ag.get("tight", {}):
+            self.tilde_eps_list, self.ci_list = reachable_set_ball(params, np.ones(params["optimizer"]["H"] + 1))  # agent.py:71-73
         if epistimic_random_vector is not None:
             self.epistimic_random_vector = epistimic_random_vector[:, :, self.s_lo:self.s_hi].to(self.torch_device, F64)
         elif generate_base_samples:
@@ -276,6 +300,77 @@ class Agent:
             self.engine.append(newX.contiguous(), newY.contiguous(), active)
         self._data_version += 1
         self._appended_since_train = True
+
+    # ---- a15: the rejection rollout (agent.py:283-443; common.dynamics_rejection) ---------------------------------
+    def train_forward_sampling_dynGP(self):
+        """Reference: a new GPyTorch model on [real || forward-sampling || hallucinated] data (agent.py:283-329).  Here the
+        factor already holds the hallucinated AND the forward-sampling points (prepare_dynamics_set appends them as it
+        goes; the order of training points does not change a posterior), so this is bookkeeping like
+        train_hallucinated_dynGP."""
+        self.model_i = _ModelView(self, self._data_version, with_hallucinated=True)
+        self._appended_since_train = False
+
+    def prepare_dynamics_set(self, X_soln, U_soln, X_kp1, base_samples=None):
+        """agent.py:331-443: roll every sampled dynamics forward from the MEASURED next state x(k+1) along the solver's input
+        sequence, conditioning each sample on its own draws (value task only: the derivative labels are NaN'd, :402), and
+        keep the samples whose trajectories stay within c_i of the solver's own prediction (:351-394); the hallucinated data
+        of a rejected sample is then replaced by that of a random surviving one (:418-436, numpy's global generator, two
+        independent choices for inputs and labels exactly like the reference) and the model is restored (:438-441).
+        X_soln (H+1, ns*nx), U_soln (H, nu), X_kp1 (nx, 1).  base_samples: optional list of (ns, g_ny, 1, T) draws, one per
+        rollout step, instead of the library-internal torch.randn of `.sample()` (tests).  Returns samples_left (ns,)."""
+        if self.world_size != 1:
+            raise NotImplementedError("prepare_dynamics_set resamples across the whole population: run it unsharded")
+        if self._pending_reset or self.in_dim_y == 1:
+            raise NotImplementedError("prepare_dynamics_set follows a completed SQP solve of the derivative model")
+        ag, opt = self.params["agent"], self.params["optimizer"]
+        ns, dev, eng = self.ns, self.torch_device, self.engine
+        var_eps = (ag["tight"]["dyn_eps"] + ag["tight"]["w_bound"]) * np.sqrt(opt["terminal_tightening"]["P"][1][1])
+        X_soln = torch.as_tensor(np.asarray(X_soln), dtype=F64).reshape(-1, ns, self.nx).to(dev)
+        X_kp1 = torch.as_tensor(np.asarray(X_kp1), dtype=F64).reshape(self.nx, -1).transpose(0, 1).to(dev)  # (1, nx)
+        U_soln = torch.as_tensor(np.asarray(U_soln), dtype=F64).to(dev)
+        n_stage = X_soln.shape[0]
+        diff = X_soln[1] - X_kp1
+        samples_left = torch.prod((torch.abs(diff) - var_eps < 0).to(torch.int32), dim=1).to(torch.int32).contiguous()
+        xu_hat = torch.cat([X_kp1, U_soln[[1]]], dim=-1).expand(ns, self.nx, 1, self.nx + self.nu).contiguous()
+        n_h0 = eng.num_hallucinated
+        value_only = np.zeros((1, self.in_dim_y), dtype=np.uint8)
+        value_only[0, 0] = 1
+        opts = eng.opts()  # the script-level draw: no truncation, no zero-variance rule (agent.py:375-377)
+        for i in range(1, n_stage - 1):
+            g_xu_hat = self.get_g_xu_hat(xu_hat)
+            eps = (base_samples[i - 1].to(dev, F64) if base_samples is not None else
+                   torch.randn(ns, self.g_ny, self.in_dim_y, 1, dtype=F64, device=dev).reshape(ns, self.g_ny, 1, self.in_dim_y))
+            mean, var, y, jl = eng.posterior(g_xu_hat, eps, opts)
+            self.model_i_call = _PosteriorView(mean, var, jl)
+            last = i == n_stage - 2
+            _, xu_next = eng.fs_advance(self.env_struct, xu_hat, y, X_soln[i + 1], float(self.ci_list[i]),
+                                        None if last else U_soln[i + 1], samples_left)
+            if last:
+                break
+            eng.append_masked(g_xu_hat, y, value_only)  # FS_*_train_batch: the point with its value label only
+            self._data_version += 1
+            self.train_forward_sampling_dynGP()
+            xu_hat = xu_next
+        eng.truncate_hallucinated(n_h0)  # the forward-sampling set is dropped again
+        self._data_version += 1
+        left = samples_left.cpu().numpy()
+        if left.sum() > 0 and (left == 0).any():
+            n_rep = int((left == 0).sum())
+            remaining = np.arange(ns)[left > 0]
+            Xh, Yh = eng.export_hallucinated()
+            dead = torch.as_tensor(np.nonzero(left == 0)[0], device=dev)
+            Xh[dead] = Xh[torch.as_tensor(np.random.choice(remaining, n_rep), device=dev)]
+            Yh[dead] = Yh[torch.as_tensor(np.random.choice(remaining, n_rep), device=dev)]
+            # the replaced samples' factors: rebuilt by conditioning on the new data set (the reference re-fits, :438-441)
+            eng.reset_hallucinated()
+            step = max(1, 512 // self.in_dim_y)
+            active = (~Yh.isnan().any(1).any(0)).cpu().numpy().astype(np.uint8)  # GPyTorch's any-over-batch slot mask
+            for p0 in range(0, Xh.shape[2], step):
+                eng.append_masked(Xh[:, :, p0:p0 + step].contiguous(), Yh[:, :, p0:p0 + step].contiguous(), active[p0:p0 + step])
+            self._data_version += 1
+        self.train_hallucinated_dynGP(sqp_iter=opt["SEMPC"]["max_sqp_iter"])
+        eng.raise_on_status()
+        return samples_left
 
     # ---- a10 -----------------------------------------------------------------------------------
     def get_batch_gp_sensitivities(self, xu_hat, sqp_iter):

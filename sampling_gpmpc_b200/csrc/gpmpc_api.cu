@@ -96,6 +96,8 @@ struct gpmpc_handle {
   // a hallucinated point with only SOME of its T scalars in the factor exists (gpmpc_append_masked; agent.py:402): the
   // kernels that find a point's rows through hrow0 (K1, K2m) are bypassed for the scalar kernels until the next reset
   bool has_partial = false;
+  int first_partial_point = -1;    // index of the first partially observed point (-1: none)
+  std::vector<int> c_before_point; // factor rows in use before hallucinated point p (for gpmpc_truncate_hallucinated)
   size_t wo_count = 0;
   // optional per-launch timing of the fused step kernel inside gpmpc_rollout (CUDA events on its stream)
   bool timing = false;
@@ -476,6 +478,8 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   st.mo = (m + 7) & ~7;
   st.c = 0; st.np = 0;
   h->has_partial = false;
+  h->first_partial_point = -1;
+  h->c_before_point.clear();
   if (m_changed || !st.Lh) {
     // the slab height depends on m: (re)allocate the per-element state from scratch
     free_factor_state(h);
@@ -521,6 +525,22 @@ int gpmpc_reset_hallucinated(gpmpc_handle* h) {
   h->st.c = 0;
   h->st.np = 0;
   h->has_partial = false;
+  h->first_partial_point = -1;
+  h->c_before_point.clear();
+  h->factor_version++;
+  return GPMPC_OK;
+}
+
+int gpmpc_truncate_hallucinated(gpmpc_handle* h, int32_t n_points) {
+  if (!h || n_points < 0 || n_points > h->st.np) return fail(h, GPMPC_ERR_ARG, "bad point count");
+  if (h->grp_size > 0) return fail(h, GPMPC_ERR_STATE, "grouped handle");
+  if (n_points == h->st.np) return GPMPC_OK;
+  if ((int)h->c_before_point.size() < h->st.np) return fail(h, GPMPC_ERR_STATE, "point bookkeeping incomplete");
+  // rows / records beyond the cut are simply not used any more (appending overwrites them)
+  h->st.c = h->condition ? h->c_before_point[n_points] : 0;
+  h->st.np = n_points;
+  h->c_before_point.resize(n_points);
+  if (h->first_partial_point >= n_points) { h->first_partial_point = -1; h->has_partial = false; }
   h->factor_version++;
   return GPMPC_OK;
 }
@@ -674,6 +694,16 @@ int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const
   CUDA_TRY(h, cudaGetLastError());
   if (d_act) CUDA_TRY(h, cudaStreamSynchronize(stream));  // caller may reuse point_active's host memory
   count_work(h, H, grow);
+  {
+    int cc = hst.c;
+    for (int i = 0; i < H; ++i) {
+      h->c_before_point.push_back(cc);
+      int mine = 0;
+      for (int t = 0; t < T; ++t) mine += (!scalar_active || scalar_active[(size_t)i * T + t]) ? 1 : 0;
+      if (grow) cc += mine;
+      if (grow && mine != 0 && mine != T && h->first_partial_point < 0) h->first_partial_point = hst.np + i;
+    }
+  }
   hst.np += H;
   if (grow) {
     hst.c += n_active;
@@ -894,6 +924,7 @@ int gpmpc_step(gpmpc_handle* h, const double* x, const double* eps, const gpmpc_
     return rc;
   }
   if (eps) {
+    h->c_before_point.push_back(hst.c);
     hst.np += 1;
     if (grow) {
       hst.c += hst.T;
@@ -971,6 +1002,8 @@ static int horizon_commit(gpmpc_handle* h, int n_steps, cudaStream_t stream) {
   }
   h->last_bytes = bytes;
   h->last_flops = flops;
+  h->c_before_point.clear();
+  for (int t = 0; t < n_steps; ++t) h->c_before_point.push_back(hst.T * t);
   hst.np = n_steps;
   hst.c = hst.T * n_steps;
   h->factor_version++;
@@ -1092,6 +1125,20 @@ static int ensure_scratch(gpmpc_handle* h, size_t bytes) {
   h->c_scratch_bytes = 0;
   CUDA_TRY(h, cudaMalloc(&h->c_scratch, bytes));
   h->c_scratch_bytes = bytes;
+  return GPMPC_OK;
+}
+
+int gpmpc_fs_advance(gpmpc_handle* h, const gpmpc_env* env, const double* xu, const double* y, const double* x_target,
+                     double c_i, const double* u_next, int32_t* samples_left, double* x_next, double* xu_next, void* stream) {
+  if (!h || !env || !xu || !y || !x_target || !samples_left || !x_next) return fail(h, GPMPC_ERR_ARG, "null argument");
+  ON_HANDLE_DEVICE(h);
+  if (env->g_ny != h->st.g_ny || env->nx > GPMPC_MAX_NX) return fail(h, GPMPC_ERR_ARG, "env does not match handle");
+  if ((u_next == nullptr) != (xu_next == nullptr)) return fail(h, GPMPC_ERR_ARG, "u_next and xu_next go together");
+  const int threads = 128;
+  k_fs_advance<<<(h->st.ns + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(*env, h->st.ns, h->st.T, xu, y, x_target,
+                                                                                       c_i, u_next, samples_left, x_next, xu_next);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
 }
 

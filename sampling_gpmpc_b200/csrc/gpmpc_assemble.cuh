@@ -111,3 +111,32 @@ __global__ void k_rollout_state(gpmpc_env env, int ns, int T, int t, int n_steps
   for (int j = 0; j < env.g_ny; ++j)
     for (int a = 0; a < env.d; ++a) xstar[((size_t)s * env.g_ny + j) * env.d + a] = zn[env.g_idx_inputs[a]];
 }
+
+// One step of the rejection rollout of Agent.prepare_dynamics_set (src/agent.py:365-415), one thread per sample:
+//   x_next   = known_dyn(xu) + B_d g_val                        (:381-383; g_val = the sampled VALUE task of every output)
+//   survive  = prod_i ( |x_target_i - x_next_i| - c_i < 0 )     (:384-389, the sample-survival test)
+//   samples_left *= survive
+//   xu_next  = [x_next, u_next] tiled over the nx rows          (:407-415), when u_next is given
+// xu [ns][nx][1][nx+nu] (row 0 of the nx tiled copies is read), y [ns][g_ny][1][T], x_target [ns][nx].
+__global__ void k_fs_advance(gpmpc_env env, int ns, int T, const double* __restrict__ xu, const double* __restrict__ y,
+                             const double* __restrict__ x_target, double c_i, const double* __restrict__ u_next,
+                             int* __restrict__ samples_left, double* __restrict__ x_next, double* __restrict__ xu_next) {
+  const int nx = env.nx, nu = env.nu, nz = nx + nu;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ns) return;
+  double z[2 * GPMPC_MAX_NX], xn[GPMPC_MAX_NX];
+  for (int k = 0; k < nz; ++k) z[k] = xu[(size_t)s * nx * nz + k];
+  rollout_next_state(env, T, z, [&](int j) { return y + ((size_t)s * env.g_ny + j) * T; }, xn);
+  int ok = 1;
+  for (int i = 0; i < nx; ++i) {
+    ok = ok && (fabs(x_target[(size_t)s * nx + i] - xn[i]) - c_i < 0.0);
+    x_next[(size_t)s * nx + i] = xn[i];
+  }
+  samples_left[s] *= ok;
+  if (!xu_next) return;
+  for (int r = 0; r < nx; ++r) {
+    double* o = xu_next + ((size_t)s * nx + r) * nz;
+    for (int i = 0; i < nx; ++i) o[i] = xn[i];
+    for (int k = 0; k < nu; ++k) o[nx + k] = u_next[k];
+  }
+}

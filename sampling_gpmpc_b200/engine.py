@@ -80,6 +80,8 @@ ABI = {
     "gpmpc_version": (C.c_char_p, []),
     "gpmpc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "gpmpc_set_grouping": (C.c_int, [_P, _I, C.c_double]),
+    "gpmpc_truncate_hallucinated": (C.c_int, [_P, _I]),
+    "gpmpc_fs_advance": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.c_double, _D, _D, _D, _D, _P]),
     "gpmpc_export_point_states": (C.c_int, [_P, _D, _P]),
     "gpmpc_base_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
 }
@@ -479,6 +481,29 @@ class GPEngine:
     def set_block_kernels(self, mma: bool):
         """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
         self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
+
+    def truncate_hallucinated(self, n_points: int):
+        """Forget the hallucinated points from index n_points on (prepare_dynamics_set's forward-sampling set)."""
+        self._check(self.lib.gpmpc_truncate_hallucinated(self.h, int(n_points)), "gpmpc_truncate_hallucinated")
+
+    def fs_advance(self, env: GpmpcEnv, xu: torch.Tensor, y: torch.Tensor, x_target: torch.Tensor, c_i: float,
+                   u_next: Optional[torch.Tensor], samples_left: torch.Tensor):
+        """One step of Agent.prepare_dynamics_set's rejection rollout (src/agent.py:381-415): -> x_next (ns,nx)
+        [, xu_next (ns,nx,1,nx+nu)]; samples_left (ns,) int32 is updated in place."""
+        ns, nx, _, nz = xu.shape
+        xu = xu.to(self.device, torch.float64).contiguous()
+        y = y.to(self.device, torch.float64).contiguous()
+        x_target = x_target.to(self.device, torch.float64).contiguous()
+        assert samples_left.dtype == torch.int32 and samples_left.is_cuda and samples_left.is_contiguous()
+        x_next = torch.empty((ns, nx), dtype=torch.float64, device=self.device)
+        xu_next = None
+        if u_next is not None:
+            u_next = u_next.to(self.device, torch.float64).contiguous()
+            xu_next = torch.empty((ns, nx, 1, nz), dtype=torch.float64, device=self.device)
+        rc = self.lib.gpmpc_fs_advance(self.h, C.byref(env), _ptr(xu), _ptr(y), _ptr(x_target), float(c_i), _ptr(u_next),
+                                       _ptr(samples_left), _ptr(x_next), _ptr(xu_next), _stream(self.device))
+        self._check(rc, "gpmpc_fs_advance")
+        return x_next, xu_next
 
     def set_grouping(self, group_size: int, min_dist: float):
         """Consecutive blocks of `group_size` samples are one reference Agent each: the min-distance filter of
