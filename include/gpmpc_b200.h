@@ -87,6 +87,19 @@ typedef struct {
   double x_equi[GPMPC_MAX_NX];
 } gpmpc_env;
 
+/* ---- one SQP GP linearisation in one call ----------------------------------------------------------------- */
+
+/* What src/solver.py:84-94 does per SQP iteration around the GP -- get_g_xu_hat, model_i(x), .sample(base_samples), sample_gp's
+ * post-processing, update_hallucinated_Dyn_dataset, the assembly of dyn_fg_jacobians and its device->host copy -- queued on
+ * `stream` by ONE call:  xu [ns][nx][H][nx+nu] (HOST, pinned, when xu_on_host, else DEVICE) = get_batch_x_hat's tensor;
+ * eps DEVICE [B][H][T];  reset_first: the deferred reset of src/agent.py:261-272 (the model of this call still holds the
+ * previous MPC step's points, the data set it appends to is empty);  mean, var, y DEVICE [B][H][T], jitter_level [B];
+ * out DEVICE [ns][nx][H][1+nx+nu] = [f, df/dx, df/du], also copied to out_host (HOST, pinned) when not NULL.
+ * Nothing synchronises: wait for `stream` before reading out_host, then gpmpc_status. */
+int gpmpc_linearise(gpmpc_handle* h, const gpmpc_env* env, const double* xu, int32_t xu_on_host, int32_t H, const double* eps,
+                    const gpmpc_sample_opts* opts, int32_t reset_first, double* mean, double* var, double* y,
+                    int32_t* jitter_level, double* out, double* out_host, void* stream);
+
 /* ---- rejection rollout (Agent.prepare_dynamics_set, src/agent.py:331-443) ------------------------------------ */
 
 /* Forgets every hallucinated point from index n_points on (their factor rows are simply no longer used): the end of

@@ -223,27 +223,37 @@ class Agent:
         if sqp_iter == 0:
             self._pending_reset = True
 
-    # ---- a13 -----------------------------------------------------------------------------------
+    # ---- a13: agent.py:480-527.  Built in PINNED HOST memory with numpy views (a few microseconds at the SQP sizes); the
+    #      one H2D copy happens inside the C call that consumes it (gpmpc_linearise) -- engine methods that are handed the
+    #      tensor directly move it themselves -------------------------------------------------------------------------
+    def _xu_buffer(self, H):
+        key = (self.ns, self.nx, H, self.nx + self.nu)
+        if getattr(self, "_xu_key", None) != key:
+            self._xu_host = torch.empty(key, dtype=F64, pin_memory=True)
+            self._xu_np = self._xu_host.numpy()
+            self._xu_key = key
+        return self._xu_host, self._xu_np
+
     def get_batch_x_hat(self, x_h, u_h):
         H = self.params["optimizer"]["H"]
-        x_h = torch.as_tensor(np.asarray(x_h), dtype=F64)
-        u_h = torch.as_tensor(np.asarray(u_h), dtype=F64)
-        xb = x_h.transpose(0, 1).reshape(self.ns_global, self.nx, H)[self.s_lo:self.s_hi].transpose(1, 2)
-        ub = torch.ones(self.ns, H, 1, dtype=F64) * u_h
-        ret = torch.cat([xb, ub], 2)
-        return torch.stack([ret] * self.nx, dim=1).to(self.torch_device)
+        host, out = self._xu_buffer(H)
+        x_h = np.asarray(x_h, dtype=np.float64).reshape(H, self.ns_global, self.nx)[:, self.s_lo:self.s_hi]
+        u_h = np.asarray(u_h, dtype=np.float64).reshape(H, -1)
+        out[:, :, :, :self.nx] = x_h.transpose(1, 0, 2)[:, None, :, :]
+        out[:, :, :, self.nx:] = u_h[None, None, :, :]
+        return host
 
     def get_batch_x_hat_u_diff(self, x_h, u_h):
         H = self.params["optimizer"]["H"]
-        x_h = torch.as_tensor(np.asarray(x_h), dtype=F64)
-        u_h = torch.as_tensor(np.asarray(u_h), dtype=F64)
-        xb = x_h.transpose(0, 1).reshape(self.ns_global, self.nx, H)[self.s_lo:self.s_hi].transpose(1, 2)
-        ub = u_h.transpose(0, 1).reshape(self.ns_global, H, self.nu)[self.s_lo:self.s_hi]
-        ret = torch.cat([xb, ub], 2)
-        return torch.stack([ret] * self.nx, dim=1).to(self.torch_device)
+        host, out = self._xu_buffer(H)
+        x_h = np.asarray(x_h, dtype=np.float64).reshape(H, self.ns_global, self.nx)[:, self.s_lo:self.s_hi]
+        u_h = np.asarray(u_h, dtype=np.float64).reshape(H, self.ns_global, self.nu)[:, self.s_lo:self.s_hi]
+        out[:, :, :, :self.nx] = x_h.transpose(1, 0, 2)[:, None, :, :]
+        out[:, :, :, self.nx:] = u_h.transpose(1, 0, 2)[:, None, :, :]
+        return host
 
     def get_g_xu_hat(self, xu_hat):
-        return xu_hat[:, 0:self.g_ny, :, list(self.spec.g_idx_inputs)].contiguous()
+        return xu_hat.to(self.torch_device)[:, 0:self.g_ny, :, list(self.spec.g_idx_inputs)].contiguous()
 
     # ---- a9 ------------------------------------------------------------------------------------
     def sample_gp(self, x_input, base_samples=None):
@@ -411,7 +421,32 @@ class Agent:
         y_gp = self.get_batch_gp_sensitivities(xu_hat, sqp_iter)
         return self.engine.assemble(self.env_struct, xu_hat, y_gp)
 
+    def _fused_linearisation_applies(self, xu_hat) -> bool:
+        ag = self.params["agent"]
+        return (self.in_dim_y > 1 and not ag["true_dyn_as_sample"] and not ag["mean_as_dyn_sample"]
+                and ag["Dyn_gp_min_data_dist"] < 0.0 and not self._appended_since_train
+                and self.epistimic_random_vector is not None and torch.is_tensor(xu_hat)
+                and (xu_hat.is_cuda or xu_hat.is_pinned()) and xu_hat.is_contiguous())
+
     def dyn_fg_jacobians(self, xu_hat, sqp_iter):
+        if self._fused_linearisation_applies(xu_hat):
+            # everything of solver.py:84-94 behind the model build in ONE C call: gather of the GP inputs, posterior, draw,
+            # post-processing, (deferred reset,) append, assembly, device->host copy
+            ag = self.params["agent"]
+            opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
+            if not hasattr(self, "_lin_bufs"):
+                self._lin_bufs = {}
+            mean, var, y_gp, jl, _, host = self.engine.linearise(
+                self.env_struct, xu_hat, self.epistimic_random_vector[self.mpc_iter][sqp_iter], opts, self._pending_reset,
+                self._lin_bufs)
+            self._pending_reset = False
+            self.model_i_call = _PosteriorView(mean, var, jl)  # views of buffers the next linearisation overwrites, like the
+            self.model_i_samples = y_gp                         # reference's model_i_call / model_i_samples are replaced
+            self._data_version += 1
+            self._appended_since_train = True
+            self.engine.raise_on_status()  # waits for the stream: `host` is complete
+            h = host.numpy().copy()  # the pinned staging buffer is reused by the next call
+            return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]
         y = self.dyn_fg_jacobians_device(xu_hat, sqp_iter)
         host = torch.empty(y.shape, dtype=F64, pin_memory=True)
         host.copy_(y, non_blocking=True)  # ONE device->host copy (the reference does three, agent.py:555-557)

@@ -84,6 +84,9 @@ struct gpmpc_handle {
   int grp_size = 0;
   double grp_min_dist = -1.0;
   unsigned char *grp_flags = nullptr, *grp_decision = nullptr;
+  // scratch of gpmpc_linearise: [x, u] on the device and the gathered GP inputs
+  double *lin_xu = nullptr, *lin_xg = nullptr;
+  size_t lin_xu_count = 0, lin_xg_count = 0;
   int eig_epoch = 0;  // draw launches so far (gpmpc_eig.cuh: a failing element publishes the epoch of its launch)
   // large-m path: shared rows of all elements by one batched GEMM (k_shared_rows) whenever inv(L_oo) does not fit in
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
@@ -380,6 +383,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
   cudaFree(h->grp_flags); cudaFree(h->grp_decision);
+  cudaFree(h->lin_xu); cudaFree(h->lin_xg);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->slice_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : h->hz_ev) if (e) cudaEventDestroy(e);
@@ -1019,6 +1023,57 @@ static unsigned long long horizon_stagger(const gpmpc_handle* h, int samples_per
 }
 
 extern "C" {
+
+int gpmpc_linearise(gpmpc_handle* h, const gpmpc_env* env, const double* xu, int32_t xu_on_host, int32_t H, const double* eps,
+                    const gpmpc_sample_opts* opts, int32_t reset_first, double* mean, double* var, double* y,
+                    int32_t* jitter_level, double* out, double* out_host, void* stream_) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  ON_HANDLE_DEVICE(h);
+  if (!env || !xu || !eps || !opts || !mean || !var || !y || !out || H < 1) return fail(h, GPMPC_ERR_ARG, "null argument");
+  if (env->g_ny != h->st.g_ny || env->d != h->st.d) return fail(h, GPMPC_ERR_ARG, "env does not match handle");
+  if (h->grp_size > 0) return fail(h, GPMPC_ERR_STATE, "grouped handle");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const DevState& st = h->st;
+  const int nz = env->nx + env->nu;
+  const size_t n_xu = (size_t)st.ns * env->nx * H * nz, n_xg = (size_t)st.B * H * st.d;
+  if (h->lin_xu_count < n_xu) {
+    cudaFree(h->lin_xu);
+    h->lin_xu_count = 0;
+    CUDA_TRY(h, dev_alloc(&h->lin_xu, n_xu));
+    h->lin_xu_count = n_xu;
+  }
+  if (h->lin_xg_count < n_xg) {
+    cudaFree(h->lin_xg);
+    h->lin_xg_count = 0;
+    CUDA_TRY(h, dev_alloc(&h->lin_xg, n_xg));
+    h->lin_xg_count = n_xg;
+  }
+  const double* xu_dev = xu;
+  if (xu_on_host) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->lin_xu, xu, n_xu * 8, cudaMemcpyHostToDevice, stream));
+    xu_dev = h->lin_xu;
+  }
+  {
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n_xg + threads - 1) / threads, (size_t)h->num_sms * 8);
+    k_gather_gp_inputs<<<blocks, threads, 0, stream>>>(*env, st.ns, H, xu_dev, h->lin_xg);
+    h->launches++;
+  }
+  rc = gpmpc_posterior(h, h->lin_xg, H, mean, var, eps, opts, y, jitter_level, stream_);
+  if (rc) return rc;
+  if (reset_first) {
+    rc = gpmpc_reset_hallucinated(h);
+    if (rc) return rc;
+  }
+  rc = gpmpc_append(h, h->lin_xg, y, nullptr, H, stream_);
+  if (rc) return rc;
+  rc = gpmpc_assemble(h, env, xu_dev, y, H, out, stream_);
+  if (rc) return rc;
+  if (out_host)
+    CUDA_TRY(h, cudaMemcpyAsync(out_host, out, (size_t)st.ns * env->nx * H * (1 + nz) * 8, cudaMemcpyDeviceToHost, stream));
+  return GPMPC_OK;
+}
 
 int gpmpc_rollout(gpmpc_handle* h, const gpmpc_env* env, const double* x0, const double* u_ff,
                   const double* eps, const gpmpc_sample_opts* opts, int32_t n_steps, double* traj,

@@ -140,3 +140,17 @@ __global__ void k_fs_advance(gpmpc_env env, int ns, int T, const double* __restr
     for (int k = 0; k < nu; ++k) o[nx + k] = u_next[k];
   }
 }
+
+// get_g_xu_hat (src/environments/*.py: xu_hat[:, 0:g_ny, :, g_idx_inputs]) as a kernel: xg[b][h][a] = xu[s][0][h][g_idx[a]]
+// (the nx rows of xu are tiled copies; the reference asserts that, pendulum1D.py:165-170)
+__global__ void k_gather_gp_inputs(gpmpc_env env, int ns, int H, const double* __restrict__ xu, double* __restrict__ xg) {
+  const int nz = env.nx + env.nu, d = env.d, g_ny = env.g_ny;
+  const long long total = (long long)ns * g_ny * H * d;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(idx % d);
+    const int hh = (int)((idx / d) % H);
+    const long long s = idx / ((long long)d * H * g_ny);
+    xg[idx] = xu[((s * env.nx + 0) * H + hh) * nz + env.g_idx_inputs[a]];
+  }
+}

@@ -81,6 +81,7 @@ ABI = {
     "gpmpc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "gpmpc_set_grouping": (C.c_int, [_P, _I, C.c_double]),
     "gpmpc_truncate_hallucinated": (C.c_int, [_P, _I]),
+    "gpmpc_linearise": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _I, _I, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _D, _D, _D, _D, _D, _P]),
     "gpmpc_fs_advance": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _D, _D, C.c_double, _D, _D, _D, _D, _P]),
     "gpmpc_export_point_states": (C.c_int, [_P, _D, _P]),
     "gpmpc_base_samples": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]),
@@ -481,6 +482,30 @@ class GPEngine:
     def set_block_kernels(self, mma: bool):
         """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
         self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
+
+    def linearise(self, env: GpmpcEnv, xu: torch.Tensor, eps: torch.Tensor, opts: GpmpcSampleOpts, reset_first: bool, bufs: dict):
+        """One SQP GP linearisation in one C call (gpmpc_linearise).  xu (ns,nx,H,nx+nu): pinned CPU tensor or CUDA tensor;
+        eps CUDA (ns,g_ny,H,T).  `bufs` caches the output tensors between calls.  Returns (mean, var, y, jl, out, out_host);
+        nothing has been waited for."""
+        ns, nx, H, nz = xu.shape
+        key = (ns, nx, H, nz)
+        if bufs.get("key") != key:
+            shp = (self.ns, self.g_ny, H, self.T)
+            mk = lambda: torch.empty(shp, dtype=torch.float64, device=self.device)
+            bufs.update(key=key, mean=mk(), var=mk(), y=mk(),
+                        jl=torch.empty((self.ns, self.g_ny), dtype=torch.int32, device=self.device),
+                        out=torch.empty((ns, nx, H, 1 + nz), dtype=torch.float64, device=self.device),
+                        out_host=torch.empty((ns, nx, H, 1 + nz), dtype=torch.float64, pin_memory=True))
+        on_host = not xu.is_cuda
+        assert xu.dtype == torch.float64 and xu.is_contiguous() and (xu.is_cuda or xu.is_pinned())
+        eps = eps.to(self.device, torch.float64).reshape(self.B, H * self.T)
+        eps = eps if eps.is_contiguous() else eps.contiguous()
+        b = bufs
+        rc = self.lib.gpmpc_linearise(self.h, C.byref(env), C.c_void_p(xu.data_ptr()), int(on_host), H, _ptr(eps), C.byref(opts),
+                                      int(reset_first), _ptr(b["mean"]), _ptr(b["var"]), _ptr(b["y"]), _ptr(b["jl"]),
+                                      _ptr(b["out"]), C.c_void_p(b["out_host"].data_ptr()), _stream(self.device))
+        self._check(rc, "gpmpc_linearise")
+        return b["mean"], b["var"], b["y"], b["jl"], b["out"], b["out_host"]
 
     def truncate_hallucinated(self, n_points: int):
         """Forget the hallucinated points from index n_points on (prepare_dynamics_set's forward-sampling set)."""

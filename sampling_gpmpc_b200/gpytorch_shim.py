@@ -214,13 +214,20 @@ class ExactGP(_Module):
     # -- hyper-parameters as the reference sets them after construction (GP_model.py:121-143) ------------------
     def _hypers(self, ns: int, g_ny: int, d: int, T: int):
         base = self.covar_module.base_kernel
-        ls = torch.as_tensor(base.lengthscale, dtype=F64).detach().cpu()
+        raw = (base.lengthscale, self.covar_module.outputscale, self.likelihood.noise, self.likelihood.task_noises)
+        if any(torch.is_tensor(t) and t.is_cuda for t in raw):
+            # one device->host copy for all four (they live on the GPU when the reference has set_default_device('cuda'))
+            flat = torch.cat([torch.as_tensor(t, dtype=F64).detach().reshape(-1).to(raw[0].device) for t in raw]).cpu()
+            parts = torch.split(flat, [int(torch.as_tensor(t).numel()) for t in raw])
+            raw = tuple(p.reshape(torch.as_tensor(t).shape) for p, t in zip(parts, raw))
+        base_ls, cov_os, lik_noise, lik_task = raw
+        ls = torch.as_tensor(base_ls, dtype=F64).detach().cpu()
         ls = ls.reshape(ns, g_ny, d) if ls.numel() == ns * g_ny * d else ls.reshape(1, g_ny, d)
-        os_ = torch.as_tensor(self.covar_module.outputscale, dtype=F64).detach().cpu()
+        os_ = torch.as_tensor(cov_os, dtype=F64).detach().cpu()
         os_ = os_.reshape(ns, g_ny) if os_.numel() == ns * g_ny else os_.reshape(1, g_ny)
-        nz = torch.as_tensor(self.likelihood.noise, dtype=F64).detach().cpu()
+        nz = torch.as_tensor(lik_noise, dtype=F64).detach().cpu()
         nz = nz.reshape(ns, g_ny, 1) if nz.numel() == ns * g_ny else nz.reshape(1, g_ny, 1)
-        tn = torch.as_tensor(self.likelihood.task_noises, dtype=F64).detach().cpu()
+        tn = torch.as_tensor(lik_task, dtype=F64).detach().cpu()
         tn = tn.reshape(ns, g_ny, T) if tn.numel() == ns * g_ny * T else tn.reshape(1, g_ny, T)
         ls = _uniform_over_samples(ls, "lengthscale")
         os_ = _uniform_over_samples(os_, "outputscale")
@@ -228,7 +235,11 @@ class ExactGP(_Module):
         return ls.numpy().copy(), os_.numpy().copy(), noise.numpy().copy(), float(_SETTINGS["jitter"])
 
     def _sync(self) -> _Backend:
-        """Bring the engine's training set to this model's (train_inputs, train_targets)."""
+        """Bring the engine's training set to this model's (train_inputs, train_targets).
+
+        The reference re-builds its model from freshly concatenated tensors at every SQP iteration (agent.py:216-258), so the
+        only way to know what changed is to compare -- on the device, with ONE host round trip per model build: every check
+        below lands in one small flag tensor that is read back once (the first build of a data set needs a second one)."""
         be = self._backend
         if be is not None and be.version == self._synced_version:
             return be
@@ -245,54 +256,72 @@ class ExactGP(_Module):
         if T != (d + 1 if use_grad else 1):
             raise NotImplementedError(f"{T} tasks for input dim {d} (use_grad={use_grad})")
         hyp = self._hypers(ns, g_ny, d, T)
-
-        # the block of points that is the same for every sample and output = the real data (agent.py:204-214)
-        same = (X == X[:1, :1]).all(3).all(1).all(0) & _nan_equal(Y, Y[:1]).all(3).all(1).all(0)
-        differ = (~same).nonzero()
-        n_same = int(differ[0, 0]) if differ.numel() else n
         key_base = (ns, g_ny, d, T, dev.index)
-        be = None
-        for n_real in sorted({k[5] for k in _BACKENDS if k[:5] == key_base}, reverse=True):
-            cand = _BACKENDS[key_base + (n_real,)]
-            if n_real <= n_same and bool((X[0, 0, :n_real] == cand.Xs).all()) and \
-                    bool(_nan_equal(Y[0, :, :n_real], cand.Ys).all()):
-                be = cand  # keep the factor of the real block already held (do not flap with coincidences)
-                break
+
+        def shared_prefix():
+            # leading block of points that is the same for every sample and output = the real data (agent.py:204-214)
+            same = (X == X[:1, :1]).all(3).all(1).all(0) & _nan_equal(Y, Y[:1]).all(3).all(1).all(0)
+            return int((~same).to(torch.int32).cumsum(0).eq(0).sum())
+
+        # fast path: ONE backend of this shape exists and its real block is still the head of the data
+        cands = [k for k in _BACKENDS if k[:5] == key_base]
+        be = _BACKENDS[cands[0]] if len(cands) == 1 and cands[0][5] <= n else None
+        flags = None
+        if be is not None:
+            n_real, old, nh = be.Xs.shape[0], be.nh, n - be.Xs.shape[0]
+            Xh, Yh = X[:, :, n_real:], Y[:, :, n_real:]
+            checks = [(X[:, :, :n_real] == be.Xs).all(), _nan_equal(Y[:, :, :n_real], be.Ys.unsqueeze(0)).all()]
+            prefix_kept = old <= nh
+            if prefix_kept and old:
+                checks += [(Xh[:, :, :old] == be.Xh).all(), _nan_equal(Yh[:, :, :old], be.Yh).all()]
+            n_new = nh - old if prefix_kept else nh
+            all_nan = Yh.isnan().any(1).any(0).reshape(-1)  # NaN flag of every hallucinated label slot (nh * T)
+            flags = torch.cat([torch.stack(checks).to(torch.uint8), all_nan.to(torch.uint8)]).cpu().numpy()  # the one sync
+            if not (flags[0] and flags[1]):
+                be = None  # different real data: rebuild below
         if be is None:
+            n_same = shared_prefix()
             if n_same < 1:
                 raise NotImplementedError("no training block shared by all samples (the reference always has real data)")
-            for k in [k for k in _BACKENDS if k[:5] == key_base]:
+            for k in cands:
                 del _BACKENDS[k]  # one real data set per shape at a time
             eng = GPEngine(ns, g_ny, d, T, n_same, device=dev)
             eng.set_hypers(*hyp)
             Xs, Ys = X[0, 0, :n_same].contiguous(), Y[0, :, :n_same].contiguous()
             eng.set_real_data(Xs, Ys)
             be = _BACKENDS[key_base + (n_same,)] = _Backend(eng, Xs, Ys, hyp)
-        elif any(not np.array_equal(a, b) for a, b in zip(hyp[:3], be.hypers[:3])) or hyp[3] != be.hypers[3]:
-            be.eng.set_hypers(*hyp)
-            be.eng.set_real_data(be.Xs, be.Ys)  # new hypers: new shared factor, the hallucinated rows go with it
-            be.hypers, be.Xh, be.Yh = hyp, None, None
-            be.version += 1
-        eng, n_real = be.eng, be.Xs.shape[0]
+            n_real, old, nh = n_same, 0, n - n_same
+            Xh, Yh = X[:, :, n_real:], Y[:, :, n_real:]
+            keep, n_new = True, nh
+            new_nan = Yh.isnan().any(1).any(0).reshape(-1).to(torch.uint8).cpu().numpy() if nh else np.zeros(0, np.uint8)
+        else:
+            keep = prefix_kept and (old == 0 or bool(flags[2] and flags[3]))
+            all_nan = flags[len(checks):]
+            if not keep:  # the hallucinated set shrank or changed: start it over (agent.py:261-272)
+                n_new = nh
+            new_nan = all_nan[(nh - n_new) * T:]
+            if any(not np.array_equal(a, b) for a, b in zip(hyp[:3], be.hypers[:3])) or hyp[3] != be.hypers[3]:
+                be.eng.set_hypers(*hyp)
+                be.eng.set_real_data(be.Xs, be.Ys)  # new hypers: new shared factor, the hallucinated rows go with it
+                be.hypers, be.Xh, be.Yh = hyp, None, None
+                be.version += 1
+                keep, old, n_new = True, 0, nh
+                new_nan = Yh.isnan().any(1).any(0).reshape(-1).to(torch.uint8).cpu().numpy() if nh else np.zeros(0, np.uint8)
+        eng = be.eng
         eng.set_condition_on_hallucinated(True)
-
-        Xh, Yh = X[:, :, n_real:], Y[:, :, n_real:]
-        nh, old = Xh.shape[2], be.nh
-        keep = old <= nh and (old == 0 or (bool((Xh[:, :, :old] == be.Xh).all()) and
-                                           bool(_nan_equal(Yh[:, :, :old], be.Yh).all())))
         if not keep:
             eng.reset_hallucinated()
             be.Xh = be.Yh = None
             be.version += 1
             old = 0
-        if nh > old:
+        if n_new > 0:
             newX, newY = Xh[:, :, old:].contiguous(), Yh[:, :, old:].contiguous()
             # observation_nan_policy('mask'): a label slot is dropped for every element if it is NaN in any;
             # slots are (point, task): a point may keep its value and lose its derivative slots (agent.py:402)
-            active = (~newY.isnan().any(1).any(0)).cpu().numpy().astype(np.uint8)  # (n_new, T)
+            active = (1 - np.asarray(new_nan, dtype=np.uint8)).reshape(n_new, T)
             step = max(1, 512 // T)
-            for p0 in range(0, nh - old, step):
-                p1 = min(nh - old, p0 + step)
+            for p0 in range(0, n_new, step):
+                p1 = min(n_new, p0 + step)
                 eng.append_masked(newX[:, :, p0:p1].contiguous(), newY[:, :, p0:p1].contiguous(), active[p0:p1])
             be.Xh = newX if be.Xh is None else torch.cat([be.Xh, newX], 2)
             be.Yh = newY if be.Yh is None else torch.cat([be.Yh, newY], 2)

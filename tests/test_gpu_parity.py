@@ -314,17 +314,17 @@ def test_rollout_from_pinned_host_buffers_is_bit_identical():
 def test_pendulum2d_rollout_matches_oracle_refit():
     """True-reachable-set shape (benchmarking/simulate_true_reachable_set.py:179-259): real data WITH derivatives
     (m = 180), d = 3, T = 4, g_ny = 2, zero-variance switch on, no feedback."""
-    from oracle.rollout_ref import reference_rollout
+    from oracle.rollout_ref import reference_true_reachable_set
     from sampling_gpmpc_b200 import configs
     from sampling_gpmpc_b200.rollout import ForwardRollout
     ns, steps = 6, 10
-    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps)
+    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps)  # the yaml's min-distance filter (1e-4) included
     g = torch.Generator().manual_seed(2)
     eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64).clamp(-2.5, 2.5)
     u = (2.0 * torch.sin(torch.linspace(0, 3, steps, dtype=torch.float64))).reshape(steps, 1)
-    fr = ForwardRollout(params, condition=True)
+    fr = ForwardRollout(params, condition=True)  # one reference Agent of ns samples
     traj = fr.run(u, eps).cpu().numpy()
-    ref = reference_rollout(params, fr.spec, u, eps, condition=True)
+    ref = reference_true_reachable_set(params, fr.spec, u, eps, ns)
     ratio = scaled_close(traj, ref, float(np.sqrt(outputscales(params).max())), RTOL)
     REPORT["rollout/pendulum2D"] = dict(traj=ratio, status=fr.engine.status())
     _dump_report()
