@@ -107,7 +107,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_rollout(ns, horizon, seed, threads):
+def cpu_reference_rollout(ns, horizon, seed, threads, return_traj=False):
     """The reference-equivalent CPU torch path (oracle: full GP re-fit per step) on a bounded sample."""
     import torch
     from oracle.rollout_ref import reference_rollout
@@ -117,8 +117,28 @@ def cpu_reference_rollout(ns, horizon, seed, threads):
     params = configs.car_residual_fs(ns, horizon, with_derivatives=True)
     u, eps = synthetic_inputs(ns, horizon, 3, seed)
     t0 = time.perf_counter()
-    reference_rollout(params, make_env_spec(params), u, eps, condition=True)
-    return time.perf_counter() - t0
+    traj = reference_rollout(params, make_env_spec(params), u, eps, condition=True)
+    dt = time.perf_counter() - t0
+    return (dt, traj) if return_traj else dt
+
+
+def gpu_parity_against_cpu(ns, horizon, seed, ref_traj, device):
+    """The trajectories the CPU leg just computed (oracle, full re-fit per step) against the CUDA path on the same inputs:
+    worst |gpu - cpu| / (1e-9 * max(|cpu|, s)), s = the state scale 14 (m/s) * sqrt(max outputscale).  <= 1 passes."""
+    import numpy as np
+    import torch
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    params = configs.car_residual_fs(ns, horizon, with_derivatives=True)
+    u, eps = synthetic_inputs(ns, horizon, 3, seed)
+    fr = ForwardRollout(params, condition=True, device=device)
+    traj = fr.run(u.to(device), eps.to(device)).cpu().numpy()
+    status = fr.check()
+    scale = 14.0 * float(np.sqrt(max(params["agent"]["Dyn_gp_outputscale"]["both"])))
+    worst = float(np.max(np.abs(traj - ref_traj) / (1e-9 * np.maximum(np.abs(ref_traj), scale))))
+    return {"samples": ns, "steps": horizon, "worst_error_over_tolerance": worst, "passes": bool(worst <= 1.0),
+            "tolerance": "1e-9 * max(|cpu|, 14 * sqrt(outputscale))", "engine_status": int(status),
+            "what": "CUDA rollout vs the oracle's full-refit CPU rollout of the cpu_baseline leg, same seeded inputs"}
 
 
 def run_reference(args):
@@ -191,7 +211,9 @@ def extras(torch, device, cpu_leg=True):
         out["pendulum_true_reachable_set"] = {
             "sample_steps_per_sec": ns2 * st2 / (ms2 * 1e-3), "ms_per_rollout": ms2, "ns": ns2, "steps": st2,
             "algorithmic_GBps": wb / ms2 / 1e6, "algorithmic_GFLOPs": wf / ms2 / 1e6, "engine_status": fr.engine.status(),
-            "shape": "g_ny=2, d=3, T=4, m=180 (derivative observations), conditioning on; shared rows by the batched GEMM (K1a)"}
+            "shape": "g_ny=2, d=3, T=4, m=180 (derivative observations), conditioning on, params_pendulum.yaml's zero-variance "
+                     "rule and min-distance filter (1e-4) on, 10^4 reference Agents of 20 samples (per-Agent reductions on the "
+                     "device); shared rows by the batched GEMM (K1a)"}
         del fr, eps2
     except Exception as exc:  # noqa: BLE001
         out["pendulum_true_reachable_set"] = {"error": repr(exc)}
@@ -221,7 +243,21 @@ def extras(torch, device, cpu_leg=True):
         torch.cuda.synchronize()
         dev_times.append(e0.elapsed_time(e1))
         x_h = x_h + 0.005 * rng.standard_normal(x_h.shape)
+    through_ref = None
+    try:  # the UNMODIFIED reference Agent (baseline/_ref copy) on the shim, in its own process
+        drv = subprocess.run([sys.executable, os.path.join(REPO, "tests", "ref_agent_driver.py"), "pendulum1D_sqp", "--time", "5"],
+                             capture_output=True, text=True, timeout=600)
+        d = json.loads([l for l in drv.stdout.splitlines() if l.startswith("{")][-1])
+        through_ref = d.get("ms_per_linearisation", d)
+        if isinstance(through_ref, dict) and "median" in through_ref:
+            through_ref = {"median_ms": through_ref["median"], "min_ms": through_ref["min"], "ns": 12,
+                           "worst_error_over_tolerance": max(d["worst_over_tolerance"].values()),
+                           "what": through_ref["what"] + " (fixture shape: ns=12, H=17; most of it is the reference's own "
+                                   "Python: model construction, tiling, asserts with device syncs)"}
+    except Exception as exc:  # noqa: BLE001
+        through_ref = {"error": repr(exc)}
     out["sqp_linearisation_ms"] = {"host_observed_ms_incl_d2h": float(np.median(times[2:])),
+                                   "through_unmodified_agent": through_ref,
                                    "device_ms": float(np.median(dev_times[2:])),
                                    "shape": "pendulum1D: ns=70, H=17, T=3 (q=51), n_obs=87",
                                    "calls": "train_hallucinated_dynGP + dyn_fg_jacobians (solver.py:84-94)"}
@@ -241,6 +277,16 @@ def extras(torch, device, cpu_leg=True):
         gd = torch.Generator(device=device).manual_seed(0)
         base = torch.stack([torch.linspace(-0.9, 0.9, Hc), torch.linspace(-0.5, 0.5, Hc)], 1).to(device, torch.float64)
         xq = (base[None, None] + 0.05 * torch.randn(20, 1, Hc, 2, generator=gd, dtype=torch.float64, device=device)).expand(20, 3, Hc, 2).contiguous()
+        # untimed first call: CUDA loads each kernel of the 7 MB library lazily at its first launch and the workspaces are
+        # allocated (cudaMalloc synchronises) -- 264 ms in round 1's device_ms_by_sqp_iteration[0]; not part of an iteration
+        ee = torch.randn(20, 3, Hc, 3, generator=gd, dtype=torch.float64, device=device).clamp(-3, 3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, yq, _ = eng.posterior(xq, ee, eng.opts(beta=3.0))
+        eng.append(xq, yq)
+        torch.cuda.synchronize()
+        first_call_ms = (time.perf_counter() - t0) * 1e3
+        eng.reset_hallucinated()
         per_it = []
         for it in range(its):
             ee = torch.randn(20, 3, Hc, 3, generator=gd, dtype=torch.float64, device=device).clamp(-3, 3)
@@ -254,7 +300,7 @@ def extras(torch, device, cpu_leg=True):
             xq = (xq + 0.03 * torch.randn(20, 1, Hc, 2, generator=gd, dtype=torch.float64, device=device)).contiguous()
         out["sqp_linearisation_car_ms"] = {"device_ms_by_sqp_iteration": per_it, "factor_rows_before_call": [150 * i for i in range(its)],
                                            "shape": "car residual: ns=20, g_ny=3, H=50, T=3 (q=150), m=45; model call + conditioning",
-                                           "engine_status": eng.status()}
+                                           "engine_status": eng.status(), "first_call_ms_incl_lazy_module_load_and_allocation": round(first_call_ms, 2)}
         del eng
     except Exception as exc:  # noqa: BLE001
         out["sqp_linearisation_car_ms"] = {"error": repr(exc)}
@@ -361,6 +407,54 @@ def run_ours(args):
     h2d = eps_host.numel() * 8 + u_host.numel() * 8
     d2h = traj_host.numel() * 8
 
+    # ---- the one collective of the path and its consumers (N > 1): rollout -> NCCL all-gather of the trajectories ->
+    #      per-stage boxes / max-deviation tightening -> per-stage convex hulls (generate_convex_hull.py:83-104) ---------------
+    gathered = None
+    if world > 1:
+        def gathered_step():
+            fr.run(u_dev, eps_dev, traj)
+            allt = fr.all_gather_trajectories(traj)  # (ns_total, nx, H+1) on every rank
+            lo, hi = eng.traj_stats(allt)
+            hulls = eng.stage_hulls(allt, 0, 1)      # ends with the device->host copy of the hull candidates
+            return allt, lo, hi, hulls
+        gathered_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            allt, lo, hi, hulls = gathered_step()
+        e1.record()
+        barrier()
+        t_g = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t_g, op=dist.ReduceOp.MAX)
+        e0.record()
+        for _ in range(args.steps):
+            fr.all_gather_trajectories(traj)
+        e1.record()
+        barrier()
+        t_ag = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t_ag, op=dist.ReduceOp.MAX)
+        gathered = {"value": world * ns * HORIZON / (float(t_g.item()) / args.steps * 1e-3), "unit": UNIT,
+                    "ms_per_step": float(t_g.item()) / args.steps,
+                    "all_gather_ms": float(t_ag.item()) / args.steps, "all_gather_bytes": int(allt.numel() * 8),
+                    "hull_vertices_stage_last": int(len(hulls[-1])),
+                    "what": "rollout + all_gather_into_tensor of the trajectories + stage boxes + stage hulls, max over ranks"}
+        del allt
+        # sharded vs single GPU, bit for bit, at a size one GPU holds: rank 0 rolls the WHOLE population out alone
+        ns_chk = 2048
+        p_chk = configs.car_residual_fs(ns_chk * world, HORIZON, with_derivatives=True)
+        u_c, eps_c = synthetic_inputs(ns_chk * world, HORIZON, 3, 4242)  # same seed on every rank: the global base samples
+        fr_c = ForwardRollout(p_chk, condition=True, rank=rank, world_size=world, device=device)
+        part = fr_c.run(u_c.to(device), eps_c.to(device))
+        whole = fr_c.all_gather_trajectories(part)
+        if rank == 0:
+            fr_1 = ForwardRollout(p_chk, condition=True, device=device)
+            single = fr_1.run(u_c.to(device), eps_c.to(device))
+            gathered["sharded_bit_identical_to_single_gpu"] = bool(torch.equal(whole, single))
+            gathered["self_check_samples"] = ns_chk * world
+            del fr_1, single
+        del fr_c, part, whole
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,10 +468,15 @@ def run_ours(args):
     achieved = work_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
     # DRAM bytes per step launch from the committed ncu capture of this same workload (profiles/, per round)
     traffic, traffic_src = None, None
+    from sampling_gpmpc_b200.engine import load_library
+    lib_version = load_library().gpmpc_version().decode()
     caps = sorted(f for f in os.listdir(os.path.join(REPO, "profiles")) if "traffic" in f and f.endswith(".json"))
     if caps and ns == 125000:
         cap = json.load(open(os.path.join(REPO, "profiles", caps[-1])))
-        traffic, traffic_src = cap["traffic_bytes_per_step_launch"], "profiles/" + caps[-1]
+        if cap.get("library_version") == lib_version:  # never quote a capture of another build
+            traffic, traffic_src = cap["traffic_bytes_per_step_launch"], "profiles/" + caps[-1]
+        else:
+            traffic_src = f"no ncu DRAM capture of library {lib_version!r} committed (latest: profiles/{caps[-1]})"
     roofline = {"bound": "hbm", "kernel": "k_step<2,3> + k_step_finish<3> (fused rollout step: one gpmpc_step call)",
                 "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
@@ -394,10 +493,16 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(gpu_launches), "roofline": roofline, "engine_status": status,
             "state_bytes_per_gpu": int(eng.state_bytes)}
+    if gathered is not None:
+        line["e2e_gathered"] = gathered
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cpu_reference_rollout(4, 5, 1, threads)  # warm the CPU path
-        dt = cpu_reference_rollout(args.cpu_samples, HORIZON, 7, threads)
+        dt, ref_traj = cpu_reference_rollout(args.cpu_samples, HORIZON, 7, threads, return_traj=True)
+        try:
+            line["parity_check"] = gpu_parity_against_cpu(args.cpu_samples, HORIZON, 7, ref_traj, device)
+        except Exception as exc:  # noqa: BLE001
+            line["parity_check"] = {"error": repr(exc)}
         line["cpu_baseline"] = {"value": args.cpu_samples * HORIZON / dt, "unit": UNIT, "cores": threads,
                                 "kind": "port",
                                 "sample": f"{args.cpu_samples} samples x {HORIZON} steps ({dt:.1f} s), oracle = reference-"

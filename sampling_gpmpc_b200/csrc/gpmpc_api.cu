@@ -92,6 +92,7 @@ struct gpmpc_handle {
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
   // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
   int wo_min_m = 1;
+  bool force_wo = false;  // experiment: the batched shared-rows GEMM also for small m (gpmpc_set_option "force_wo")
   int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   // SQP-mode model call: tensor-core kernel k_posterior_mma (default) or the scalar substitution kernel k_posterior
   // (gpmpc_set_block_kernels / GPMPC_BLOCK_SCALAR=1: the independent reference semantics the parity tests compare with)
@@ -837,7 +838,7 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   bool loo_smem = loop_sz * 8 + shared_tab + 8 * per_warp <= budget;
   // ... or, for large m, not by this kernel at all: batched GEMM first (k_shared_rows), NB = column blocks per tile
   int nb = 0;
-  if (!loo_smem && m >= h->wo_min_m)
+  if ((!loo_smem || h->force_wo) && m >= h->wo_min_m)
     for (nb = h->wo_max_nb; nb >= 1; --nb)
       if ((size_t)st.mo * 8 * nb * 8 + 1024 <= budget) break;
   if (nb >= 1) {
@@ -1483,6 +1484,7 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   if (n == "rollout_fused") h->fused_rollout = value != 0;
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
+  else if (n == "force_wo") h->force_wo = value != 0;
   else return fail(h, GPMPC_ERR_ARG, "unknown option " + n);
   return GPMPC_OK;
 }

@@ -16,8 +16,9 @@ u, eps = u.cuda(), eps.cuda()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
 for cfg in cfgs:
-    if cfg == "step":
+    if cfg in ("step", "wo"):
         fr.engine.set_option("rollout_fused", 0)
+        fr.engine.set_option("force_wo", int(cfg == "wo"))
     else:
         g, s = cfg.split(":")
         fr.engine.set_option("rollout_fused", 1)

@@ -1,8 +1,9 @@
 """ncu csv (gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum per launch of one conditioned car rollout,
-tools/profile_rollout.py 125000 50) -> profiles/r1_traffic_<tag>.json, the `roofline.traffic` source of bench.py.
+tools/profile_rollout.py 125000 50) -> profiles/r<round>_traffic_<tag>.json, the `roofline.traffic` source of bench.py.
     python tools/traffic_summary.py gpurun_out/traffic.csv profiles/r1_traffic_v18.json"""
 import csv, json, sys
 src, dst = sys.argv[1], sys.argv[2]
+version = sys.argv[3] if len(sys.argv) > 3 else None
 rows = list(csv.DictReader([l for l in open(src) if l.startswith('"')]))
 k = {}
 for r in rows:
@@ -17,7 +18,7 @@ for r in rows:
         gb = v * {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}[unit]
         d["dram_read_GB" if "read" in r["Metric Name"] else "dram_write_GB"] += gb
 step = [n for n in k if n.startswith("k_step")]
-n_steps = max(k[n]["launches"] for n in step)
+n_steps = max(k[n]["launches"] for n in step if n.startswith("k_step<"))  # (k_step_finish also has its eigen-redo launches)
 traffic = sum(k[n]["dram_read_GB"] + k[n]["dram_write_GB"] for n in step) * 1e9 / n_steps
 tot = sum(d["time_ms_ncu_serialised"] for d in k.values())
 B, m = 375000, 45
@@ -27,6 +28,6 @@ out = {"source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram
        "kernels": {n: {a: (round(b, 3) if isinstance(b, float) else b) for a, b in d.items()} for n, d in k.items()},
        "step_share_of_rollout_time": sum(k[n]["time_ms_ncu_serialised"] for n in step) / tot,
        "traffic_bytes_per_step_launch": traffic, "algorithmic_bytes_per_step_launch": alg,
-       "traffic_over_algorithmic": traffic / alg}
+       "traffic_over_algorithmic": traffic / alg, "library_version": version}
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out, indent=1))
