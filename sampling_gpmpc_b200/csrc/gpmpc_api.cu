@@ -494,8 +494,10 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
   {
     CUDA_TRY(h, opt_in_smem(h, k_factor_real, h->max_dyn_smem));
     CUDA_TRY(h, opt_in_smem(h, k_invert_real, h->max_dyn_smem));
-    if ((size_t)m * 8 * K0B_WARPS > (size_t)h->max_dyn_smem)
-      return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~7000)");
+    int k0b_warps = K0B_WARPS;  // one column of inv(L_oo) per warp, m doubles of shared memory each
+    while (k0b_warps > 1 && (size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem) k0b_warps >>= 1;
+    if ((size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem)
+      return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~29000)");
     // m in the thousands: the factorisation cooperatively over all SMs (one grid barrier per pivot); GPMPC_K0_COOP_MIN_M
     int coop_min_m = 768;
     if (const char* e = getenv("GPMPC_K0_COOP_MIN_M")) coop_min_m = atoi(e);
@@ -509,7 +511,7 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     } else {
       k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
     }
-    k_invert_real<<<dim3((m + K0B_WARPS - 1) / K0B_WARPS, g_ny), K0B_WARPS * 32, (size_t)m * 8 * K0B_WARPS, stream>>>(st);
+    k_invert_real<<<dim3((m + k0b_warps - 1) / k0b_warps, g_ny), k0b_warps * 32, (size_t)m * 8 * k0b_warps, stream>>>(st);
     h->launches++;
   }
   h->launches++;

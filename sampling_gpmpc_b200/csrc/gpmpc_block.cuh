@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(K0_THREADS) k_factor_real_coop(DevState st) {
 __global__ void __launch_bounds__(K0B_WARPS * 32) k_invert_real(DevState st) {
   extern __shared__ __align__(16) double k0b_x[];  // [K0B_WARPS][m]
   const int j = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int m = st.m, jj = blockIdx.x * K0B_WARPS + wid;
+  const int m = st.m, jj = blockIdx.x * (blockDim.x >> 5) + wid;  // (the launch picks 4, 2 or 1 warps per CTA by m)
   if (jj >= m) return;
   const double* A = st.Loo + (size_t)j * m * m;
   double* LP = st.LooP + (size_t)j * subpanel_off((m + 7) >> 3, 0);

@@ -3,6 +3,8 @@ fused step over  ns x horizon x training-set size m x input dim d  on ONE GPU, e
 GB/s and GFLOP/s (gpmpc_last_launch_work) against the measured HBM / FP64 peaks.
 
     python tools/sweep.py [--quick] [--out gpurun_out/sweep.json]
+    torchrun --nproc-per-node N tools/sweep.py --only-oversize   # N GPUs: the points whose factor state exceeds ONE GPU's HBM,
+                                                                  # samples sharded contiguously (no collective on the data path)
 
 Inputs as SURVEY.md states them: X_real ~ U[-1,1]^d (seed 0), y = sum sin(x_i) with the analytic gradient as
 derivative observations when --grad-obs (m = n_real * T) else values only (m = n_real); lengthscale 1, outputscale 1,
@@ -30,8 +32,14 @@ def state_bytes(ns, g_ny, T, m, steps):
     return ns * g_ny * 8.0 * 8 * (P * (mo + 8) + 4 * P * (P - 1))
 
 
-def run_point(ns, steps, n_real, d, g_ny, grad_obs, reps):
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+
+
+def run_point(ns_total, steps, n_real, d, g_ny, grad_obs, reps):
     T = d + 1
+    per = -(-ns_total // WORLD)
+    ns = max(0, min(per, ns_total - RANK * per))  # this rank's contiguous shard
     g = torch.Generator().manual_seed(0)
     X = torch.rand(n_real, d, generator=g, dtype=torch.float64) * 2 - 1
     Y = torch.full((g_ny, n_real, T), float("nan"), dtype=torch.float64)
@@ -64,6 +72,13 @@ def run_point(ns, steps, n_real, d, g_ny, grad_obs, reps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        if WORLD > 1:  # the step loop of the slowest rank
+            import torch.distributed as dist
+            t = torch.tensor([ms, by, fl], dtype=torch.float64, device="cuda")
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, by, fl = float(tm[0]), float(t[1]), float(t[2])
         if rep > 0 and (best is None or ms < best):
             best, work = ms, (by, fl)
     st = eng.status()
@@ -71,8 +86,8 @@ def run_point(ns, steps, n_real, d, g_ny, grad_obs, reps):
     sb = eng.state_bytes
     del eng
     torch.cuda.empty_cache()
-    return {"ns": ns, "steps": steps, "n_real": n_real, "m": m, "d": d, "T": T, "g_ny": g_ny, "ms": best,
-            "sample_steps_per_s": ns * steps / best * 1e3, "alg_GBps": work[0] / best / 1e6,
+    return {"ns": ns_total, "n_gpus": WORLD, "steps": steps, "n_real": n_real, "m": m, "d": d, "T": T, "g_ny": g_ny, "ms": best,
+            "sample_steps_per_s": ns_total * steps / best * 1e3, "alg_GBps": work[0] / best / 1e6,
             "alg_GFLOPs": work[1] / best / 1e6, "state_GB": sb / 1e9, "status": st}
 
 
@@ -82,7 +97,13 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--g-ny", type=int, default=2)
     ap.add_argument("--max-seconds", type=float, default=400.0)
+    ap.add_argument("--large-m", action="store_true", help="only the m = 1e4 points small enough for the block-kernel fallback")
+    ap.add_argument("--only-oversize", action="store_true", help="only the points that do not fit one GPU (multi-GPU runs)")
     a = ap.parse_args()
+    if WORLD > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     pk = peaks()
     if a.quick:
         grid = [(1000, 10, 100, 2, False), (1000, 10, 250, 3, True), (200, 10, 1000, 2, False)]
@@ -99,15 +120,26 @@ def main():
         need = state_bytes(ns, a.g_ny, d + 1, m, steps)
         # rough cost model to keep the sweep bounded: skip points that would take > ~20 s
         est_flop = ns * a.g_ny * steps * (d + 1) * (m * m + m * steps * (d + 1) + (steps * (d + 1)) ** 2 / 3.0)
-        if m > 4000:
+        if m > 4000 and not a.large_m:
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d,
-                            "why": "m = 1e4: neither K1a's kernel tile (mo x 8 doubles of shared memory) nor K1's per-warp w array holds such an "
-                                   "m (DESIGN.md 7); not run"})
+                            "why": "m = 1e4: served by the general block kernels only (gpmpc_step falls back to posterior + append, "
+                                   "inv(L_oo) re-streamed per element): run separately with --large-m (DESIGN.md 7)"})
             continue
-        if need > HBM_BUDGET:
-            skipped.append({"ns": ns, "steps": steps, "m": m, "d": d, "why": f"factor state {need / 1e9:.0f} GB > HBM"})
+        if a.large_m and (m <= 4000 or ns * a.g_ny * steps > 40000):
             continue
-        if est_flop > 2e14 or time.time() - t_start > a.max_seconds:
+        if a.only_oversize and need <= HBM_BUDGET:
+            continue
+        if need > HBM_BUDGET * WORLD:
+            skipped.append({"ns": ns, "steps": steps, "m": m, "d": d,
+                            "why": f"factor state {need / 1e9:.0f} GB > HBM of {WORLD} GPU(s)"})
+            continue
+        elapsed = time.time() - t_start
+        if WORLD > 1:  # every rank must take the same decision
+            import torch.distributed as dist
+            te = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            elapsed = float(te[0])
+        if est_flop > 2e14 * WORLD or elapsed > a.max_seconds:
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d, "why": "time budget of the sweep"})
             continue
         try:
@@ -116,16 +148,20 @@ def main():
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d, "why": f"error: {e}"[:200]})
             torch.cuda.empty_cache()
             continue
-        r["hbm_frac"] = r["alg_GBps"] / pk["hbm_gbs"]
-        r["fp64_frac"] = r["alg_GFLOPs"] / 1e3 / pk["fp64_tflops"]
+        r["hbm_frac"] = r["alg_GBps"] / pk["hbm_gbs"] / WORLD   # fractions of the aggregate peaks of the GPUs used
+        r["fp64_frac"] = r["alg_GFLOPs"] / 1e3 / pk["fp64_tflops"] / WORLD
         r["bound"] = "hbm" if r["hbm_frac"] >= r["fp64_frac"] else "fp64"
         rows.append(r)
-        print("ns=%-8d steps=%-4d m=%-6d d=%d T=%d  %9.2f ms  %12.0f sample-steps/s  %7.0f GB/s (%.2f)  %8.0f GFLOP/s (%.3f)  st=%d"
+        if RANK == 0:
+          print("ns=%-8d steps=%-4d m=%-6d d=%d T=%d  %9.2f ms  %12.0f sample-steps/s  %7.0f GB/s (%.2f)  %8.0f GFLOP/s (%.3f)  st=%d"
               % (ns, steps, r["m"], d, r["T"], r["ms"], r["sample_steps_per_s"], r["alg_GBps"], r["hbm_frac"],
                  r["alg_GFLOPs"], r["fp64_frac"], r["status"]), flush=True)
+    if RANK != 0:
+        return
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     json.dump({"peaks": pk, "g_ny": a.g_ny, "rows": rows, "skipped": skipped,
-               "note": "one GPU; per point best of the timed passes after one warm-up pass; CUDA events around the "
+               "n_gpus": WORLD,
+               "note": f"{WORLD} GPU(s), samples sharded contiguously, max over ranks; per point best of the timed passes after one warm-up pass; CUDA events around the "
                        "whole step loop (host launch overhead included: small ns x steps points are launch-bound)"},
               open(a.out, "w"), indent=1)
     print(f"{len(rows)} points, {len(skipped)} skipped -> {a.out}")
