@@ -92,6 +92,9 @@ struct gpmpc_handle {
   // shared memory beside the warps (m > ~130) and m >= wo_min_m; GPMPC_WO_MIN_M overrides the threshold (tests use it
   // to reach the one-element-per-pass path through L2, which measured 28 % slower at m = 180, 7.8x slower at m = 1000)
   int wo_min_m = 1;
+  bool force_big = false;            // tests: k_step_big (+ k-slab GEMM) for any m
+  int big_slab_cap = 0;              // tests: cap on the rows of K per GEMM pass (several slabs at small m)
+  bool force_block_fallback = false;  // tests: gpmpc_step through posterior + append even where k_step_big applies
   bool force_wo = false;  // experiment: the batched shared-rows GEMM also for small m (gpmpc_set_option "force_wo")
   int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   // SQP-mode model call: tensor-core kernel k_posterior_mma (default) or the scalar substitution kernel k_posterior
@@ -755,22 +758,67 @@ static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double*
 }
 
 // Regime A (large m): W_o = inv(L_oo) K_o for every element, NB column blocks of 8 per tile
+// slab = rows of K per pass (multiple of 8); slab >= mo: the one-pass form
 template <int D, int T, int NB>
-static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double* x, cudaStream_t stream) {
+static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double* x, cudaStream_t stream, int slab = 1 << 30) {
   constexpr int E = 8 * NB / T;
   auto kern = k_shared_rows<D, T, NB>;
   CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem));
-  const size_t smem = ((size_t)st.mo * 8 * NB + ((E * D + 1) & ~1)) * 8;
+  slab = std::min(slab, st.mo);
+  const size_t smem = ((size_t)slab * 8 * NB + ((E * D + 1) & ~1)) * 8;
   const int n_tiles = (st.ns + E - 1) / E;
   // few row panels (m of a few hundred): 8 warps per CTA balance them better than 16 and two CTAs share an SM
   const int Pm = st.mo / 8;
   const int threads = Pm <= 32 ? 256 : SR_THREADS;
   const int per_sm = threads == 256 && 2 * (smem + 1024) <= (size_t)h->max_dyn_smem ? 2 : 1;
   dim3 grid(std::min(n_tiles, std::max(1, h->num_sms * per_sm / st.g_ny)), st.g_ny);
-  kern<<<grid, threads, smem, stream>>>(st, x);
-  h->launches++;
+  for (int k_lo = 0; k_lo < st.mo; k_lo += slab) {
+    kern<<<grid, threads, smem, stream>>>(st, x, k_lo, std::min(st.mo, k_lo + slab));
+    h->launches++;
+  }
   CUDA_TRY(h, cudaGetLastError());
   return GPMPC_OK;
+}
+
+// The step for training sets beyond k_step's per-warp w array (m in the thousands): batched shared-rows GEMM in k-slabs,
+// then k_step_big (one CTA per element, w_o in global memory), then the usual finishing kernel.
+template <int D, int T>
+static int launch_step_big(gpmpc_handle* h, const DevState& st, const double* x, const double* eps, const gpmpc_sample_opts& o,
+                           double* mean, double* var, double* y, int* jl, int grow, cudaStream_t stream, bool* handled) {
+  *handled = false;
+  const size_t budget = (size_t)h->max_dyn_smem;
+  const int P8 = (st.c + 7) / 8;
+  const int FS = T + T * (T + 1) / 2;
+  const size_t big_smem = ((size_t)std::max(8 * P8, 1) * T + (size_t)(BIG_THREADS / 32) * std::max(8 * T, FS)) * 8;
+  if (big_smem + 1024 > budget) return GPMPC_OK;  // own rows beyond shared memory too: the general block kernels
+  const size_t need = (size_t)st.B * st.mo * T;
+  if (h->wo_count < need) {
+    cudaFree(h->st.Wo);
+    h->st.Wo = nullptr;
+    h->wo_count = 0;
+    CUDA_TRY(h, dev_alloc(&h->st.Wo, need));
+    h->wo_count = need;
+  }
+  DevState stw = st;
+  stw.Wo = h->st.Wo;
+  // column blocks per tile: as many as leave a slab of >= 512 rows of K in shared memory
+  int nb = std::min(3, h->wo_max_nb), slab = 0;
+  for (; nb >= 1; --nb) {
+    slab = (int)((budget - 2048) / ((size_t)64 * nb)) & ~7;
+    if (slab >= 512 || nb == 1) break;
+  }
+  if (h->big_slab_cap >= 8) slab = std::min(slab, h->big_slab_cap);
+  if (slab < 8) return GPMPC_OK;
+  int rc = nb == 3 ? launch_shared_rows<D, T, 3>(h, stw, x, stream, slab)
+           : nb == 2 ? launch_shared_rows<D, T, 2>(h, stw, x, stream, slab)
+                     : launch_shared_rows<D, T, 1>(h, stw, x, stream, slab);
+  if (rc) return rc;
+  CUDA_TRY(h, opt_in_smem(h, k_step_big, h->max_dyn_smem));
+  k_step_big<<<st.B, BIG_THREADS, big_smem, stream>>>(stw, x, grow);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  *handled = true;
+  return launch_step_finish<T>(h, stw, x, eps, o, mean, var, y, jl, grow, stream);
 }
 
 template <int D, int T, bool LOO_SMEM, bool WO = false>
@@ -826,6 +874,7 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
     int rc = launch_step_shared<D, T>(h, st, x, eps, o, mean, var, y, jl, stream, handled);
     if (rc || *handled) return rc;
   }
+  if (h->force_big && h->grp_size == 0) return launch_step_big<D, T>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
   // shared-memory budget, mirroring the carve-up at the top of k_step
   const int m = st.m, Pm = (m + 7) / 8, P8 = (st.c + 7) / 8;
   const size_t loop_sz = subpanel_off(Pm, 0);
@@ -870,7 +919,9 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
   }
   const size_t fixed = shared_tab + (loo_smem ? loop_sz * 8 : 0);
   *handled = fixed + per_warp <= budget;
-  if (!*handled) return GPMPC_OK;  // factor too tall for the per-warp w array: general block kernels take over
+  if (!*handled && h->grp_size == 0 && !h->force_block_fallback)  // m beyond the per-warp w array: GEMM in k-slabs + k_step_big
+    return launch_step_big<D, T>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
+  if (!*handled) return GPMPC_OK;  // general block kernels take over
   int warps = (int)std::min<size_t>(STEP_MAX_WARPS, (budget - fixed) / per_warp);
   // small launches: spread the samples over the SMs rather than filling few CTAs
   const int per_cta_need = (st.ns * st.g_ny + h->num_sms - 1) / h->num_sms;
@@ -1487,6 +1538,9 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;
+  else if (n == "force_block_fallback") h->force_block_fallback = value != 0;
+  else if (n == "force_big") h->force_big = value != 0;
+  else if (n == "big_slab_cap") h->big_slab_cap = (int)value & ~7;
   else return fail(h, GPMPC_ERR_ARG, "unknown option " + n);
   return GPMPC_OK;
 }

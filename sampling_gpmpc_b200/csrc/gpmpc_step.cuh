@@ -626,9 +626,12 @@ __device__ __forceinline__ bool real_point_full(const DevState& st, int i, int p
 template <int NC>
 __device__ __forceinline__ int sr_rot(int row) { return NC == 16 ? 4 * (row & 3) : 4 * ((row >> 1) & 1); }
 
+// k_lo / k_hi (multiples of 8): only the rows [k_lo, k_hi) of K (= columns of inv(L_oo)) are processed by this launch and the
+// result is ADDED to st.Wo when k_lo > 0 -- the k-slab form for training sets whose kernel tile K[mo][8 NB] does not fit in
+// shared memory (m = 10^4: 640 KB for NB = 1); the host walks the slabs.  k_lo = 0, k_hi = mo is the one-pass form.
 template <int D, int T, int NB>
 __global__ void __launch_bounds__(SR_THREADS, 1)
-k_shared_rows(DevState st, const double* __restrict__ x) {
+k_shared_rows(DevState st, const double* __restrict__ x, int k_lo, int k_hi) {
   constexpr int NC = 8 * NB, E = NC / T;
   constexpr uint32_t KSTEP = 4 * NC * 8;  // bytes of K per k-step (4 rows)
   extern __shared__ __align__(128) double smem[];
@@ -636,10 +639,12 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int m = st.m, mo = st.mo, Pm = mo >> 3;
-  double* sK = smem;                  // [mo][NC]
-  double* sx = sK + (size_t)mo * NC;  // [E][D]
+  const int ks = k_hi - k_lo;         // rows of K in this pass
+  const bool one_pass = k_lo == 0 && k_hi == mo;
+  double* sK = smem;                  // [ks][NC]   (row i of K at local row i - k_lo)
+  double* sx = sK + (size_t)ks * NC;  // [E][D]
   const double* gL = st.LooP + (size_t)j_out * subpanel_off(Pm, 0);
-  for (int idx = threadIdx.x; idx < mo * NC; idx += blockDim.x) sK[idx] = 0.0;  // padding rows / columns stay 0
+  for (int idx = threadIdx.x; idx < ks * NC; idx += blockDim.x) sK[idx] = 0.0;  // padding rows / columns stay 0
   double il[D];
 #pragma unroll
   for (int a = 0; a < D; ++a) il[a] = 1.0 / st.ls[j_out * D + a];
@@ -658,13 +663,14 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
       sx[threadIdx.x] = e < e_live ? x[((size_t)(s0 + e) * st.g_ny + j_out) * D + a] : 0.0;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < m * E; idx += blockDim.x) {
-      const int i = idx / E, e = idx - i * E;
+    const int i_hi = min(m, k_hi);
+    for (int idx = threadIdx.x; idx < (i_hi - k_lo) * E; idx += blockDim.x) {
+      const int il_ = idx / E, e = idx - il_ * E, i = k_lo + il_;
       double xs[D];
 #pragma unroll
       for (int a = 0; a < D; ++a) xs[a] = sx[e * D + a];
       const int pt = st.obs_pt[i], ta = st.obs_task[i];
-      if (real_point_full<T>(st, i, pt, ta, m)) {
+      if (one_pass && real_point_full<T>(st, i, pt, ta, m)) {  // (a point's rows may straddle a slab boundary: row by row there)
         // all T tasks of the point are observed (rows i - ta .. i - ta + T - 1): ONE exp for its T x T block, by the
         // thread of its task-0 row
         if (ta != 0) continue;
@@ -681,16 +687,18 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
       } else {
         double out[T];
         kernel_row<D, T>(st.Xr + (size_t)pt * D, ta, xs, il, os, out);
-        const int rot = sr_rot<NC>(i);
+        const int rot = sr_rot<NC>(il_);
 #pragma unroll
-        for (int tb = 0; tb < T; ++tb) sK[i * NC + (e * T + tb + rot) % NC] = out[tb];
+        for (int tb = 0; tb < T; ++tb) sK[il_ * NC + (e * T + tb + rot) % NC] = out[tb];
       }
     }
     __syncthreads();
 
-    for (int pi = warp; pi < Pm; pi += nw) {
-      const int p = Pm - 1 - pi, n4 = 2 * p + 2;  // k-steps of 4 columns in this panel
-      const double* ap = gL + subpanel_off(p, 0) + sp_idx(tig, gid);
+    const int p_first = k_lo >> 3;  // panels above the slab have no columns in it (lower triangular)
+    for (int pi = warp; pi < Pm - p_first; pi += nw) {
+      const int p = Pm - 1 - pi;
+      const int n4 = (min(k_hi, 8 * p + 8) - k_lo) >> 2;  // k-steps of 4 columns of this panel inside the slab
+      const double* ap = gL + subpanel_off(p, 0) + sp_idx(tig, gid) + (size_t)(k_lo >> 2) * 32;
       double acc[NB][4];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.0;
@@ -723,8 +731,11 @@ k_shared_rows(DevState st, const double* __restrict__ x) {
         for (int hh = 0; hh < 2; ++hh) {
           const int col = nb * 8 + 2 * tig + hh;
           const int e = col / T, tb = col - e * T;
-          if (e < e_live)
-            st.Wo[(((size_t)(s0 + e) * st.g_ny + j_out) * mo + row) * T + tb] = acc[nb][hh] + acc[nb][2 + hh];
+          if (e < e_live) {
+            double* wo = st.Wo + (((size_t)(s0 + e) * st.g_ny + j_out) * mo + row) * T + tb;
+            const double v = acc[nb][hh] + acc[nb][2 + hh];
+            *wo = k_lo > 0 ? *wo + v : v;
+          }
         }
     }
   }
@@ -1049,5 +1060,130 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
       for (int jc = 0; jc < i; ++jc) gblk[sp_idx(i, jc)] = blk[i][jc];     // transposed inverse row
     }
     r0 = r1;
+  }
+}
+
+// K1b: the fused step for training sets too large for the per-warp w array of k_step (m in the thousands and up; the shared
+// rows w_o = inv(L_oo) k_o of every element come from the batched GEMM k_shared_rows, st.Wo).  One CTA per batch element, w_o
+// stays in global memory (L2), only the own rows' part of w lives in shared memory; plain FP64 FMAs: for such m the step is the
+// GEMM (T m^2 flops per element) and this kernel only streams the element's c x (m + c) own rows once (memory bound).
+//   A  kernel entries of the hallucinated points                              -> wh [c8][T] (shared)
+//   C  own rows, sub-panel by sub-panel: dot = L[rows][cols < n_off] w (k-blocks over the warps, lane = one (row, column mod 4)
+//      of a k-block, 256-byte coalesced loads), rhs = k - dot, 8 x 8 block by substitution
+//   D  W^T [W | beta] over the m shared rows (global) and the c own rows       -> st.fin (k_step's layout; k_step_finish follows)
+//   F  (first half) the new rows' entries left of their diagonal block = w
+#define BIG_THREADS 256
+__global__ void __launch_bounds__(BIG_THREADS) k_step_big(DevState st, const double* __restrict__ x, int grow_factor) {
+  extern __shared__ __align__(16) double bsm[];
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int j = b % st.g_ny, d = st.d, T = st.T, m = st.m, mo = st.mo, c = st.c, np = st.np;
+  const int P8 = (c + 7) >> 3, c8 = 8 * P8;
+  const int FS = T + T * (T + 1) / 2;
+  double* wh = bsm;                          // [c8][T]   k, then w of the own rows
+  double* red = wh + (size_t)max(c8, 1) * T; // [nw][8][T] partial dots of a sub-panel / [nw][FS] partial moments
+  const double* wo = st.Wo + (size_t)b * mo * T;
+  const double* xb = x + (size_t)b * d;
+  const double* ls = st.ls + j * d;
+  const double os = st.os[j];
+  double* Le = st.Lh + (size_t)b * st.elem_stride;
+
+  for (int idx = tid; idx < c8 * T; idx += nt) wh[idx] = 0.0;
+  __syncthreads();
+  for (int idx = tid; idx < np * T * T; idx += nt) {
+    const int p = idx / (T * T), ta = (idx / T) % T, tb = idx % T;
+    const int r0 = st.hrow0[p];
+    if (r0 < 0) continue;
+    wh[(r0 + ta) * T + tb] = cov_scalar(st.Xh + ((size_t)b * st.cap_points + p) * d, ta, xb, tb, ls, os, d);
+  }
+  __syncthreads();
+
+  // lane <-> element of a k-block: [row half][column 0..3][row 0..3 of the half]  (sp_idx)
+  const int l_half = lane >> 4, l_col = (lane >> 2) & 3, l_row = (lane & 3) + 4 * l_half;
+  for (int p8 = 0; p8 < P8; ++p8) {
+    const int n_off = mo + 8 * p8, nkb = n_off >> 2;
+    const double* sp = Le + subpanel_off(p8, mo);
+    double acc[GPMPC_MAX_T];
+#pragma unroll
+    for (int t = 0; t < GPMPC_MAX_T; ++t) acc[t] = 0.0;
+    for (int kb = warp; kb < nkb; kb += nw) {
+      const double lv = __ldcg(sp + (size_t)kb * 32 + lane);
+      const int col = 4 * kb + l_col;
+      const double* wr = col < mo ? wo + (size_t)col * T : wh + (size_t)(col - mo) * T;
+#pragma unroll
+      for (int t = 0; t < GPMPC_MAX_T; ++t)
+        if (t < T) acc[t] = fma(lv, wr[t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < GPMPC_MAX_T; ++t) {
+      if (t < T) {
+        double v = acc[t];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        if (l_col == 0) red[((size_t)warp * 8 + l_row) * T + t] = v;
+      }
+    }
+    __syncthreads();
+    if (tid < T) {
+      // rhs = k - dot, then the 8 x 8 diagonal block by substitution (lower part: L, diagonal slot: 1 / L_kk); one thread per
+      // right-hand side
+      const int t = tid, nvalid = min(8, c - 8 * p8);
+      const double* blk = sp + (size_t)n_off * 8;
+      double w8[8];
+      for (int i = 0; i < 8; ++i) {
+        double dot = 0.0;
+        for (int w = 0; w < nw; ++w) dot += red[((size_t)w * 8 + i) * T + t];
+        double v = wh[(8 * p8 + i) * T + t] - dot;
+        for (int k = 0; k < i; ++k) v = fma(-__ldcg(blk + sp_idx(k, i)), w8[k], v);
+        w8[i] = i < nvalid ? v * __ldcg(blk + sp_idx(i, i)) : 0.0;
+      }
+      for (int i = 0; i < 8; ++i) wh[(8 * p8 + i) * T + t] = w8[i];
+    }
+    __syncthreads();
+  }
+
+  // ---- D: moments ----
+  {
+    double mom[GPMPC_MAX_T + GPMPC_MAX_T * (GPMPC_MAX_T + 1) / 2];
+#pragma unroll
+    for (int q = 0; q < GPMPC_MAX_T + GPMPC_MAX_T * (GPMPC_MAX_T + 1) / 2; ++q) mom[q] = 0.0;
+    const double* beta_o = st.beta_o + (size_t)j * m;
+    const double* beta_h = st.beta_h + (size_t)b * st.c_cap;
+    for (int row = tid; row < m + c; row += nt) {
+      const double* wr = row < m ? wo + (size_t)row * T : wh + (size_t)(row - m) * T;
+      const double be = row < m ? beta_o[row] : beta_h[row - m];
+      double wv_[GPMPC_MAX_T];
+#pragma unroll
+      for (int t = 0; t < GPMPC_MAX_T; ++t) wv_[t] = t < T ? wr[t] : 0.0;
+#pragma unroll
+      for (int r = 0; r < GPMPC_MAX_T; ++r) {
+        if (r < T) {
+          mom[r] = fma(wv_[r], be, mom[r]);
+#pragma unroll
+          for (int s2 = 0; s2 <= r; ++s2) mom[GPMPC_MAX_T + r * (r + 1) / 2 + s2] = fma(wv_[r], wv_[s2], mom[GPMPC_MAX_T + r * (r + 1) / 2 + s2]);
+        }
+      }
+    }
+    // block reduction of the FS moments
+    for (int r = 0; r < T; ++r) {
+      double v = warp_sum(mom[r]);
+      if (lane == 0) red[(size_t)warp * FS + r] = v;
+      for (int s2 = 0; s2 <= r; ++s2) {
+        double u = warp_sum(mom[GPMPC_MAX_T + r * (r + 1) / 2 + s2]);
+        if (lane == 0) red[(size_t)warp * FS + T + r * (r + 1) / 2 + s2] = u;
+      }
+    }
+    __syncthreads();
+    if (tid < FS) {
+      double v = 0.0;
+      for (int w = 0; w < nw; ++w) v += red[(size_t)w * FS + tid];
+      st.fin[(size_t)b * FS + tid] = v;
+    }
+  }
+  if (!grow_factor) return;
+  // ---- F (first half): L[c + r][t] = w[t][r] for the shared columns and the own columns left of the new block ----
+  for (int t = tid; t < m + c; t += nt) {
+    const double* wr = t < m ? wo + (size_t)t * T : wh + (size_t)(t - m) * T;
+    const int tt = t < m ? t : mo + (t - m);
+    for (int r = 0; r < T; ++r) Le[subpanel_off((c + r) >> 3, mo) + sp_idx(tt, (c + r) & 7)] = wr[r];
   }
 }

@@ -122,10 +122,9 @@ def main():
         est_flop = ns * a.g_ny * steps * (d + 1) * (m * m + m * steps * (d + 1) + (steps * (d + 1)) ** 2 / 3.0)
         if m > 4000 and not a.large_m:
             skipped.append({"ns": ns, "steps": steps, "m": m, "d": d,
-                            "why": "m = 1e4: served by the general block kernels only (gpmpc_step falls back to posterior + append, "
-                                   "inv(L_oo) re-streamed per element): run separately with --large-m (DESIGN.md 7)"})
+                            "why": "m = 1e4 (shared rows by the k-slab GEMM, own rows by k_step_big): run separately with --large-m"})
             continue
-        if a.large_m and (m <= 4000 or ns * a.g_ny * steps > 40000):
+        if a.large_m and (m <= 4000 or ns * a.g_ny * steps > 400000):
             continue
         if a.only_oversize and need <= HBM_BUDGET:
             continue
