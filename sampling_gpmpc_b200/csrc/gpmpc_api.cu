@@ -56,6 +56,11 @@ struct gpmpc_handle {
   long long cache_version = -1;  // factor_version the posterior cache was built against
   int cache_H = 0;
   int ws_n = 0, ws_q = 0, ws_H = 0;  // workspace capacity
+  // Sigma* / mean w.r.t. the REAL data only, produced by the same pass as the full ones when the caller is about to reset the
+  // hallucinated set (gpmpc_linearise with reset_first): the append after the reset then needs no second posterior pass
+  double *S2buf = nullptr, *mu2buf = nullptr;
+  bool want_real_only = false, real_cache_valid = false;
+  int real_cache_H = 0;
   long long launches = 0;
   double last_bytes = 0.0, last_flops = 0.0;
   // rollout scratch
@@ -221,12 +226,17 @@ static int ensure_workspace(gpmpc_handle* h, int H) {
   // re-allocates (cudaFree / cudaMalloc synchronise the device: 10-20 ms spikes otherwise)
   const int new_n = std::max(std::max(n + n / 2, st.m + st.c_cap), h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E);
+  cudaFree(h->S2buf); cudaFree(h->mu2buf);
   st.W = st.S = st.C = st.mu = st.xc = st.E = nullptr;
+  h->S2buf = h->mu2buf = nullptr;
+  h->real_cache_valid = false;
   const size_t B = (size_t)st.B;
   CUDA_TRY(h, dev_alloc(&st.W, B * new_n * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&st.S, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&st.C, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&st.mu, B * (size_t)new_q));
+  CUDA_TRY(h, dev_alloc(&h->S2buf, B * (size_t)new_q * new_q));
+  CUDA_TRY(h, dev_alloc(&h->mu2buf, B * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&st.xc, B * (size_t)new_H * st.d));
   // iteration matrix of the eigen-root fallback, only where it does not fit in shared memory
   const bool e_global = (size_t)new_q * new_q * 8 > (size_t)(h->max_dyn_smem - EIG_STATIC_SMEM);
@@ -384,6 +394,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin); cudaFree(st.Wo);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.eig_flag);
+  cudaFree(h->S2buf); cudaFree(h->mu2buf);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
   cudaFree(h->grp_flags); cudaFree(h->grp_decision);
@@ -448,6 +459,7 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     for (int i = 0; i < m; ++i) yobs[(size_t)j * m + i] = hy[((size_t)j * n + pt[i]) * T + task[i]];
 
   h->have_real = false;  // until every allocation and the factorisation below have succeeded
+  h->real_cache_valid = false;
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
@@ -598,6 +610,11 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   gpmpc_sample_opts o = opts ? *opts : gpmpc_sample_opts{-1.0, -1.0, 0, 0};
+  const bool with_real = h->want_real_only && h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q && st.c > 0;
+  h->want_real_only = false;
+  h->real_cache_valid = with_real;  // any other model call overwrites W: the real-only cache goes with it
+  h->real_cache_H = H;
+  if (with_real) { st.S2 = h->S2buf; st.mu2 = h->mu2buf; }
   if (h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q) {
     rc = dispatch_posterior_mma(h, st, x, H, mean, var, eps, o, y, jitter_level, (cudaStream_t)stream);
     if (rc) return rc;
@@ -685,6 +702,14 @@ int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
+  if (grow && !reuse && hst.c == 0 && h->real_cache_valid && h->real_cache_H == H) {
+    // the hallucinated set was reset after the model call: W's real rows, Sigma* and the mean w.r.t. the real data alone
+    // came out of that same pass (k_pm_gram's second accumulators); k_append checks on the device that x is the same
+    st.S = h->S2buf;
+    st.mu = h->mu2buf;
+    reuse = 1;
+  }
+  h->real_cache_valid = false;
   if (grow && !reuse && h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q) {
     // the factor changed since the last model call (e.g. the reset of agent.py:261-272 between the model call and the
     // conditioning): W, Sigma*, mean for these points against the CURRENT factor, on the tensor-core kernels
@@ -1114,6 +1139,7 @@ int gpmpc_linearise(gpmpc_handle* h, const gpmpc_env* env, const double* xu, int
     k_gather_gp_inputs<<<blocks, threads, 0, stream>>>(*env, st.ns, H, xu_dev, h->lin_xg);
     h->launches++;
   }
+  h->want_real_only = reset_first != 0;
   rc = gpmpc_posterior(h, h->lin_xg, H, mean, var, eps, opts, y, jitter_level, stream_);
   if (rc) return rc;
   if (reset_first) {

@@ -286,12 +286,20 @@ k_pm_gram(DevState st, const double* __restrict__ x, int H) {
       const int col = (tile - n_tiles) * 8 + gid;
       const double* beta_o = st.beta_o + (size_t)j * m;
       const double* beta_h = st.beta_h + (size_t)b * st.c_cap;
-      double a = 0.0;
+      double a = 0.0, a_real = 0.0;
       if (col < q)
-        for (int r = tig; r < n; r += 4) a = fma(__ldcg(W + (size_t)r * q + col), r < m ? beta_o[r] : beta_h[r - m], a);
+        for (int r = tig; r < n; r += 4) {
+          a = fma(__ldcg(W + (size_t)r * q + col), r < m ? beta_o[r] : beta_h[r - m], a);
+          if (r + 4 >= m && r < m) a_real = a;  // the partial sum after this lane's last real row: same order as a pass over m rows
+        }
       a += __shfl_xor_sync(0xffffffffu, a, 1);
       a += __shfl_xor_sync(0xffffffffu, a, 2);
       if (tig == 0 && col < q) mu[col] = a;
+      if (st.mu2) {
+        a_real += __shfl_xor_sync(0xffffffffu, a_real, 1);
+        a_real += __shfl_xor_sync(0xffffffffu, a_real, 2);
+        if (tig == 0 && col < q) st.mu2[(size_t)b * q + col] = a_real;
+      }
       continue;
     }
     int rb = 0;
@@ -300,6 +308,8 @@ k_pm_gram(DevState st, const double* __restrict__ x, int H) {
     const int ca = rb * 8 + gid, cbb = sb * 8 + gid;
     const bool oka = ca < q, okb = cbb < q;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    double acr[4] = {0.0, 0.0, 0.0, 0.0};  // the same sums over the REAL rows only (st.S2): rows >= m enter as zeros
+    const bool want_real = st.S2 != nullptr;
     for (int k = 0; k < n4; k += 8) {
       double av[8], bv[8];
 #pragma unroll
@@ -310,6 +320,13 @@ k_pm_gram(DevState st, const double* __restrict__ x, int H) {
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) dmma(acc[2 * (u & 1)], acc[2 * (u & 1) + 1], av[u], bv[u]);
+      if (want_real && 4 * k < m) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool real = 4 * (k + u) + tig < m;
+          dmma(acr[2 * (u & 1)], acr[2 * (u & 1) + 1], real ? av[u] : 0.0, real ? bv[u] : 0.0);
+        }
+      }
     }
     const int r = rb * 8 + gid;
 #pragma unroll
@@ -319,6 +336,7 @@ k_pm_gram(DevState st, const double* __restrict__ x, int H) {
         const double kss = cov_scalar(xb + (size_t)(r / T) * d, r % T, xb + (size_t)(s / T) * d, s % T,
                                       st.ls + j * d, os, d);
         S[(size_t)r * q + s] = kss - (acc[hh] + acc[2 + hh]);
+        if (want_real) st.S2[(size_t)b * q * q + (size_t)r * q + s] = kss - (acr[hh] + acr[2 + hh]);
       }
     }
   }

@@ -81,6 +81,8 @@ struct DevState {
   double* S;            // [B][q][q]  Sigma* (lower triangle valid)
   double* C;            // [B][q][q]  scratch for Cholesky
   double* mu;           // [B][q]
+  double* S2;           // [B][q][q]  Sigma* w.r.t. the REAL data only (the model of a call whose hallucinated set is about to be
+  double* mu2;          // [B][q]     reset, agent.py:261-272: k_append then needs no second posterior pass); NULL: not wanted
   double* xc;           // [B][H][d]  test points the cache was built for
   double* E;            // [B][q][q]  iteration matrix of the eigen-root fallback when it does not fit in shared memory
 };
