@@ -161,9 +161,12 @@ def _uniform_over_samples(t: torch.Tensor, what: str) -> torch.Tensor:
 class Posterior:
     """What the reference reads off `model(x)`: agent.py:640-706, simulate_true_reachable_set.py:208-236."""
 
-    def __init__(self, model: "ExactGP", backend: _Backend, x: torch.Tensor, mean, var, token: int):
+    def __init__(self, model: "ExactGP", backend: _Backend, x: torch.Tensor, mean, var, token: int, out_device=None):
         self._model, self._be, self._x, self._token = model, backend, x, token
-        self.mean, self._var = mean, var
+        # results live where the caller's test inputs live (GPyTorch computes on the inputs' device): with
+        # common.use_cuda False the reference's own post-processing (agent.py:646-708) then keeps working on CPU tensors
+        self._out = out_device if out_device is not None else mean.device
+        self.mean, self._var = mean.to(self._out), var.to(self._out)
         self.jitter_level: Optional[torch.Tensor] = None
 
     @property
@@ -190,15 +193,15 @@ class Posterior:
             be.post_token += 1
             self._token = be.post_token
         if base_samples is None:  # GPyTorch draws randn(*batch, q, 1); a 1x1 covariance uses the unclamped sqrt (A.6)
-            eps = torch.randn(ns, g_ny, H * T, 1, dtype=F64, device=self.mean.device).reshape(ns, g_ny, H, T)
+            eps = torch.randn(ns, g_ny, H * T, 1, dtype=F64, device=self._out).reshape(ns, g_ny, H, T)
             opts = eng.opts(unclamped_sqrt_1x1=True)
         else:
-            eps = base_samples.to(self.mean.device, F64).reshape(ns, g_ny, H, T)
+            eps = base_samples.to(eng.device, F64).reshape(ns, g_ny, H, T)
             opts = eng.opts()
         y, jl = eng.sample(eps, H, opts)
-        self.jitter_level = jl
-        eng.raise_on_status()  # NotPSDError after 3 jitter escalations, like psd_safe_cholesky
-        return y
+        self.jitter_level = jl.to(self._out)
+        eng.raise_on_status()  # NanError / NotPSDError where GPyTorch raises, a warning where it falls back to the eigen root
+        return y.to(self._out)
 
 
 class ExactGP(_Module):
@@ -331,10 +334,11 @@ class ExactGP(_Module):
 
     def __call__(self, x: torch.Tensor) -> Posterior:
         be = self._sync()
+        out_device = x.device
         x = x.to(be.eng.device, F64)
         mean, var = be.eng.posterior(x)
         be.post_token += 1
-        return Posterior(self, be, x, mean, var, be.post_token)
+        return Posterior(self, be, x, mean, var, be.post_token, out_device)
 
 
 # ---- gpytorch.settings -------------------------------------------------------------------------------------------

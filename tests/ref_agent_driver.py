@@ -72,24 +72,29 @@ def main():
 
     z = np.load(os.path.join(HERE, "golden", case + ".npz"))
     params = yaml.safe_load(str(z["params_yaml"]))
-    params["common"]["use_cuda"] = True  # the yamls of the closed-loop configs say so too (params_pendulum1D_samples.yaml:80)
+    # the yamls of the closed-loop configs say use_cuda True (params_pendulum1D_samples.yaml:80); --cpu-tensors keeps the
+    # reference's tensors on the CPU (use_cuda False, e.g. params_car_residual.yaml): the shim then computes on the GPU and
+    # hands CPU tensors back, so the reference's own post-processing keeps working
+    on_gpu = "--cpu-tensors" not in sys.argv
+    params["common"]["use_cuda"] = on_gpu
+    dev = "cuda" if on_gpu else "cpu"
     n_calls = len([k for k in z.files if k.startswith("gp_val_")])
     fs = params["env"]["use_model_without_derivatives"]
     n_sqp = 1 if fs else params["optimizer"]["SEMPC"]["max_sqp_iter"]
     torch.manual_seed(params["experiment"]["rnd_seed"]["value"])
     with contextlib.redirect_stdout(io.StringIO()):
         agent = Agent(params, envs[params["env"]["dynamics"]](params))
-    assert agent.use_cuda and agent.Dyn_gp_X_train_batch.is_cuda
+    assert agent.use_cuda == on_gpu and agent.Dyn_gp_X_train_batch.is_cuda == on_gpu
     # real data as recorded (the env classes regenerate it to the last ulp or two; 1e-16 input differences are amplified
     # ~1e5 x by the solve) and the fixture's base samples: the reference draws them from the generator of the device it
     # runs on (agent.py:84-93), the fixture holds the CPU stream -- loading them is what
     # simulate_forward_sampling_car.py:78-80 does with its pickled epistemic vectors
     dX = float((agent.Dyn_gp_X_train.cpu() - torch.tensor(z["X_real"], device="cpu")).abs().max())
-    agent.Dyn_gp_X_train = torch.tensor(z["X_real"], device="cuda")
-    agent.Dyn_gp_Y_train = torch.tensor(z["Y_real"], device="cuda")
+    agent.Dyn_gp_X_train = torch.tensor(z["X_real"], device=dev)
+    agent.Dyn_gp_Y_train = torch.tensor(z["Y_real"], device=dev)
     agent.real_data_batch()
     eps_own_shape = tuple(agent.epistimic_random_vector.shape)
-    agent.epistimic_random_vector = torch.tensor(z["eps"], device="cuda")
+    agent.epistimic_random_vector = torch.tensor(z["eps"], device=dev)
 
     os_ = np.asarray(params["agent"]["Dyn_gp_outputscale"]["both"], dtype=np.float64).reshape(-1)
     s_val = float(np.sqrt(os_.max()))
@@ -139,7 +144,7 @@ def main():
     out = {"case": case, "reference": ref, "calls": n_calls, "worst_over_tolerance": worst, "jitter_levels_equal": jitter_ok,
            "hallucinated_counts_equal": n_h_ok, "hallucinated_inputs_bit_equal": halluc_ok, "real_X_regenerated_max_abs_diff": dX,
            "eps_shape_generated_by_reference": list(eps_own_shape), "model_class": type(agent.model_i).__mro__[1].__module__,
-           "native_library": _engine.LIB_PATH, "device": torch.cuda.get_device_name(0)}
+           "native_library": _engine.LIB_PATH, "device": torch.cuda.get_device_name(0), "reference_tensors_on": dev}
     if reps:
         first = list(times)
         times.clear()

@@ -24,15 +24,15 @@ def _reference_present():
 
 
 @pytest.mark.skipif(not _reference_present(), reason="no reference checkout (run __graft_entry__.build() where /root/reference is mounted)")
-@pytest.mark.parametrize("case", CASES)
-def test_unmodified_reference_agent_on_the_gpu_matches_its_own_fixtures(case):
-    r = subprocess.run([sys.executable, DRIVER, case], capture_output=True, text=True, timeout=900)
+@pytest.mark.parametrize("case,extra", [(c, []) for c in CASES] + [("pendulum1D_sqp", ["--cpu-tensors"]), ("car_residual_fs", ["--cpu-tensors"])])
+def test_unmodified_reference_agent_on_the_gpu_matches_its_own_fixtures(case, extra):
+    r = subprocess.run([sys.executable, DRIVER, case, *extra], capture_output=True, text=True, timeout=900)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert line, r.stdout[-2000:] + r.stderr[-4000:]
     out = json.loads(line[-1])
     out_dir = os.path.join(REPO, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
-    with open(os.path.join(out_dir, f"reference_agent_{case}.json"), "w") as f:
+    with open(os.path.join(out_dir, f"reference_agent_{case}{'_cpu_tensors' if extra else ''}.json"), "w") as f:
         json.dump(out, f, indent=1)
     assert "unavailable" not in out, out
     assert out["model_class"].startswith("src.GP_model"), out["model_class"]  # the reference's own model class on the shim
