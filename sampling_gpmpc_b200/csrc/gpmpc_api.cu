@@ -1444,13 +1444,15 @@ int gpmpc_stage_hulls(gpmpc_handle* h, const double* traj, int32_t ns, int32_t n
       cap = ns;
       continue;
     }
-    std::vector<int> hcand((size_t)H1 * cap);
-    std::vector<double> hxy((size_t)H1 * cap * 2);
-    // one strided copy of the used prefixes would need per-stage lengths; the lists are small, copy whole rows up to worst
+    // host staging sized by the longest list actually produced (the capacity is ~ns / 8 per stage: 100+ MB of vectors per call
+    // at 10^6 samples when sized by it)
+    const size_t wl = (size_t)std::max(worst, 1);
+    std::vector<int> hcand((size_t)H1 * wl);
+    std::vector<double> hxy((size_t)H1 * wl * 2);
     if (worst > 0) {
-      CUDA_TRY(h, cudaMemcpy2DAsync(hcand.data(), (size_t)cap * 4, cand, (size_t)cap * 4, (size_t)worst * 4, H1,
+      CUDA_TRY(h, cudaMemcpy2DAsync(hcand.data(), wl * 4, cand, (size_t)cap * 4, (size_t)worst * 4, H1,
                                     cudaMemcpyDeviceToHost, stream));
-      CUDA_TRY(h, cudaMemcpy2DAsync(hxy.data(), (size_t)cap * 16, cxy, (size_t)cap * 16, (size_t)worst * 16, H1,
+      CUDA_TRY(h, cudaMemcpy2DAsync(hxy.data(), wl * 16, cxy, (size_t)cap * 16, (size_t)worst * 16, H1,
                                     cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(h, cudaStreamSynchronize(stream));
     }
@@ -1458,7 +1460,7 @@ int gpmpc_stage_hulls(gpmpc_handle* h, const double* traj, int32_t ns, int32_t n
       std::vector<HullPt> p;
       p.reserve((size_t)hc[t] + HULL_DIRS);
       for (int k = 0; k < hc[t]; ++k)
-        p.push_back(HullPt{hxy[((size_t)t * cap + k) * 2], hxy[((size_t)t * cap + k) * 2 + 1], hcand[(size_t)t * cap + k]});
+        p.push_back(HullPt{hxy[((size_t)t * wl + k) * 2], hxy[((size_t)t * wl + k) * 2 + 1], hcand[(size_t)t * wl + k]});
       for (int k = 0; k < HULL_DIRS; ++k)
         p.push_back(HullPt{hpoly[((size_t)t * HULL_DIRS + k) * 2], hpoly[((size_t)t * HULL_DIRS + k) * 2 + 1],
                            hext[(size_t)t * HULL_DIRS + k]});
