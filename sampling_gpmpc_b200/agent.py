@@ -457,6 +457,31 @@ class Agent:
         return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]
 
 
+    def linearise_p_lin(self, x_h, u_h, sqp_iter, tail, use_feedback_K: bool = False, u_per_sample: bool = False) -> np.ndarray:
+        """solver.py:84-131 between `ocp_solver.get` and `ocp_solver.set(stage, "p", p_lin)` as ONE device pass and ONE
+        device->host copy: the linearisation of every sampled dynamics at the iterate (dyn_fg_jacobians) packed straight into
+        the acados stage parameters.  x_h (H, ns*nx), u_h (H, nu) [or (H, ns*nu) with u_per_sample], tail (H, n_tail) =
+        hstack(u_h, xg, w, tilde_eps) per stage.  Returns (H, P); row `stage` is that stage's p_lin."""
+        xu = self.get_batch_x_hat_u_diff(x_h, u_h) if u_per_sample else self.get_batch_x_hat(x_h, u_h)
+        if self._fused_linearisation_applies(xu):
+            ag = self.params["agent"]
+            opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
+            if not hasattr(self, "_lin_bufs"):
+                self._lin_bufs = {}
+            mean, var, y_gp, jl, lin, _ = self.engine.linearise(
+                self.env_struct, xu, self.epistimic_random_vector[self.mpc_iter][sqp_iter], opts, self._pending_reset,
+                self._lin_bufs, copy_to_host=False)
+            self._pending_reset = False
+            self.model_i_call = _PosteriorView(mean, var, jl)
+            self.model_i_samples = y_gp
+            self._data_version += 1
+            self._appended_since_train = True
+        else:
+            lin = self.dyn_fg_jacobians_device(xu, sqp_iter)
+        out = self.pack_p_lin(lin, x_h, tail, use_feedback_K)
+        self.engine.raise_on_status()
+        return out
+
     # ---- f1: the acados stage parameters (solver.py:98-131) -------------------------------------
     def pack_p_lin(self, lin: torch.Tensor, x_h, tail, use_feedback_K: bool = False) -> np.ndarray:
         """lin = dyn_fg_jacobians_device(...) (ns,nx,H,1+nx+nu); x_h (H, ns*nx) the SQP iterate; tail (H, n_tail) =

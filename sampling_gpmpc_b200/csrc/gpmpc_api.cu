@@ -540,10 +540,7 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
 
 int gpmpc_reset_hallucinated(gpmpc_handle* h) {
   if (!h) return GPMPC_ERR_ARG;
-  if (h->st.pstate && h->st.np > 0) {
-    ON_HANDLE_DEVICE(h);
-    cudaMemset(h->st.pstate, 0, (size_t)h->st.B * std::max(h->st.cap_points, 1));
-  }
+  // (st.pstate needs no clearing: the state of point p is written by the step that records it, entries at p >= np are never read)
   h->st.c = 0;
   h->st.np = 0;
   h->has_partial = false;

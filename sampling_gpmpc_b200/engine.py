@@ -483,7 +483,8 @@ class GPEngine:
         """SQP-mode model call on the tensor cores (default) or by the scalar substitution kernel (reference semantics)."""
         self._check(self.lib.gpmpc_set_block_kernels(self.h, int(mma)), "gpmpc_set_block_kernels")
 
-    def linearise(self, env: GpmpcEnv, xu: torch.Tensor, eps: torch.Tensor, opts: GpmpcSampleOpts, reset_first: bool, bufs: dict):
+    def linearise(self, env: GpmpcEnv, xu: torch.Tensor, eps: torch.Tensor, opts: GpmpcSampleOpts, reset_first: bool, bufs: dict,
+                  copy_to_host: bool = True):
         """One SQP GP linearisation in one C call (gpmpc_linearise).  xu (ns,nx,H,nx+nu): pinned CPU tensor or CUDA tensor;
         eps CUDA (ns,g_ny,H,T).  `bufs` caches the output tensors between calls.  Returns (mean, var, y, jl, out, out_host);
         nothing has been waited for."""
@@ -503,7 +504,8 @@ class GPEngine:
         b = bufs
         rc = self.lib.gpmpc_linearise(self.h, C.byref(env), C.c_void_p(xu.data_ptr()), int(on_host), H, _ptr(eps), C.byref(opts),
                                       int(reset_first), _ptr(b["mean"]), _ptr(b["var"]), _ptr(b["y"]), _ptr(b["jl"]),
-                                      _ptr(b["out"]), C.c_void_p(b["out_host"].data_ptr()), _stream(self.device))
+                                      _ptr(b["out"]), C.c_void_p(b["out_host"].data_ptr()) if copy_to_host else None,
+                                      _stream(self.device))
         self._check(rc, "gpmpc_linearise")
         return b["mean"], b["var"], b["y"], b["jl"], b["out"], b["out_host"]
 

@@ -542,3 +542,28 @@ def test_product_agent_generates_the_reference_base_samples():
     os_ = outputscales(params)
     for k, (gp_val, y_grad, u_grad) in enumerate(outs):
         assert scaled_close(gp_val, z[f"gp_val_{k}"], float(np.sqrt(os_.max())) * 4.0, RTOL) <= 1.0
+
+
+def test_linearise_p_lin_equals_dyn_fg_jacobians_plus_the_reference_concat_loop():
+    """Agent.linearise_p_lin (gpmpc_linearise + gpmpc_pack_plin, one device->host copy) against the reference's own sequence:
+    dyn_fg_jacobians -> three arrays -> the per-stage / per-sample np.concatenate of src/solver.py:98-131 (restated in
+    oracle/consumers_ref.py).  Same kernels underneath: bit-exact."""
+    from oracle import consumers_ref as cref
+    z, params = load_case("pendulum1D_sqp")
+    a, b = _make_agent(params, z), _make_agent(params, z)
+    ns, nx, nu, H = params["agent"]["num_dyn_samples"], 2, 1, params["optimizer"]["H"]
+    rng = np.random.default_rng(5)
+    for k in range(n_calls(z)):
+        x_h, u_h = z[f"x_h_{k}"], z[f"u_h_{k}"]
+        xg = rng.standard_normal((H, nx))
+        w = rng.standard_normal((H, 1))
+        te = [np.array([0.01 * t]) for t in range(H)]
+        tail = np.hstack([u_h, xg, w, np.stack(te)])
+        for ag in (a, b):
+            ag.mpc_iteration(k)
+            ag.train_hallucinated_dynGP(0)
+        got = a.linearise_p_lin(x_h, u_h, 0, tail)
+        gp_val, y_grad, u_grad = b.dyn_fg_jacobians(b.get_batch_x_hat(x_h, u_h), 0)
+        want = np.stack(cref.pack_p_lin(gp_val, y_grad, u_grad, x_h, u_h, xg, w, te, ns, nx, None))
+        assert got.shape == want.shape and np.array_equal(got, want), k
+    assert a.engine.status() & ~0x301 == 0
