@@ -104,3 +104,32 @@ def test_save_X_traj_matches_the_reference_pickle_format(tmp_path):
     assert [os.path.basename(q) for q in paths] == ["data_X_traj_0.pkl", "data_X_traj_1.pkl", "data_X_traj_2.pkl"]
     parts = [pickle.load(open(q, "rb")) for q in paths]
     assert np.array_equal(np.vstack(parts), traj.numpy())  # the consumer's np.vstack over the job files
+
+
+def test_reachable_set_ball_matches_the_reference_function():
+    """sampling_gpmpc_b200.agent.reachable_set_ball restates src/utils/reachable_set.py:3-39 (host scalar math that
+    prepare_dynamics_set reads its acceptance radii from); compared with the reference's own function where the checkout is
+    mounted (CPU container; skipped on the GPU box)."""
+    import contextlib
+    import importlib.util
+    import io
+    import os
+    import pytest
+    ref_root = os.environ.get("GPMPC_REFERENCE", "/root/reference")
+    path = os.path.join(ref_root, "src", "utils", "reachable_set.py")
+    if not os.path.isfile(path):
+        pytest.skip("reference checkout not mounted")
+    spec = importlib.util.spec_from_file_location("ref_reachable_set", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pytest.importorskip("torch")  # agent.py imports torch at module level
+    from sampling_gpmpc_b200.agent import reachable_set_ball
+    params = {"optimizer": {"H": 17, "terminal_tightening": {"P": [[10.47241433, 0.2680862], [0.2680862, 8.74083638]],
+                                                              "K": [[-18.82703934, -7.32095004]]}},
+              "agent": {"tight": {"Lipschitz": 0.96, "dyn_eps": 0.002, "w_bound": 0.0001}}}
+    V = np.linspace(1.0, 0.5, 18)
+    with contextlib.redirect_stdout(io.StringIO()):
+        want_eps, want_ci = mod.get_reachable_set_ball(params, V)
+    got_eps, got_ci = reachable_set_ball(params, V)
+    assert np.array_equal(np.asarray(got_ci), np.asarray(want_ci))
+    assert len(got_eps) == len(want_eps) and all(np.array_equal(a, b) for a, b in zip(got_eps, want_eps))
