@@ -330,7 +330,7 @@ static int dispatch_posterior_mma(gpmpc_handle* h, const DevState& st, const dou
 
 extern "C" {
 
-const char* gpmpc_version(void) { return "gpmpc_b200 0.2 (sm_100a)"; }
+const char* gpmpc_version(void) { return "gpmpc_b200 0.3 (sm_100a)"; }
 
 int64_t gpmpc_base_samples(uint8_t* rng_state, int64_t state_bytes, int64_t slots, int64_t n, double beta, double* out) {
   if (!rng_state || !out || state_bytes != (int64_t)gpmpc_rng::STATE_BYTES || slots < 0 || n < 1 || !(beta > 0.0))

@@ -13,10 +13,15 @@
 // t < off + 8p + 8 (64 bytes per column, "column group"); sub-panels follow one another in row order, so an
 // element's factor is ONE contiguous stream that the fused step kernel pulls through shared memory with TMA bulk
 // copies in consumption order.  Inside a sub-panel the columns are taken four at a time ("k-block", 256 bytes = the
-// A operand of one mma.m8n8k4) and a k-block is stored as [row half h][column 0..3][row 0..3 of the half]
-// (sp_idx): the 16 lanes of a half-warp then read one contiguous 128-byte run when they load the A fragment
-// (lane = 4*row + column), i.e. conflict-free; the plain [column][8 rows] order put a half-warp on banks 0-7 and
-// 16-23 only (2-way conflict on every A load, measured: 289 conflict wavefronts per element-step at c = 30).
+// A operand of one mma.m8n8k4) and a k-block is stored ROW-major, [row 0..7][column 0..3] (sp_idx):
+//   * the A fragment of lane = 4*row + column is double number `lane` of the k-block: a warp reads one contiguous
+//     256-byte run, conflict-free (the plain [column][8 rows] order put a half-warp on banks 0-7 and 16-23 only:
+//     2-way conflict on every A load, measured 289 conflict wavefronts per element-step at c = 30);
+//   * four consecutive columns of ONE row are one aligned 32-byte DRAM sector, so appending a row writes whole
+//     sectors.  (Round 1 stored [row half][column][row of the half]: equally conflict-free, but a new row then
+//     put 8 bytes into every 32-byte sector it touched -- L2 had to fetch the other 24 from DRAM before writing
+//     the sector back: ~4x write amplification plus the fill reads on the appended rows, 15 % of the DRAM traffic
+//     of the car rollout.)
 //   off = 0 for the shared real-data factor L_oo (storage column = column);
 //   off = mo = roundup8(m) for an element's own rows: storage columns [0, m) are the shared columns, [m, mo)
 //   are zero padding (so that every column range the kernel iterates over in steps of 4 is aligned), and
@@ -33,7 +38,7 @@ __host__ __device__ __forceinline__ size_t subpanel_off(int p, int off) {
 
 // index (doubles) inside a sub-panel of the entry (storage column t, row r of the sub-panel, 0 <= r < 8)
 __host__ __device__ __forceinline__ size_t sp_idx(int t, int r) {
-  return (size_t)(t >> 2) * 32 + ((r >> 2) & 1) * 16 + (t & 3) * 4 + (r & 3);
+  return (size_t)(t >> 2) * 32 + (size_t)(r & 7) * 4 + (t & 3);
 }
 
 struct DevState {

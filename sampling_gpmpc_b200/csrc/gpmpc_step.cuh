@@ -592,11 +592,13 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
     double* rowp[T];
 #pragma unroll
     for (int r = 0; r < T; ++r) rowp[r] = Le + subpanel_off((c + r) >> 3, mo) + sp_idx(0, (c + r) & 7);
+    // (lanes = consecutive storage columns: every 4 lanes fill one 32-byte sector of the row; the padding columns are
+    // written too, as zeros, so that the sector of column m - 1 is complete)
     for (int t = lane; t < mo + c; t += 32) {
-      if (t >= m && t < mo) continue;  // padding columns stay 0
+      const bool pad = t >= m && t < mo;
       const size_t to = sp_idx(t, 0);
 #pragma unroll
-      for (int r = 0; r < T; ++r) rowp[r][to] = wv[t * T + r];
+      for (int r = 0; r < T; ++r) rowp[r][to] = pad ? 0.0 : wv[t * T + r];
     }
   }
 }
@@ -1097,8 +1099,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_step_big(DevState st, const dou
   }
   __syncthreads();
 
-  // lane <-> element of a k-block: [row half][column 0..3][row 0..3 of the half]  (sp_idx)
-  const int l_half = lane >> 4, l_col = (lane >> 2) & 3, l_row = (lane & 3) + 4 * l_half;
+  // lane <-> element of a k-block: [row 0..7][column 0..3]  (sp_idx)
+  const int l_col = lane & 3, l_row = lane >> 2;
   for (int p8 = 0; p8 < P8; ++p8) {
     const int n_off = mo + 8 * p8, nkb = n_off >> 2;
     const double* sp = Le + subpanel_off(p8, mo);
@@ -1117,8 +1119,8 @@ __global__ void __launch_bounds__(BIG_THREADS) k_step_big(DevState st, const dou
     for (int t = 0; t < GPMPC_MAX_T; ++t) {
       if (t < T) {
         double v = acc[t];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
         if (l_col == 0) red[((size_t)warp * 8 + l_row) * T + t] = v;
       }
     }

@@ -80,12 +80,33 @@ class ForwardRollout:
             eps = eps[:, self.s_lo:self.s_hi]
         self.engine.reset_hallucinated()
         out = self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
+        self._last_run = (u_ff, eps, out) if getattr(self, "_fused", False) else None
         if check:
             self.check()
         return out
 
+    def use_fused_horizon(self, on: bool = True):
+        """Opt in to the one-launch rollout kernel (csrc/gpmpc_horizon.cuh; bit-identical results, measured slower than the
+        step-wise path at the bench shape -- DESIGN.md 3 K1h)."""
+        self._fused = bool(on)
+        self.engine.set_option("rollout_fused", int(self._fused))
+
     def check(self) -> int:
-        """Synchronises and turns the device status word into the reference's error behaviour (engine.raise_on_status)."""
+        """Synchronises and turns the device status word into the reference's error behaviour (engine.raise_on_status).
+        The fused-horizon kernel cannot take GPyTorch's batch-wide eigen-root fallback in flight; when a draw of such a
+        rollout failed its jitter ladder the rollout is repeated on the step-wise path, which can."""
+        from .engine import ST_SAMPLE_NOT_PD
+        if getattr(self, "_fused", False) and getattr(self, "_last_run", None) is not None:
+            s = self.engine.status()
+            if s & ST_SAMPLE_NOT_PD:  # (a NaN flagged next to it is the failed draw's own NaN, carried into the next step)
+                self.engine.status(clear=True)
+                self.engine.set_option("rollout_fused", 0)
+                try:
+                    u_ff, eps, traj = self._last_run
+                    self.engine.reset_hallucinated()
+                    self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
+                finally:
+                    self.engine.set_option("rollout_fused", 1)
         return self.engine.raise_on_status()
 
     def run_from_host(self, u_ff: torch.Tensor, eps_host: torch.Tensor, traj: Optional[torch.Tensor] = None,

@@ -4,6 +4,7 @@ arithmetic in the same order => BIT-IDENTICAL trajectories and an identical hand
 recorded points), for ragged sample counts, both car / pendulum-like shapes, any grouping / staggering of the persistent
 grid.  The step-wise path itself is held to the oracle by tests/test_gpu_parity.py."""
 import numpy as np
+import warnings
 import pytest
 import torch
 
@@ -106,3 +107,56 @@ def test_shapes_the_fused_kernel_does_not_serve_fall_back_to_the_step_wise_path(
     fr = ForwardRollout(params, condition=True)
     traj = fr.run(u, eps)
     assert torch.isfinite(traj).all() and fr.engine.launch_count > 16
+
+
+def test_failed_ladder_in_the_fused_kernel_is_redone_step_wise_with_the_eigen_root():
+    """A draw that fails its (no-op) jitter ladder inside the one-launch kernel: check() repeats the rollout on the step-wise
+    path, whose in-stream redo takes GPyTorch's batch-wide eigen root.  Trajectories, status word and the error raised equal
+    those of a rollout that ran step-wise from the start (here: the eigen-root draw succeeds, conditioning on the noise-free
+    singular point then fails like the reference's re-fit would)."""
+    from sampling_gpmpc_b200 import configs
+    from sampling_gpmpc_b200.engine import ST_SAMPLE_EIG
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    ns, steps = 9, 6
+    params = configs.pendulum2D_rollout(num_dyn_samples=ns, steps=steps, min_data_dist=-1)
+    params["env"]["train_data_has_derivatives"] = True
+    params["agent"]["Dyn_gp_jitter"] = 0.0
+    params["agent"]["Dyn_gp_noise"] = 1e-30
+    params["agent"]["Dyn_gp_task_noises"]["multiplier"] = 1e-30
+    params["agent"]["Dyn_gp_variance_is_zero"] = -1
+    # 2 far-apart noise-free real points; the start state [0, 0] with u_0 = 0 sits exactly on the first one: the 4 x 4
+    # posterior covariance there is rounding noise around 0
+    X = torch.tensor([[0.0, 0.0, 0.0], [1.5, -1.0, 4.0]], dtype=torch.float64)
+    Y = torch.zeros(2, 2, 4, dtype=torch.float64)
+    Y[:, :, 0] = torch.tensor([[0.1, -0.2], [0.3, 0.05]])
+    g = torch.Generator().manual_seed(6)
+    eps = torch.randn(steps, ns, 2, 1, 4, generator=g, dtype=torch.float64).clamp(-2.5, 2.5)
+    u = torch.zeros(steps, 1, dtype=torch.float64)
+    u[1:, 0] = torch.linspace(0.5, 2.0, steps - 1)
+
+    def outcome(fr):
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            try:
+                return ("status", fr.check()), [str(x.message)[:40] for x in w]
+            except Exception as e:  # noqa: BLE001  (the TYPE of the error is what is compared)
+                return ("raised", type(e).__name__), [str(x.message)[:40] for x in w]
+
+    ref = ForwardRollout(params, condition=True, X_real=X, Y_real=Y)
+    want = ref.run(u, eps).clone()
+    st_ref = ref.engine.status()
+    if not st_ref & ST_SAMPLE_EIG:
+        pytest.skip("the singular first step did not break the Cholesky on this build")
+    want_outcome = outcome(ref)
+    fr = ForwardRollout(params, condition=True, X_real=X, Y_real=Y)
+    fr.use_fused_horizon(True)
+    l0 = fr.engine.launch_count
+    got = fr.run(u, eps)
+    assert fr.engine.launch_count - l0 <= 3  # the one-launch path ran first
+    assert not fr.engine.status() & ST_SAMPLE_EIG  # ... and could not take the eigen root itself
+    l1 = fr.engine.launch_count
+    got_outcome = outcome(fr)
+    assert fr.engine.launch_count - l1 > steps  # the step-wise repeat
+    assert got_outcome == want_outcome
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    assert not torch.isnan(want[:, :, 1]).any()  # the eigen-root draw of the singular step itself is finite
