@@ -361,16 +361,33 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
   const char* prod_base = (const char*)(st.Lh + (size_t)(s_first * st.g_ny + j_out) * st.elem_stride);
   int prod_left = (elem_bytes > 0 && s_first < st.ns) ? (st.ns - s_first + nwarps_total - 1) / nwarps_total : 0;  // elements
   unsigned prod_off = 0, prod_slot = 0;
+  // The LAST sub-panel of the stream holds only v = c mod 8 rows so far (v = 0: it is full).  A k-block is row-major, so
+  // its valid rows are the first 32 v bytes of its 256: those k-blocks are fetched one small bulk copy each (lane i takes
+  // k-block i of the chunk) into their usual places in the slot -- the rows never fetched keep stale shared memory, which
+  // only ever reaches accumulator rows >= v that subpanel_finish discards by selection.  5.5 % fewer factor bytes from DRAM
+  // over the car rollout.
+  const unsigned tail_rows = (unsigned)(c & 7);
+  const unsigned tail_start = tail_rows ? (unsigned)subpanel_off(P8 - 1, mo) * 8u : elem_bytes;
   auto produce_one = [&]() {
     if (prod_left == 0) return;
     const unsigned bytes = min((unsigned)STEP_SLOT_BYTES, elem_bytes - prod_off);
+    const unsigned bulk = prod_off < tail_start ? min(prod_off + bytes, tail_start) - prod_off : 0u;  // one copy
+    const unsigned nkb_t = (bytes - bulk) >> 8;                                                          // tail k-blocks
+    const unsigned tx = bulk + nkb_t * tail_rows * 32u;
     const uint32_t bar = bars_s + prod_slot * 8;
+    const uint32_t dst = ring_s + prod_slot * STEP_SLOT_BYTES;
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.eq.u32 p, %4, 0;\n\t"
-        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
-        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}"
-        ::"r"(bar), "r"(bytes), "r"(ring_s + prod_slot * STEP_SLOT_BYTES), "l"(prod_base + prod_off), "r"(lane) : "memory");
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %5;\n\t"
+        "setp.ne.and.u32 q, %1, 0, p;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %1, [%0];\n\t}"
+        ::"r"(bar), "r"(bulk), "r"(dst), "l"(prod_base + prod_off), "r"(lane), "r"(tx) : "memory");
+    if ((unsigned)lane < nkb_t) {
+      const unsigned o = bulk + (unsigned)lane * 256u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst + o), "l"(prod_base + prod_off + o), "r"(tail_rows * 32u), "r"(bar) : "memory");
+    }
     prod_slot = prod_slot + 1 == STEP_NST ? 0 : prod_slot + 1;
     prod_off += bytes;
     if (prod_off == elem_bytes) {
