@@ -192,6 +192,40 @@ def extras(torch, device, cpu_leg=True):
     del fr, eps
     torch.cuda.empty_cache()
 
+    # the reference's OWN sample counts (params_car_residual_fs.yaml: 200 dynamics samples; the SQP configs 20): the step-wise
+    # rollout is launch-latency bound there, ForwardRollout's default takes the one-launch kernel (k_horizon) instead
+    try:
+        small = {}
+        for ns_s in (20, 200, 2000):
+            frs = ForwardRollout(configs.car_residual_fs(ns_s, HORIZON, with_derivatives=True), condition=True, device=device)
+            us, es = synthetic_inputs(ns_s, HORIZON, 3, 3)
+            us, es = us.to(device), es.to(device)
+            row = {}
+            for label, mode in (("step_wise_ms", False), ("default_ms", "auto")):
+                frs.use_fused_horizon(mode)
+                best = None
+                for _ in range(4):
+                    torch.cuda.synchronize()
+                    e0.record()
+                    tr = frs.run(us, es)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms_s = e0.elapsed_time(e1)
+                    best = ms_s if best is None else min(best, ms_s)
+                row[label] = best
+                row[label.replace("_ms", "_one_launch")] = bool(frs.engine.get_option("last_rollout_fused"))
+                if mode is False:
+                    ref_tr = tr.clone()
+            row["bit_identical"] = bool(torch.equal(tr, ref_tr))
+            row["default_sample_steps_per_sec"] = ns_s * HORIZON / (row["default_ms"] * 1e-3)
+            small[str(ns_s)] = row
+            del frs
+        out["small_batch_car_rollout"] = dict(small, what="conditioned car rollout, 50 steps, at the reference's own sample counts: "
+                                              "host-observed ms per rollout incl. launch latency (best of 4), step-wise vs "
+                                              "ForwardRollout's default (one k_horizon launch while a warp gets <= 4 samples)")
+    except Exception as exc:  # noqa: BLE001
+        out["small_batch_car_rollout"] = {"error": repr(exc)}
+
     # the other large-batch rollout of the reference: benchmarking/simulate_true_reachable_set.py (2-D pendulum, real data WITH
     # derivative observations: m = 180, g_ny = 2, d = 3, T = 4, 30 steps; 20 samples x 10^4 repeats = 2e5 samples)
     try:

@@ -133,11 +133,17 @@ int gpmpc_export_point_states(const gpmpc_handle* h, uint8_t* out, void* stream)
 /* ---- tuning switches ------------------------------------------------------------------------------- */
 
 /* name = "rollout_fused"  (0 default: one gpmpc_step per horizon step; 1: gpmpc_rollout runs the whole horizon in ONE launch,
- *                          csrc/gpmpc_horizon.cuh, where the shape allows -- measured slower at the bench shape, kept as an option),
+ *                          csrc/gpmpc_horizon.cuh, where the shape allows; 2: automatic = one launch only while the step-wise
+ *                          rollout would be launch-latency bound, i.e. for the reference's own sample counts (20 ... ~2000),
+ *                          where it is 1.2 - 2.5x faster; at the bench shape it is slower.  The one-launch kernel cannot take
+ *                          the batch-wide eigen-root fallback of a failed jitter ladder: it flags GPMPC_ST_SAMPLE_NOT_PD and
+ *                          the caller repeats the rollout with "rollout_fused" 0 -- rollout.ForwardRollout does),
  *        "hz_groups"      (cap on the samples one CTA of the fused kernel holds at a time; 0 = as many as fit),
  *        "hz_stagger_ns"  (spread of the sample groups' start times in the fused kernel; -1 = automatic, 0 = none).
  * The results do not depend on any of them (bit-identical trajectories). */
 int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value);
+/* reads an option back; also "last_rollout_fused" (1 if the last gpmpc_rollout took the one-launch kernel) */
+int gpmpc_get_option(gpmpc_handle* h, const char* name, int64_t* value);
 
 /* ---- base samples (host only) -------------------------------------------------------------------- */
 

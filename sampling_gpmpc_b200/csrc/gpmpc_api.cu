@@ -72,11 +72,14 @@ struct gpmpc_handle {
   void* c_scratch = nullptr;
   size_t c_scratch_bytes = 0;
   int max_dyn_smem = 0, num_sms = 148;
-  // fused-horizon rollout (k_horizon, one launch per rollout): a measured prototype that LOSES to the step-wise path at the
-  // bench shape (254.7 ms vs 220.4 ms per rollout on the same box, profiles/r2_horizon_probe.txt), so it is
-  // opt-in: GPMPC_ROLLOUT_FUSED=1 / gpmpc_set_option("rollout_fused", 1).  GPMPC_HZ_GROUPS caps the sample groups per CTA
-  // (L2 footprint = #SMs x groups x g_ny factors), GPMPC_HZ_STAGGER_NS spreads the groups' starts over the horizon
-  bool fused_rollout = false;
+  // fused-horizon rollout (k_horizon, one launch per rollout).  It LOSES to the step-wise path at the bench shape (254.7 ms vs
+  // 220.4 ms per rollout on the same box, profiles/r2_horizon_probe.txt) and WINS where the step-wise rollout is
+  // launch-latency bound -- the reference's own sample counts: 1.0 vs 2.5 ms at 20 samples, 1.2 vs 2.4 ms at 200, 4.9 vs 5.8 ms
+  // at 2000 (profiles/r2_small_batch_rollout.txt).  gpmpc_set_option("rollout_fused", v) / GPMPC_ROLLOUT_FUSED=v: 0 never
+  // (default of the C ABI: a failed jitter ladder is then redone in-stream through the eigen root), 1 wherever the shape allows,
+  // 2 automatic = only while every warp of the fused kernel gets at most HZ_AUTO_MAX_SERIAL samples.  GPMPC_HZ_GROUPS caps the
+  // sample groups per CTA (L2 footprint = #SMs x groups x g_ny factors), GPMPC_HZ_STAGGER_NS spreads the groups' starts
+  int fused_rollout = 0;
   int hz_groups_cap = 0;
   long long hz_stagger_ns = -1;      // < 0: automatic (one sample-horizon of the previous fused rollout)
   double hz_last_ms = 0.0;           // device time of the previous fused launch (for the automatic stagger)
@@ -357,7 +360,7 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   if (const char* e = getenv("GPMPC_WO_MIN_M")) h->wo_min_m = atoi(e);
   if (const char* e = getenv("GPMPC_BLOCK_SCALAR")) h->block_mma = atoi(e) == 0;
   if (const char* e = getenv("GPMPC_WO_MAX_NB")) h->wo_max_nb = std::min(3, std::max(1, atoi(e)));
-  if (const char* e = getenv("GPMPC_ROLLOUT_FUSED")) h->fused_rollout = atoi(e) != 0;
+  if (const char* e = getenv("GPMPC_ROLLOUT_FUSED")) h->fused_rollout = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("GPMPC_HZ_GROUPS")) h->hz_groups_cap = atoi(e);
   if (const char* e = getenv("GPMPC_HZ_STAGGER_NS")) h->hz_stagger_ns = atoll(e);
   DevState& st = h->st;
@@ -1043,7 +1046,12 @@ static int horizon_groups(const gpmpc_handle* h, int n_steps) {
     const HzLayout L = hz_layout(st.g_ny, st.n_real, st.m, st.mo, st.d, st.T, n_steps, groups);
     if ((size_t)L.total * 8 + 256 <= (size_t)h->max_dyn_smem) break;
   }
-  return std::max(groups, 0);
+  if (groups < 1) return 0;
+  // automatic: only while the step-wise rollout would be launch-latency bound (few samples per warp of the fused kernel)
+  if (h->fused_rollout == 2 && (st.ns + h->num_sms * groups - 1) / (h->num_sms * groups) > HZ_AUTO_MAX_SERIAL) return 0;
+  // small batches: one sample group per CTA over as many SMs as there are samples, rather than few full CTAs
+  if (h->hz_groups_cap <= 0) groups = std::min(groups, std::max(1, (st.ns + h->num_sms - 1) / h->num_sms));
+  return groups;
 }
 
 template <int D, int T>
@@ -1559,13 +1567,28 @@ int gpmpc_set_grouping(gpmpc_handle* h, int32_t group_size, double min_dist) {
 int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(h, GPMPC_ERR_ARG, "null argument");
   const std::string n(name);
-  if (n == "rollout_fused") h->fused_rollout = value != 0;
+  if (n == "rollout_fused") h->fused_rollout = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;
   else if (n == "force_block_fallback") h->force_block_fallback = value != 0;
   else if (n == "force_big") h->force_big = value != 0;
   else if (n == "big_slab_cap") h->big_slab_cap = (int)value & ~7;
+  else return fail(h, GPMPC_ERR_ARG, "unknown option " + n);
+  return GPMPC_OK;
+}
+
+int gpmpc_get_option(gpmpc_handle* h, const char* name, int64_t* value) {
+  if (!h || !name || !value) return fail(h, GPMPC_ERR_ARG, "null argument");
+  const std::string n(name);
+  if (n == "rollout_fused") *value = h->fused_rollout;
+  else if (n == "last_rollout_fused") *value = h->last_rollout_fused ? 1 : 0;
+  else if (n == "hz_groups") *value = h->hz_groups_cap;
+  else if (n == "hz_stagger_ns") *value = h->hz_stagger_ns;
+  else if (n == "force_wo") *value = h->force_wo;
+  else if (n == "force_block_fallback") *value = h->force_block_fallback;
+  else if (n == "force_big") *value = h->force_big;
+  else if (n == "big_slab_cap") *value = h->big_slab_cap;
   else return fail(h, GPMPC_ERR_ARG, "unknown option " + n);
   return GPMPC_OK;
 }

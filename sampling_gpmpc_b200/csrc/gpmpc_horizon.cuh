@@ -24,6 +24,8 @@
 #ifndef HZ_MAX_WARPS
 #define HZ_MAX_WARPS 12  // 384 threads: up to 168 registers per thread
 #endif
+// "rollout_fused" = 2 (automatic): samples one warp group may take one after the other (measured: ahead at 4, behind at 34)
+#define HZ_AUTO_MAX_SERIAL 4
 #ifndef HZ_SEG
 #define HZ_SEG 48        // 8-row column groups per TMA chunk / ring slot (3 KB); multiple of 8
 #endif

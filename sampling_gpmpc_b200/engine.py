@@ -79,6 +79,7 @@ ABI = {
     "gpmpc_rollout_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "gpmpc_version": (C.c_char_p, []),
     "gpmpc_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "gpmpc_get_option": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64)]),
     "gpmpc_set_grouping": (C.c_int, [_P, _I, C.c_double]),
     "gpmpc_truncate_hallucinated": (C.c_int, [_P, _I]),
     "gpmpc_linearise": (C.c_int, [_P, C.POINTER(GpmpcEnv), _D, _I, _I, _D, C.POINTER(GpmpcSampleOpts), _I, _D, _D, _D, _D, _D, _D, _P]),
@@ -542,6 +543,12 @@ class GPEngine:
         """Tuning switches of the C ABI (gpmpc_set_option): rollout_fused, hz_groups, hz_stagger_ns.  Results do not depend
         on them."""
         self._check(self.lib.gpmpc_set_option(self.h, name.encode(), int(value)), "gpmpc_set_option")
+
+    def get_option(self, name: str) -> int:
+        """Reads a gpmpc_set_option switch back; also "last_rollout_fused" (did the last rollout take the one-launch kernel)."""
+        v = C.c_int64(0)
+        self._check(self.lib.gpmpc_get_option(self.h, name.encode(), C.byref(v)), "gpmpc_get_option")
+        return int(v.value)
 
     def set_timing(self, on: bool):
         self._check(self.lib.gpmpc_set_timing(self.h, int(on)), "gpmpc_set_timing")

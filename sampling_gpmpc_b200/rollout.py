@@ -70,43 +70,45 @@ class ForwardRollout:
         self.env = make_env_struct(self.spec, K, params["env"]["goal_state"] if fb else None)
         self.opts = self.engine.opts(ag["Dyn_gp_beta"], ag["Dyn_gp_variance_is_zero"])
         self.x0 = torch.tensor(params["env"]["start"], dtype=F64, device=self.device).expand(self.ns, -1).contiguous()
+        self.use_fused_horizon("auto")
 
     def run(self, u_ff: torch.Tensor, eps: torch.Tensor, traj: Optional[torch.Tensor] = None,
             check: bool = False) -> torch.Tensor:
         """u_ff (steps, nu); eps (steps, ns_global or ns, g_ny, 1, T) standard-normal draws (the reference's
         epistimic_random_vector[:, 1]).  Returns this rank's trajectories (ns, nx, steps+1) on the device.  The call
-        only queues work; `check=True` (or `check()` later) waits for it and raises NotPSDError where GPyTorch would."""
+        only queues work; `check=True` (or `check()` later) waits for it and raises NotPSDError where GPyTorch would.
+
+        Small batches (the reference's own sample counts, up to ~2000 samples) run as ONE launch of the fused-horizon
+        kernel (use_fused_horizon: automatic by default), which cannot take GPyTorch's batch-wide eigen-root fallback of a
+        failed jitter ladder in flight: for those the status word is read right away (one 4-byte copy behind a ~1 ms
+        kernel) and a rollout that hit a failed ladder is repeated step-wise, so the result is the step-wise one either way."""
         if eps.shape[1] == self.ns_global and self.world_size > 1:
             eps = eps[:, self.s_lo:self.s_hi]
         self.engine.reset_hallucinated()
         out = self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
-        self._last_run = (u_ff, eps, out) if getattr(self, "_fused", False) else None
+        if self._fused_mode and self.engine.get_option("last_rollout_fused"):
+            from .engine import ST_SAMPLE_NOT_PD
+            if self.engine.status() & ST_SAMPLE_NOT_PD:  # (a NaN flagged next to it is the failed draw's own, carried forward)
+                self.engine.status(clear=True)
+                self.engine.set_option("rollout_fused", 0)
+                try:
+                    self.engine.reset_hallucinated()
+                    self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, out)
+                finally:
+                    self.engine.set_option("rollout_fused", self._fused_mode)
         if check:
             self.check()
         return out
 
-    def use_fused_horizon(self, on: bool = True):
-        """Opt in to the one-launch rollout kernel (csrc/gpmpc_horizon.cuh; bit-identical results, measured slower than the
-        step-wise path at the bench shape -- DESIGN.md 3 K1h)."""
-        self._fused = bool(on)
-        self.engine.set_option("rollout_fused", int(self._fused))
+    def use_fused_horizon(self, mode="auto"):
+        """The one-launch rollout kernel (csrc/gpmpc_horizon.cuh; bit-identical results): "auto" (default) = only where the
+        step-wise rollout is launch-latency bound (1.2 - 2.5x faster there; slower at the bench shape),
+        True = wherever the shape allows, False = never."""
+        self._fused_mode = 2 if mode == "auto" else int(bool(mode))
+        self.engine.set_option("rollout_fused", self._fused_mode)
 
     def check(self) -> int:
-        """Synchronises and turns the device status word into the reference's error behaviour (engine.raise_on_status).
-        The fused-horizon kernel cannot take GPyTorch's batch-wide eigen-root fallback in flight; when a draw of such a
-        rollout failed its jitter ladder the rollout is repeated on the step-wise path, which can."""
-        from .engine import ST_SAMPLE_NOT_PD
-        if getattr(self, "_fused", False) and getattr(self, "_last_run", None) is not None:
-            s = self.engine.status()
-            if s & ST_SAMPLE_NOT_PD:  # (a NaN flagged next to it is the failed draw's own NaN, carried into the next step)
-                self.engine.status(clear=True)
-                self.engine.set_option("rollout_fused", 0)
-                try:
-                    u_ff, eps, traj = self._last_run
-                    self.engine.reset_hallucinated()
-                    self.engine.rollout(self.env, self.x0, u_ff, eps, self.opts, traj)
-                finally:
-                    self.engine.set_option("rollout_fused", 1)
+        """Synchronises and turns the device status word into the reference's error behaviour (engine.raise_on_status)."""
         return self.engine.raise_on_status()
 
     def run_from_host(self, u_ff: torch.Tensor, eps_host: torch.Tensor, traj: Optional[torch.Tensor] = None,

@@ -33,7 +33,7 @@ def _pendulum(ns, steps, seed):
 def _run(params, eps, u, fused, **options):
     from sampling_gpmpc_b200.rollout import ForwardRollout
     fr = ForwardRollout(params, condition=True)
-    fr.engine.set_option("rollout_fused", int(fused))
+    fr.use_fused_horizon(bool(fused))
     for k, v in options.items():
         fr.engine.set_option(k, v)
     traj = fr.run(u, eps)
@@ -143,20 +143,37 @@ def test_failed_ladder_in_the_fused_kernel_is_redone_step_wise_with_the_eigen_ro
                 return ("raised", type(e).__name__), [str(x.message)[:40] for x in w]
 
     ref = ForwardRollout(params, condition=True, X_real=X, Y_real=Y)
+    ref.use_fused_horizon(False)
+    l0 = ref.engine.launch_count
     want = ref.run(u, eps).clone()
+    launches_ref = ref.engine.launch_count - l0
     st_ref = ref.engine.status()
     if not st_ref & ST_SAMPLE_EIG:
         pytest.skip("the singular first step did not break the Cholesky on this build")
     want_outcome = outcome(ref)
-    fr = ForwardRollout(params, condition=True, X_real=X, Y_real=Y)
-    fr.use_fused_horizon(True)
-    l0 = fr.engine.launch_count
-    got = fr.run(u, eps)
-    assert fr.engine.launch_count - l0 <= 3  # the one-launch path ran first
-    assert not fr.engine.status() & ST_SAMPLE_EIG  # ... and could not take the eigen root itself
-    l1 = fr.engine.launch_count
-    got_outcome = outcome(fr)
-    assert fr.engine.launch_count - l1 > steps  # the step-wise repeat
-    assert got_outcome == want_outcome
-    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    for mode in (True, "auto"):
+        fr = ForwardRollout(params, condition=True, X_real=X, Y_real=Y)
+        fr.use_fused_horizon(mode)
+        l0 = fr.engine.launch_count
+        got = fr.run(u, eps)
+        # the one-launch kernel ran first (horizon + row tables), then the step-wise repeat
+        assert fr.engine.launch_count - l0 == launches_ref + 2
+        assert fr.engine.get_option("last_rollout_fused") == 0
+        assert fr.engine.status() == st_ref
+        assert outcome(fr) == want_outcome
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
     assert not torch.isnan(want[:, :, 1]).any()  # the eigen-root draw of the singular step itself is finite
+
+
+def test_automatic_choice_is_the_one_launch_kernel_for_small_batches_only():
+    """ForwardRollout's default: one launch while a warp of the fused kernel gets at most 4 samples, step-wise beyond."""
+    from sampling_gpmpc_b200.rollout import ForwardRollout
+    for ns, fused in ((40, 1), (2300, 1), (2400, 0)):
+        params, eps, u = _car(ns, 6, 3)
+        fr = ForwardRollout(params, condition=True)
+        l0 = fr.engine.launch_count
+        traj = fr.run(u, eps)
+        assert fr.engine.get_option("last_rollout_fused") == fused, ns
+        assert (fr.engine.launch_count - l0 <= 2) == bool(fused)
+        fr2, ref = _run(params, eps, u, fused=False)
+        assert torch.equal(traj, ref) and fr.engine.status() == 0

@@ -16,12 +16,16 @@ u, eps = u.cuda(), eps.cuda()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
 for cfg in cfgs:
-    if cfg in ("step", "wo"):
-        fr.engine.set_option("rollout_fused", 0)
+    if cfg == "auto":
+        fr.use_fused_horizon("auto")
+        fr.engine.set_option("hz_groups", 0)
+        fr.engine.set_option("hz_stagger_ns", -1)
+    elif cfg in ("step", "wo"):
+        fr.use_fused_horizon(False)
         fr.engine.set_option("force_wo", int(cfg == "wo"))
     else:
         g, s = cfg.split(":")
-        fr.engine.set_option("rollout_fused", 1)
+        fr.use_fused_horizon(True)
         fr.engine.set_option("hz_groups", int(g))
         fr.engine.set_option("hz_stagger_ns", int(s))
     times = []
