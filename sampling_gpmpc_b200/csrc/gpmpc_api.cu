@@ -81,6 +81,8 @@ struct gpmpc_handle {
   // sample groups per CTA (L2 footprint = #SMs x groups x g_ny factors), GPMPC_HZ_STAGGER_NS spreads the groups' starts
   int fused_rollout = 0;
   int hz_groups_cap = 0;
+  int step_grid_cap = 0;             // > 0: CTAs (= SMs) the step kernel may take; the rest stay free for a concurrent stream
+  int step_warps_cap = 0;            // > 0: warps per CTA of the step kernel (two such CTAs of two streams share an SM)
   long long hz_stagger_ns = -1;      // < 0: automatic (one sample-horizon of the previous fused rollout)
   double hz_last_ms = 0.0;           // device time of the previous fused launch (for the automatic stagger)
   int hz_last_samples_per_group = 0;
@@ -771,7 +773,13 @@ static int launch_step_finish(gpmpc_handle* h, const DevState& st, const double*
     CUDA_TRY(h, cudaGetLastError());
     return GPMPC_OK;
   }
-  k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_ALL);
+  // the plain fused step: the diagonal-block part of the append specialised on c mod 8 (uniform over the launch)
+#define FIN_CASE(IF_) case IF_: k_step_finish<T, IF_><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_ALL); break;
+  switch ((eps && grow && T > 1) ? (st.c & 7) : -1) {
+    FIN_CASE(0) FIN_CASE(1) FIN_CASE(2) FIN_CASE(3) FIN_CASE(4) FIN_CASE(5) FIN_CASE(6) FIN_CASE(7)
+    default: k_step_finish<T><<<fin_blocks, FIN_THREADS, 0, stream>>>(st, x, eps, o, mean, var, y, jl, grow, FIN_ALL);
+  }
+#undef FIN_CASE
   h->launches++;
   if (eps && T > 1 && !(o.flags & GPMPC_OPT_NO_EIG_FALLBACK)) {
     // GPyTorch's batch-wide eigen-root fallback: exits on the device unless an element of this step failed its ladder
@@ -854,7 +862,8 @@ static int launch_step_impl(gpmpc_handle* h, const DevState& st, const double* x
   CUDA_TRY(h, opt_in_smem(h, kern, h->max_dyn_smem, true));
   // persistent CTAs, one per SM, split over the g_ny outputs; each warp loops over samples
   const int want = (st.ns + warps - 1) / warps;
-  const int resident = std::max(1, h->num_sms / st.g_ny);
+  int resident = std::max(1, h->num_sms / st.g_ny);
+  if (h->step_grid_cap > 0) resident = std::max(1, std::min(resident, h->step_grid_cap / st.g_ny));
   dim3 grid(std::min(want, resident), st.g_ny);
   kern<<<grid, warps * 32, smem, stream>>>(st, x, grow);
   h->launches++;
@@ -948,6 +957,7 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
     return launch_step_big<D, T>(h, st, x, eps, o, mean, var, y, jl, grow, stream, handled);
   if (!*handled) return GPMPC_OK;  // general block kernels take over
   int warps = (int)std::min<size_t>(STEP_MAX_WARPS, (budget - fixed) / per_warp);
+  if (h->step_warps_cap > 0) warps = std::min(warps, h->step_warps_cap);
   // small launches: spread the samples over the SMs rather than filling few CTAs
   const int per_cta_need = (st.ns * st.g_ny + h->num_sms - 1) / h->num_sms;
   warps = std::max(1, std::min(warps, std::max(per_cta_need, 1)));
@@ -1569,6 +1579,8 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   const std::string n(name);
   if (n == "rollout_fused") h->fused_rollout = (int)std::max<int64_t>(0, std::min<int64_t>(2, value));
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
+  else if (n == "step_grid_cap") h->step_grid_cap = (int)value;
+  else if (n == "step_warps_cap") h->step_warps_cap = (int)value;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;
   else if (n == "force_block_fallback") h->force_block_fallback = value != 0;
@@ -1584,6 +1596,8 @@ int gpmpc_get_option(gpmpc_handle* h, const char* name, int64_t* value) {
   if (n == "rollout_fused") *value = h->fused_rollout;
   else if (n == "last_rollout_fused") *value = h->last_rollout_fused ? 1 : 0;
   else if (n == "hz_groups") *value = h->hz_groups_cap;
+  else if (n == "step_grid_cap") *value = h->step_grid_cap;
+  else if (n == "step_warps_cap") *value = h->step_warps_cap;
   else if (n == "hz_stagger_ns") *value = h->hz_stagger_ns;
   else if (n == "force_wo") *value = h->force_wo;
   else if (n == "force_block_fallback") *value = h->force_block_fallback;

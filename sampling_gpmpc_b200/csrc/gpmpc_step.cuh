@@ -714,7 +714,12 @@ k_shared_rows(DevState st, const double* __restrict__ x, int k_lo, int k_hi) {
     __syncthreads();
 
     const int p_first = k_lo >> 3;  // panels above the slab have no columns in it (lower triangular)
-    for (int pi = warp; pi < Pm - p_first; pi += nw) {
+    // panels longest first, dealt to the warps in serpentine order (0 .. nw-1, nw-1 .. 0, ...): panel p costs 2 (p + 1)
+    // k-steps, so plain round-robin leaves warp 0 with 90 of them and warp 7 with 48 at m = 180 (8 warps); this way 76 / 62
+    for (int rnd = 0;; ++rnd) {
+      const int pi = rnd * nw + ((rnd & 1) ? nw - 1 - warp : warp);
+      if (rnd * nw >= Pm - p_first) break;
+      if (pi >= Pm - p_first) continue;
       const int p = Pm - 1 - pi;
       const int n4 = (min(k_hi, 8 * p + 8) - k_lo) >> 2;  // k-steps of 4 columns of this panel inside the slab
       const double* ap = gL + subpanel_off(p, 0) + sp_idx(tig, gid) + (size_t)(k_lo >> 2) * 32;
@@ -896,7 +901,56 @@ struct GroupArgs {
   int group_elems;            // batch elements per group = group_size * g_ny
 };
 
-template <int T>
+// The diagonal-block part of the append for ONE 8 x 8 block with everything known at compile time: IF = block row of the first
+// new row, new rows [R0, R1) of the T fall into this block (c is uniform over a launch, so the host dispatches on c mod 8).
+// The 8 x 8 mirror then lives in registers -- with run-time bounds it is a local-memory array and its loads form a serial chain
+// of DRAM round trips (ncu: 63 % of k_step_finish's stall samples sat on these loops) -- and every load is issued before the
+// first use.  Same arithmetic, same order as the run-time form in k_step_finish.
+template <int T, int IF, int R0, int R1>
+__device__ __forceinline__ void finish_block_const(double* Le, int c, int mo, const TriT<T>& Ln, const double (&rdn)[T]) {
+  const int kb = c + R0 - IF;  // first own row of this block (a multiple of 8)
+  double* sp = Le + subpanel_off(kb >> 3, mo);
+  double* gblk = sp + (size_t)(mo + kb) * 8;
+  double blk[8][8];
+  // old columns t < IF: the old inverse (slots on and above the diagonal: column t, rows <= t) and the new rows' L entries
+#pragma unroll
+  for (int t = 0; t < 8; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (t < IF && (i <= t || (i >= IF && i < IF + (R1 - R0)))) blk[t][i] = gblk[sp_idx(t, i)];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i >= IF && i < IF + (R1 - R0)) {
+      const int r = R0 + (i - IF);
+#pragma unroll
+      for (int s = 0; s < T; ++s)
+        if (s >= R0 && s < r) blk[IF + (s - R0)][i] = Ln.v[r * (r + 1) / 2 + s];
+      blk[i][i] = rdn[r];
+#pragma unroll
+      for (int jc = 0; jc < 8; ++jc) {
+        if (jc < i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (t >= jc && t < i) acc = fma(blk[t][i], blk[t][jc], acc);
+          blk[i][jc] = -rdn[r] * acc;  // slot (row jc, column i)
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < T; ++s)
+        if (s < R0) sp[sp_idx(mo + c + s, i)] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (t >= IF && t <= i) gblk[sp_idx(t, i)] = blk[t][i];  // new columns of row i (incl. 1 / L_ii)
+#pragma unroll
+      for (int jc = 0; jc < 8; ++jc)
+        if (jc < i) gblk[sp_idx(i, jc)] = blk[i][jc];  // transposed inverse row
+    }
+  }
+}
+
+// IFC = c mod 8 when the host knows it (the plain fused step), -1 = run-time block bounds
+template <int T, int IFC = -1>
 __global__ void __launch_bounds__(FIN_THREADS)
 k_step_finish(DevState st, const double* __restrict__ x, const double* __restrict__ eps, gpmpc_sample_opts opts,
               double* __restrict__ mean, double* __restrict__ var, double* __restrict__ y,
@@ -910,6 +964,12 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
   // Everything this kernel writes depends only on st.fin, eps and the old factor rows, so the repeat simply overwrites.
   if (eig_redo && (T == 1 || *(volatile int*)st.eig_flag != st.eig_epoch)) return;
   const int j_out = b % st.g_ny, d = st.d, c = st.c, mo = st.mo;
+  if (IFC > 0 && grow_factor && eps && mode != FIN_DRAW) {
+    // the diagonal block the new rows fall into (4 lines of 128 B) is needed at the very end: start fetching it now
+    const char* blk0 = (const char*)(st.Lh + (size_t)b * st.elem_stride + subpanel_off(c >> 3, mo) + (size_t)(mo + (c & ~7)) * 8);
+#pragma unroll
+    for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(blk0 + 128 * l));
+  }
   const double* fi = st.fin + (size_t)b * FS;
   const double os = st.os[j_out];
   double macc[T];
@@ -1052,33 +1112,40 @@ k_step_finish(DevState st, const double* __restrict__ x, const double* __restric
     }
   }
   // diagonal blocks touched by rows c .. c+T-1 (at most two): blk[col][row] mirrors the 8 x 8 block in memory
-  // (lower: L, diagonal: 1/L_kk, upper: transposed inverse); the old rows' part and the new rows' entries under
+  // (lower: L, diagonal: 1/L_kk, upper: transposed inverse); the old rows' inverse and the new rows' entries under
   // old columns (written by k_step) are read back, the new rows are completed and their slots written.
   double* Le = st.Lh + (size_t)b * st.elem_stride;
-  int r0 = 0;
-  while (r0 < T) {
-    const int kb = (c + r0) & ~7;                    // first own row of this block
-    const int i_first = c + r0 - kb;                 // block row of the first new row
-    const int r1 = min(T, r0 + 8 - i_first);         // new rows [r0, r1) fall into this block
-    double* gblk = Le + subpanel_off(kb >> 3, mo) + (size_t)(mo + kb) * 8;
-    double blk[8][8];
-    for (int t = 0; t < i_first; ++t)                // old columns: old rows' slots and the new rows' L entries
-      for (int i = 0; i < i_first + (r1 - r0); ++i) blk[t][i] = gblk[sp_idx(t, i)];
-    for (int r = r0; r < r1; ++r) {
-      const int i = i_first + (r - r0);
-      for (int s = r0; s < r; ++s) blk[i_first + (s - r0)][i] = Ln.v[r * (r + 1) / 2 + s];
-      blk[i][i] = rdn[r];
-      for (int jc = 0; jc < i; ++jc) {
-        double acc = 0.0;
-        for (int t = jc; t < i; ++t) acc = fma(blk[t][i], blk[t][jc], acc);
-        blk[i][jc] = -rdn[r] * acc;                  // slot (row jc, column i)
+  if constexpr (IFC >= 0) {
+    // c mod 8 known at compile time (the host dispatches on it: c is uniform over the launch): the block lives in registers
+    constexpr int R1 = T < 8 - IFC ? T : 8 - IFC;
+    finish_block_const<T, IFC, 0, R1>(Le, c, mo, Ln, rdn);
+    if constexpr (R1 < T) finish_block_const<T, 0, R1, T>(Le, c, mo, Ln, rdn);
+  } else {
+    int r0 = 0;
+    while (r0 < T) {
+      const int kb = (c + r0) & ~7;                    // first own row of this block
+      const int i_first = c + r0 - kb;                 // block row of the first new row
+      const int r1 = min(T, r0 + 8 - i_first);         // new rows [r0, r1) fall into this block
+      double* gblk = Le + subpanel_off(kb >> 3, mo) + (size_t)(mo + kb) * 8;
+      double blk[8][8];
+      for (int t = 0; t < i_first; ++t)                // old columns: old rows' slots and the new rows' L entries
+        for (int i = 0; i < i_first + (r1 - r0); ++i) blk[t][i] = gblk[sp_idx(t, i)];
+      for (int r = r0; r < r1; ++r) {
+        const int i = i_first + (r - r0);
+        for (int s = r0; s < r; ++s) blk[i_first + (s - r0)][i] = Ln.v[r * (r + 1) / 2 + s];
+        blk[i][i] = rdn[r];
+        for (int jc = 0; jc < i; ++jc) {
+          double acc = 0.0;
+          for (int t = jc; t < i; ++t) acc = fma(blk[t][i], blk[t][jc], acc);
+          blk[i][jc] = -rdn[r] * acc;                  // slot (row jc, column i)
+        }
+        double* rowi = Le + subpanel_off(kb >> 3, mo);
+        for (int s = 0; s < r0; ++s) rowi[sp_idx(mo + c + s, i)] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
+        for (int t = i_first; t <= i; ++t) gblk[sp_idx(t, i)] = blk[t][i];   // new columns of row i (incl. 1/L_ii)
+        for (int jc = 0; jc < i; ++jc) gblk[sp_idx(i, jc)] = blk[i][jc];     // transposed inverse row
       }
-      double* rowi = Le + subpanel_off(kb >> 3, mo);
-      for (int s = 0; s < r0; ++s) rowi[sp_idx(mo + c + s, i)] = Ln.v[r * (r + 1) / 2 + s];  // new columns of an earlier block
-      for (int t = i_first; t <= i; ++t) gblk[sp_idx(t, i)] = blk[t][i];   // new columns of row i (incl. 1/L_ii)
-      for (int jc = 0; jc < i; ++jc) gblk[sp_idx(i, jc)] = blk[i][jc];     // transposed inverse row
+      r0 = r1;
     }
-    r0 = r1;
   }
 }
 
