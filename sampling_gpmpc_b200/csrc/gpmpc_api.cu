@@ -60,6 +60,12 @@ struct gpmpc_handle {
   // hallucinated set (gpmpc_linearise with reset_first): the append after the reset then needs no second posterior pass
   double *S2buf = nullptr, *mu2buf = nullptr;
   bool want_real_only = false, real_cache_valid = false;
+  // chol(Sigma_app + noise) factorised beside the draw for the append that follows (k_pm_finish's second CTA row -> st.Lpre):
+  // requested by gpmpc_linearise; pre_kind 1 = against the current factor (valid while factor_version == pre_version),
+  // 2 = against the real data alone (valid for the append right after a reset), 0 = none
+  bool prefactor_next = false;
+  int pre_kind = 0, pre_H = 0;
+  long long pre_version = -1;
   int real_cache_H = 0;
   long long launches = 0;
   double last_bytes = 0.0, last_flops = 0.0;
@@ -230,15 +236,17 @@ static int ensure_workspace(gpmpc_handle* h, int H) {
   // sized for the reserved capacity where one is known (gpmpc_reserve / Agent: H * max_sqp_iter), so that the SQP loop never
   // re-allocates (cudaFree / cudaMalloc synchronise the device: 10-20 ms spikes otherwise)
   const int new_n = std::max(std::max(n + n / 2, st.m + st.c_cap), h->ws_n), new_q = std::max(q, h->ws_q), new_H = std::max(H, h->ws_H);
-  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E);
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.Lpre);
   cudaFree(h->S2buf); cudaFree(h->mu2buf);
-  st.W = st.S = st.C = st.mu = st.xc = st.E = nullptr;
+  st.W = st.S = st.C = st.mu = st.xc = st.E = st.Lpre = nullptr;
+  h->pre_kind = 0;
   h->S2buf = h->mu2buf = nullptr;
   h->real_cache_valid = false;
   const size_t B = (size_t)st.B;
   CUDA_TRY(h, dev_alloc(&st.W, B * new_n * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&st.S, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&st.C, B * (size_t)new_q * new_q));
+  CUDA_TRY(h, dev_alloc(&st.Lpre, B * ((size_t)new_q * (new_q + 1) / 2 + 1)));
   CUDA_TRY(h, dev_alloc(&st.mu, B * (size_t)new_q));
   CUDA_TRY(h, dev_alloc(&h->S2buf, B * (size_t)new_q * new_q));
   CUDA_TRY(h, dev_alloc(&h->mu2buf, B * (size_t)new_q));
@@ -314,7 +322,13 @@ static int launch_posterior_mma(gpmpc_handle* h, const DevState& st, const doubl
   if (!mean && !var && !eps) return GPMPC_OK;  // W, Sigma*, mean stay in the workspace (recompute before an append)
   size_t tri = eps ? tri_bytes(h, q) : 0;
   if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;
-  k_pm_finish<<<st.B, BLK_THREADS, tri, stream>>>(st, H, mean, var, eps, o, y, jl, tri ? 1 : 0);
+  // the append's own Cholesky beside the draw's (second CTA row), when the caller announced the append (gpmpc_linearise)
+  const int pre = (h->prefactor_next && tri && q >= 2 && st.Lpre) ? (st.S2 ? 2 : 1) : 0;
+  h->prefactor_next = false;
+  h->pre_kind = pre;
+  h->pre_H = H;
+  h->pre_version = h->factor_version;
+  k_pm_finish<<<dim3(st.B, pre ? 2 : 1), BLK_THREADS, tri, stream>>>(st, H, mean, var, eps, o, y, jl, tri ? 1 : 0, pre);
   h->launches += 1;
   return launch_sample_eig(h, st, H, eps, o, y, jl, stream);
 }
@@ -398,7 +412,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin); cudaFree(st.Wo);
-  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.eig_flag);
+  cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.Lpre); cudaFree(st.eig_flag);
   cudaFree(h->S2buf); cudaFree(h->mu2buf);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
   cudaFree((void*)st.Yr); cudaFree((void*)st.real_full);
@@ -617,6 +631,8 @@ int gpmpc_posterior(gpmpc_handle* h, const double* x, int32_t H, double* mean, d
   h->real_cache_valid = with_real;  // any other model call overwrites W: the real-only cache goes with it
   h->real_cache_H = H;
   if (with_real) { st.S2 = h->S2buf; st.mu2 = h->mu2buf; }
+  h->pre_kind = 0;  // (set again by launch_posterior_mma when this call prefactors)
+  if (!(h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q)) h->prefactor_next = false;
   if (h->block_mma && !h->has_partial && H * st.T <= PM_MAX_Q) {
     rc = dispatch_posterior_mma(h, st, x, H, mean, var, eps, o, y, jitter_level, (cudaStream_t)stream);
     if (rc) return rc;
@@ -704,7 +720,9 @@ int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const
   DevState st = h->st;
   st.W_stride = (long long)h->ws_n * (H * st.T);
   int reuse = (h->cache_version == h->factor_version && h->cache_H == H) ? 1 : 0;
+  int prefactored = (reuse && h->pre_kind == 1 && h->pre_version == h->factor_version && h->pre_H == H && !d_act) ? 1 : 0;
   if (grow && !reuse && hst.c == 0 && h->real_cache_valid && h->real_cache_H == H) {
+    prefactored = (h->pre_kind == 2 && h->pre_H == H && !d_act) ? 1 : 0;
     // the hallucinated set was reset after the model call: W's real rows, Sigma* and the mean w.r.t. the real data alone
     // came out of that same pass (k_pm_gram's second accumulators); k_append checks on the device that x is the same
     st.S = h->S2buf;
@@ -726,7 +744,9 @@ int gpmpc_append_masked(gpmpc_handle* h, const double* x, const double* y, const
   if (rc) return rc;
   size_t tri = grow ? tri_bytes(h, H * st.T) : 0;
   if (tri + 8192 > (size_t)h->max_dyn_smem) tri = 0;  // k_append also holds 2 KB of static shared memory
-  k_append<<<st.B, BLK_THREADS, tri, stream>>>(st, x, y, d_act, H, st.np, reuse, grow ? 1 : 0, tri ? 1 : 0);
+  if (!grow || !tri || !reuse) prefactored = 0;
+  h->pre_kind = 0;
+  k_append<<<st.B, BLK_THREADS, tri, stream>>>(st, x, y, d_act, H, st.np, reuse, grow ? 1 : 0, tri ? 1 : 0, prefactored);
   h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   if (d_act) CUDA_TRY(h, cudaStreamSynchronize(stream));  // caller may reuse point_active's host memory
@@ -1155,6 +1175,7 @@ int gpmpc_linearise(gpmpc_handle* h, const gpmpc_env* env, const double* xu, int
     h->launches++;
   }
   h->want_real_only = reset_first != 0;
+  h->prefactor_next = h->condition;  // the append below factorises Sigma* + noise: do it beside the draw
   rc = gpmpc_posterior(h, h->lin_xg, H, mean, var, eps, opts, y, jitter_level, stream_);
   if (rc) return rc;
   if (reset_first) {

@@ -352,8 +352,10 @@ __device__ void block_sample(const DevState& st, int b, int H, const double* __r
       int info;
       if (tri) {
         __syncthreads();
-        for (int r = tid; r < q; r += nt)  // row r of the lower triangle is contiguous in both layouts
-          for (int s = 0; s <= r; ++s) tri[r * (r + 1) / 2 + s] = S[(size_t)r * q + s] + (s == r ? add : 0.0);
+        for (int idx = tid; idx < q * q; idx += nt) {  // coalesced over the rows of S
+          const int r = idx / q, s = idx - r * q;
+          if (s <= r) tri[r * (r + 1) / 2 + s] = S[idx] + (s == r ? add : 0.0);
+        }
         info = block_cholesky_packed(tri, q);
       } else {
         for (int idx = tid; idx < q * q; idx += nt) {
@@ -455,7 +457,8 @@ k_sample(DevState st, int H, const double* __restrict__ eps, gpmpc_sample_opts o
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BLK_THREADS)
 k_append(DevState st, const double* __restrict__ x, const double* __restrict__ ylab,
-         const unsigned char* __restrict__ active, int H, int pt_base, int reuse, int grow_factor, int tri_ok) {
+         const unsigned char* __restrict__ active, int H, int pt_base, int reuse, int grow_factor, int tri_ok,
+         int prefactored) {
   extern __shared__ __align__(16) double dyn_tri[];
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int j = b % st.g_ny, d = st.d, T = st.T, q = H * T;
@@ -509,10 +512,21 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   const double* noise = st.noise + j * T;
   int info;
   if (tri_ok) {
-    for (int rr = tid; rr < qa; rr += nt)
-      for (int ss = 0; ss <= rr; ++ss)
-        dyn_tri[rr * (rr + 1) / 2 + ss] = S[(size_t)sh_act[rr] * q + sh_act[ss]] + (ss == rr ? noise[sh_act[rr] % T] : 0.0);
-    info = block_cholesky_packed(dyn_tri, qa);  // the rest of the kernel reads the factor straight from shared memory
+    const int ntri = qa * (qa + 1) / 2;
+    if (prefactored && sh_same) {
+      // chol(Sigma_app + noise) was factorised beside the draw (k_pm_finish, second CTA row): pick it up
+      const double* pre = st.Lpre + (size_t)b * (ntri + 1);
+      for (int idx = tid; idx < ntri; idx += nt) dyn_tri[idx] = pre[idx];
+      info = (int)pre[ntri];
+      __syncthreads();
+    } else {
+      for (int idx = tid; idx < qa * qa; idx += nt) {
+        const int rr = idx / qa, ss = idx - rr * qa;
+        if (ss <= rr)
+          dyn_tri[rr * (rr + 1) / 2 + ss] = S[(size_t)sh_act[rr] * q + sh_act[ss]] + (ss == rr ? noise[sh_act[rr] % T] : 0.0);
+      }
+      info = block_cholesky_packed(dyn_tri, qa);  // the rest of the kernel reads the factor straight from shared memory
+    }
   } else {
     for (int idx = tid; idx < qa * qa; idx += nt) {
       int rr = idx / qa, ss = idx % qa;
@@ -529,6 +543,82 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     if (tid == 0) atomicOr(st.status, GPMPC_ST_APPEND_NOT_PD);
     return;
   }
+  __shared__ double sh_beta[512];
+  if (b == 0)
+    for (int rr = tid; rr < qa; rr += nt) {
+      st.hobs_pt[st.c + rr] = pt_base + sh_act[rr] / T;
+      st.hobs_task[st.c + rr] = sh_act[rr] % T;
+    }
+  if (tri_ok) {
+    // Factor in shared memory: warp 0 solves for beta_new (a serial chain of qa rows) WHILE the other warps write the new rows
+    // and complete the touched diagonal blocks' transposed inverses -- none of the three needs the others' results.
+    if (tid < 32) {
+      double* beta = st.beta_h + (size_t)b * st.c_cap + st.c;
+      const double* yb = ylab + (size_t)b * q;
+      for (int rr = tid; rr < qa; rr += 32) sh_beta[rr] = yb[sh_act[rr]] - mu[sh_act[rr]];
+      __syncwarp();
+      for (int rr = 0; rr < qa; ++rr) {
+        double acc = 0.0;
+        for (int ss = tid; ss < rr; ss += 32) acc += dyn_tri[rr * (rr + 1) / 2 + ss] * sh_beta[ss];
+        acc = warp_sum(acc);
+        if (tid == 0) sh_beta[rr] = (sh_beta[rr] - acc) / dyn_tri[rr * (rr + 1) / 2 + rr];
+        __syncwarp();
+      }
+      for (int rr = tid; rr < qa; rr += 32) beta[rr] = sh_beta[rr];
+      return;
+    }
+    const int wt = tid - 32, wnt = nt - 32;  // the writers
+    // new rows k = c + rr, written column by column (rr fastest: contiguous within a column)
+    for (int idx = wt; idx < qa * n; idx += wnt) {
+      int k = idx / qa, rr = idx % qa;
+      *own_entry(st, b, st.c + rr, k) = W[(size_t)k * q + sh_act[rr]];
+    }
+    for (int idx = wt; idx < qa * qa; idx += wnt) {
+      int ss = idx / qa, rr = idx % qa;
+      if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = dyn_tri[rr * (rr + 1) / 2 + ss];
+      else if (ss == rr) *own_entry(st, b, st.c + rr, n + rr) = 1.0 / dyn_tri[rr * (rr + 1) / 2 + rr];
+    }
+    // transposed inverses of the 8 x 8 diagonal blocks the new rows touch (gpmpc_state.cuh; same arithmetic, same order as
+    // warp_update_dinv): one warp per block, LANE j < 8 owns column j of the block's inverse in registers,
+    //   inv[i][j] = -(1 / L_ii) * sum_{t = j}^{i - 1} L[i][t] inv[t][j],   inv[j][j] = 1 / L_jj,
+    // fed from the factor in shared memory (new rows and columns), from W (new rows under old columns of a block that was
+    // partly filled before) and from the old rows' slots in global memory -- nothing this kernel itself writes is read back.
+    const int lane = tid & 31, wi = (tid >> 5) - 1, wn = (nt >> 5) - 1, c0 = st.c;
+    for (int kb = (c0 & ~7) + 8 * wi; kb < c0 + qa; kb += 8 * wn) {
+      if (lane >= 8) continue;
+      const int jc = lane;
+      double invc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = kb + i;  // own row
+        invc[i] = 0.0;
+        if (k >= c0 + qa) continue;
+        if (k < c0) {
+          // an old row of a partly filled block: its slots are complete
+          if (i == jc) invc[i] = __ldcg(own_entry(st, b, k, st.m + k));
+          else if (i > jc) invc[i] = __ldcg(own_entry(st, b, kb + jc, st.m + k));
+          continue;
+        }
+        const int rr = k - c0;
+        const double rd = 1.0 / dyn_tri[rr * (rr + 1) / 2 + rr];
+        if (i == jc) invc[i] = rd;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (t < i) {
+            const int oc = kb + t;  // own column
+            const double lit = oc < c0 ? W[(size_t)(st.m + oc) * q + sh_act[rr]] : dyn_tri[rr * (rr + 1) / 2 + (oc - c0)];
+            if (t >= jc) acc = fma(lit, invc[t], acc);
+          }
+        }
+        if (jc < i) {
+          invc[i] = -rd * acc;
+          __stcg(own_entry(st, b, kb + jc, st.m + k), invc[i]);
+        }
+      }
+    }
+    return;
+  }
   // new rows k = c + rr, written column by column (rr fastest: contiguous within a column)
   for (int idx = tid; idx < qa * n; idx += nt) {
     int k = idx / qa, rr = idx % qa;
@@ -536,13 +626,11 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   }
   for (int idx = tid; idx < qa * qa; idx += nt) {
     int ss = idx / qa, rr = idx % qa;
-    if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = tri_ok ? dyn_tri[rr * (rr + 1) / 2 + ss] : C[(size_t)rr * qa + ss];
-    else if (ss == rr)
-      *own_entry(st, b, st.c + rr, n + rr) = 1.0 / (tri_ok ? dyn_tri[rr * (rr + 1) / 2 + rr] : C[(size_t)rr * qa + rr]);
+    if (ss < rr) *own_entry(st, b, st.c + rr, n + ss) = C[(size_t)rr * qa + ss];
+    else if (ss == rr) *own_entry(st, b, st.c + rr, n + rr) = 1.0 / C[(size_t)rr * qa + rr];
   }
   // beta_new = L_nn^{-1} (y - mu): forward substitution by one warp, the partial solution kept in shared memory
   // (sh_beta aliases nothing: 512 doubles) so that a row costs a shared-memory round trip, not an L2 one
-  __shared__ double sh_beta[512];
   if (tid < 32) {
     double* beta = st.beta_h + (size_t)b * st.c_cap + st.c;
     const double* yb = ylab + (size_t)b * q;
@@ -550,15 +638,9 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     __syncwarp();
     for (int rr = 0; rr < qa; ++rr) {
       double acc = 0.0;
-      if (tri_ok)
-        for (int ss = tid; ss < rr; ss += 32) acc += dyn_tri[rr * (rr + 1) / 2 + ss] * sh_beta[ss];
-      else
-        for (int ss = tid; ss < rr; ss += 32) acc += C[(size_t)rr * qa + ss] * sh_beta[ss];
+      for (int ss = tid; ss < rr; ss += 32) acc += C[(size_t)rr * qa + ss] * sh_beta[ss];
       acc = warp_sum(acc);
-      if (tid == 0) {
-        const double lrr = tri_ok ? dyn_tri[rr * (rr + 1) / 2 + rr] : C[(size_t)rr * qa + rr];
-        sh_beta[rr] = (sh_beta[rr] - acc) / lrr;
-      }
+      if (tid == 0) sh_beta[rr] = (sh_beta[rr] - acc) / C[(size_t)rr * qa + rr];
       __syncwarp();
     }
     for (int rr = tid; rr < qa; rr += 32) beta[rr] = sh_beta[rr];
@@ -567,9 +649,4 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
   // transposed inverses of the 8 x 8 diagonal blocks the new rows touch: the blocks are independent, one warp each
   for (int kb = (st.c & ~7) + 8 * (tid >> 5); kb < st.c + qa; kb += 8 * (nt >> 5))
     warp_update_dinv(st, b, max(kb, st.c), min(kb + 8, st.c + qa), tid & 31);
-  if (b == 0)
-    for (int rr = tid; rr < qa; rr += nt) {
-      st.hobs_pt[st.c + rr] = pt_base + sh_act[rr] / T;
-      st.hobs_task[st.c + rr] = sh_act[rr] % T;
-    }
 }

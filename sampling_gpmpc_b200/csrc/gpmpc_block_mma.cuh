@@ -342,12 +342,31 @@ k_pm_gram(DevState st, const double* __restrict__ x, int H) {
   }
 }
 
-// mean / variance out, then the draw (tri_ok: q(q+1)/2 doubles of dynamic shared memory for the packed Cholesky)
+// mean / variance out, then the draw (tri_ok: q(q+1)/2 doubles of dynamic shared memory for the packed Cholesky).
+// pre_kind != 0 (grid.y = 2): the CTAs with blockIdx.y = 1 factorise, at the same time, the matrix the append that follows
+// will need -- chol(Sigma_app + noise), Sigma_app = st.S (1) or st.S2 (2: the hallucinated set is about to be reset), all
+// scalars active -- into st.Lpre: the second q x q Cholesky of an SQP linearisation leaves the critical path
+// (same fill expression and the same block_cholesky_packed as k_append: bit-identical factor).
 __global__ void __launch_bounds__(BLK_THREADS)
 k_pm_finish(DevState st, int H, double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ eps,
-            gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level, int tri_ok) {
+            gpmpc_sample_opts opts, double* __restrict__ y, int* __restrict__ jitter_level, int tri_ok, int pre_kind) {
   extern __shared__ __align__(16) double dyn_tri[];
   const int b = blockIdx.x, q = H * st.T;
+  if (blockIdx.y == 1) {
+    const int tid = threadIdx.x, nt = blockDim.x, T = st.T;
+    const double* Sa = (pre_kind == 2 ? st.S2 : st.S) + (size_t)b * q * q;
+    const double* noise = st.noise + (b % st.g_ny) * T;
+    const int ntri = q * (q + 1) / 2;
+    for (int idx = tid; idx < q * q; idx += nt) {
+      const int r = idx / q, s2 = idx - r * q;
+      if (s2 <= r) dyn_tri[r * (r + 1) / 2 + s2] = Sa[idx] + (s2 == r ? noise[r % T] : 0.0);
+    }
+    const int info = block_cholesky_packed(dyn_tri, q);
+    double* out = st.Lpre + (size_t)b * (ntri + 1);
+    for (int idx = tid; idx < ntri; idx += nt) out[idx] = dyn_tri[idx];
+    if (tid == 0) out[ntri] = (double)info;
+    return;
+  }
   const double* S = st.S + (size_t)b * q * q;
   const double* mu = st.mu + (size_t)b * q;
   for (int r = threadIdx.x; r < q; r += blockDim.x) {

@@ -90,6 +90,8 @@ struct DevState {
   double* mu2;          // [B][q]     reset, agent.py:261-272: k_append then needs no second posterior pass); NULL: not wanted
   double* xc;           // [B][H][d]  test points the cache was built for
   double* E;            // [B][q][q]  iteration matrix of the eigen-root fallback when it does not fit in shared memory
+  double* Lpre;         // [B][q(q+1)/2 + 1]  packed chol(Sigma_app + noise) + its info word, factorised beside the draw by
+                        //   k_pm_finish's second CTA row for the k_append that follows (gpmpc_linearise); NULL: not allocated
 };
 
 // cov( task ta of f at xa , task tb of f at xb ) for the scaled SE kernel with derivative tasks
