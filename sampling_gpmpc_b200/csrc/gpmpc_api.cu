@@ -16,6 +16,7 @@
 #include "gpmpc_post.cuh"
 #include "gpmpc_step.cuh"
 #include "gpmpc_block_mma.cuh"
+#include "gpmpc_k0.cuh"
 #include "gpmpc_horizon.cuh"
 #include "gpmpc_eig.cuh"
 #include "gpmpc_rng.cuh"
@@ -526,26 +527,40 @@ int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void*
     if (rc) return rc;
   }
   {
-    CUDA_TRY(h, opt_in_smem(h, k_factor_real, h->max_dyn_smem));
-    CUDA_TRY(h, opt_in_smem(h, k_invert_real, h->max_dyn_smem));
-    int k0b_warps = K0B_WARPS;  // one column of inv(L_oo) per warp, m doubles of shared memory each
-    while (k0b_warps > 1 && (size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem) k0b_warps >>= 1;
-    if ((size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem)
-      return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~29000)");
-    // m in the thousands: the factorisation cooperatively over all SMs (one grid barrier per pivot); GPMPC_K0_COOP_MIN_M
-    int coop_min_m = 768;
-    if (const char* e = getenv("GPMPC_K0_COOP_MIN_M")) coop_min_m = atoi(e);
     int coop_ok = 0;
     cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, h->device);
-    if (coop_ok && m >= coop_min_m && (size_t)m * 16 + 1024 <= (size_t)h->max_dyn_smem) {
-      CUDA_TRY(h, opt_in_smem(h, k_factor_real_coop, h->max_dyn_smem));
+    // m in the thousands: blocked factorisation + strip-wise inverse on the tensor cores (gpmpc_k0.cuh; 2.7 s -> ~0.1 s at
+    // m = 10^4); below GPMPC_K0_BLOCKED_MIN_M the per-pivot kernels, whose results the reference-sized tests are pinned to
+    int blocked_min_m = 768;
+    if (const char* e = getenv("GPMPC_K0_BLOCKED_MIN_M")) blocked_min_m = atoi(e);
+    if (coop_ok && m >= blocked_min_m) {
+      const size_t smem = (size_t)3 * K0P * K0P_LD * sizeof(double);
+      CUDA_TRY(h, opt_in_smem(h, k_factor_real_blocked, (int)smem));
       void* args[] = {(void*)&st};
-      CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)k_factor_real_coop, dim3(h->num_sms), dim3(K0_THREADS), args,
-                                              (size_t)m * 16, stream));
+      CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)k_factor_real_blocked, dim3(h->num_sms), dim3(K0F_THREADS), args, smem, stream));
+      const int Pm = (m + 7) / 8;
+      k_invert_real_mma<<<dim3((Pm + 1) / 2, g_ny), K0I_WARPS * 32, 0, stream>>>(st);
+      k_beta_from_inverse<<<dim3((Pm + 3) / 4, g_ny), 128, 0, stream>>>(st);
     } else {
-      k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
+      CUDA_TRY(h, opt_in_smem(h, k_factor_real, h->max_dyn_smem));
+      CUDA_TRY(h, opt_in_smem(h, k_invert_real, h->max_dyn_smem));
+      int k0b_warps = K0B_WARPS;  // one column of inv(L_oo) per warp, m doubles of shared memory each
+      while (k0b_warps > 1 && (size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem) k0b_warps >>= 1;
+      if ((size_t)m * 8 * k0b_warps > (size_t)h->max_dyn_smem)
+        return fail(h, GPMPC_ERR_ARG, "more observed real scalars than K0 supports (m <= ~29000)");
+      // m in the thousands: the factorisation cooperatively over all SMs (one grid barrier per pivot); GPMPC_K0_COOP_MIN_M
+      int coop_min_m = 768;
+      if (const char* e = getenv("GPMPC_K0_COOP_MIN_M")) coop_min_m = atoi(e);
+      if (coop_ok && m >= coop_min_m && (size_t)m * 16 + 1024 <= (size_t)h->max_dyn_smem) {
+        CUDA_TRY(h, opt_in_smem(h, k_factor_real_coop, h->max_dyn_smem));
+        void* args[] = {(void*)&st};
+        CUDA_TRY(h, cudaLaunchCooperativeKernel((void*)k_factor_real_coop, dim3(h->num_sms), dim3(K0_THREADS), args,
+                                                (size_t)m * 16, stream));
+      } else {
+        k_factor_real<<<g_ny, K0_THREADS, (size_t)m * 8, stream>>>(st);
+      }
+      k_invert_real<<<dim3((m + k0b_warps - 1) / k0b_warps, g_ny), k0b_warps * 32, (size_t)m * 8 * k0b_warps, stream>>>(st);
     }
-    k_invert_real<<<dim3((m + k0b_warps - 1) / k0b_warps, g_ny), k0b_warps * 32, (size_t)m * 8 * k0b_warps, stream>>>(st);
     h->launches++;
   }
   h->launches++;
