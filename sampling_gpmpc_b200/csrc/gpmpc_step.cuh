@@ -214,14 +214,16 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // byte offset of this lane's A-fragment element (row gid, column tig) inside a k-block
 __device__ __forceinline__ uint32_t a_lane_off(int gid, int tig) { return (uint32_t)sp_idx(tig, gid) * 8; }
 
+// bf: the B-fragment registers, kept by the caller across calls (the dead lanes never load them: any finite-or-not value does,
+// so zeroing them per call -- four instructions, ~16 calls per element-step -- is not needed)
 template <int T>
-__device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint32_t wa, int n4) {
+__device__ __forceinline__ void mma_accumulate(double (&c)[4], double (&bf)[4], uint32_t la, uint32_t wa, int n4) {
   constexpr int WSTEP = 4 * T * 8;  // bytes of w per 4 columns
   // B fragments: only T < 8 of the 8 columns are live; the dead ones belong to the lanes with gid >= T -- for T <= 4 the
   // whole upper half-warp -- which issue no shared-memory access at all (their wavefront disappears; stale register
   // values only ever reach accumulator columns nobody reads)
   const uint32_t live = (T >= 8 || ((threadIdx.x & 31) >> 2) < T) ? 1u : 0u;
-  double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+  double &b0 = bf[0], &b1 = bf[1], &b2 = bf[2], &b3 = bf[3];
   int it = 0;
   for (; it + 4 <= n4; it += 4) {
     const double a0 = lds<0>(la), a1 = lds<256>(la), a2 = lds<512>(la), a3 = lds<768>(la);
@@ -247,6 +249,11 @@ __device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint
     dmma(c[0], c[1], a0, b0);
     dmma(c[2], c[3], a1, b1);
   }
+}
+template <int T>
+__device__ __forceinline__ void mma_accumulate(double (&c)[4], uint32_t la, uint32_t wa, int n4) {
+  double bf[4] = {0.0, 0.0, 0.0, 0.0};
+  mma_accumulate<T>(c, bf, la, wa, n4);
 }
 
 // Finishes one sub-panel: rows n_off .. n_off+7 of wv (shared address wblk) hold the kernel entries, c the
@@ -399,6 +406,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
 #pragma unroll
   for (int i = 0; i < STEP_NST; ++i) produce_one();
   unsigned cons_slot = 0, cons_parity = 0;  // slot / phase parity of the chunk being consumed
+  double bfrag[4] = {0.0, 0.0, 0.0, 0.0};   // B-fragment registers of mma_accumulate, kept across its calls
 
   // this element's test input and base samples are loaded one element ahead
   double xs_n[D];
@@ -444,76 +452,50 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
     }
 
     // ---- A: kernel vector, one exp per training POINT (and the element's beta) ------------------------------
-    // hallucinated points first: their global loads overlap with the real points' arithmetic
-    for (int p0 = 0; p0 < np; p0 += 64) {
-      const int pa = p0 + lane, pb = pa + 32;
-      int ra = pa < np ? sHrow[pa] : -1, rb = pb < np ? sHrow[pb] : -1;
-      if (st.pstate) {
-        // grouped rollout: a masked / dropped point keeps its (null) factor rows but contributes no kernel entries
-        const unsigned char* ps = st.pstate + (size_t)b * st.cap_points;
-        if (ra >= 0 && ps[pa]) ra = -2 - ra;
-        if (rb >= 0 && ps[pb]) rb = -2 - rb;
-      }
-      double xa[D], xb[D], ba[T], bb[T];
-      if (ra >= 0) {
-#pragma unroll
-        for (int a = 0; a < D; ++a) xa[a] = Xb[(size_t)pa * D + a];
-#pragma unroll
-        for (int r = 0; r < T; ++r) ba[r] = bh[ra + r];
-      }
-      if (rb >= 0) {
-#pragma unroll
-        for (int a = 0; a < D; ++a) xb[a] = Xb[(size_t)pb * D + a];
-#pragma unroll
-        for (int r = 0; r < T; ++r) bb[r] = bh[rb + r];
-      }
-      if (ra >= 0) {
-        double kb[T][T];
-        kernel_block<D, T>(xa, xs, il, os, kb);
-#pragma unroll
-        for (int ta = 0; ta < T; ++ta) {
-#pragma unroll
-          for (int tb = 0; tb < T; ++tb) wv[(mo + ra + ta) * T + tb] = kb[ta][tb];
-          wb[mo + ra + ta] = ba[ta];
+    // real and hallucinated points share ONE pass over the lanes (point index qi: the n_real real points first, then the np
+    // hallucinated ones): the exp / derivative-block sequence runs once per 32 points of either kind -- separate loops ran it
+    // once for the <= 32 real points and once or twice more for the hallucinated ones, ~150 warp-instructions per pass
+    {
+      const int n_rl = WO ? 0 : st.n_real;
+      for (int q0 = 0; q0 < n_rl + np; q0 += 32) {
+        const int qi = q0 + lane, ph = qi - n_rl;
+        const bool is_real = qi < n_rl;
+        int ra = -1;  // first own row of hallucinated point ph (>= 0: in the factor; <= -2: null rows at -2 - ra)
+        if (!is_real && ph < np) {
+          ra = sHrow[ph];
+          // grouped rollout: a masked / dropped point keeps its (null) factor rows but contributes no kernel entries
+          if (st.pstate && ra >= 0 && st.pstate[(size_t)b * st.cap_points + ph]) ra = -2 - ra;
         }
-      }
-      if (rb >= 0) {
-        double kb[T][T];
-        kernel_block<D, T>(xb, xs, il, os, kb);
+        double xa[D], ba[T];
+        if (is_real) {
 #pragma unroll
-        for (int ta = 0; ta < T; ++ta) {
+          for (int a = 0; a < D; ++a) xa[a] = sXr[qi * D + a];
+        } else if (ra >= 0) {
 #pragma unroll
-          for (int tb = 0; tb < T; ++tb) wv[(mo + rb + ta) * T + tb] = kb[ta][tb];
-          wb[mo + rb + ta] = bb[ta];
+          for (int a = 0; a < D; ++a) xa[a] = Xb[(size_t)ph * D + a];
+#pragma unroll
+          for (int r = 0; r < T; ++r) ba[r] = bh[ra + r];
         }
-      }
-      if (ra <= -2 || rb <= -2) {  // null rows: zero kernel entries, zero beta
+        if (is_real || ra >= 0) {
+          double kb[T][T];
+          kernel_block<D, T>(xa, xs, il, os, kb);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int rr = half ? rb : ra;
-          if (rr <= -2) {
-            const int r0 = -2 - rr;
+          for (int ta = 0; ta < T; ++ta) {
+            const int row = is_real ? sRrow[qi * T + ta] : mo + ra + ta;
+            if (row >= 0) {
 #pragma unroll
-            for (int ta = 0; ta < T; ++ta) {
-#pragma unroll
-              for (int tb = 0; tb < T; ++tb) wv[(mo + r0 + ta) * T + tb] = 0.0;
-              wb[mo + r0 + ta] = 0.0;
+              for (int tb = 0; tb < T; ++tb) wv[row * T + tb] = kb[ta][tb];
+              if (!is_real) wb[row] = ba[ta];
             }
           }
-        }
-      }
-    }
-    for (int p = lane; !WO && p < st.n_real; p += 32) {
-      double xa[D], kb[T][T];
+        } else if (ra <= -2) {  // null rows: zero kernel entries, zero beta
+          const int r0 = -2 - ra;
 #pragma unroll
-      for (int a = 0; a < D; ++a) xa[a] = sXr[p * D + a];
-      kernel_block<D, T>(xa, xs, il, os, kb);
+          for (int ta = 0; ta < T; ++ta) {
 #pragma unroll
-      for (int ta = 0; ta < T; ++ta) {
-        const int row = sRrow[p * T + ta];
-        if (row >= 0) {
-#pragma unroll
-          for (int tb = 0; tb < T; ++tb) wv[row * T + tb] = kb[ta][tb];
+            for (int tb = 0; tb < T; ++tb) wv[(mo + r0 + ta) * T + tb] = 0.0;
+            wb[mo + r0 + ta] = 0.0;
+          }
         }
       }
     }
@@ -525,7 +507,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
       const uint32_t boff = (uint32_t)subpanel_off(p8, 0) * 8;
       double acc[4] = {0.0, 0.0, 0.0, 0.0};
       if (LOO_SMEM) {
-        mma_accumulate<T>(acc, sL_s + boff + a_lane, wv_s + b_lane, 2 * p8 + 2);
+        mma_accumulate<T>(acc, bfrag, sL_s + boff + a_lane, wv_s + b_lane, 2 * p8 + 2);
       } else {
         const double* lp = gL + boff / 8 + a_lane / 8;
         for (int it = 0; it < 2 * p8 + 2; it += 2) {
@@ -562,7 +544,7 @@ k_step(DevState st, const double* __restrict__ x, int grow_factor) {
         int rem = n_off;
         while (rem > 0) {
           const int piece = min(rem, STEP_SEG - cpos);
-          mma_accumulate<T>(acc, ring_s + cons_slot * STEP_SLOT_BYTES + cpos * 64 + a_lane, wa, piece >> 2);
+          mma_accumulate<T>(acc, bfrag, ring_s + cons_slot * STEP_SLOT_BYTES + cpos * 64 + a_lane, wa, piece >> 2);
           wa += piece * T * 8;
           rem -= piece;
           cpos += piece;
