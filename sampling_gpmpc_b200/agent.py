@@ -328,14 +328,14 @@ class Agent:
         independent choices for inputs and labels exactly like the reference) and the model is restored (:438-441).
         X_soln (H+1, ns*nx), U_soln (H, nu), X_kp1 (nx, 1).  base_samples: optional list of (ns, g_ny, 1, T) draws, one per
         rollout step, instead of the library-internal torch.randn of `.sample()` (tests).  Returns samples_left (ns,)."""
-        if self.world_size != 1:
-            raise NotImplementedError("prepare_dynamics_set resamples across the whole population: run it unsharded")
         if self._pending_reset or self.in_dim_y == 1:
             raise NotImplementedError("prepare_dynamics_set follows a completed SQP solve of the derivative model")
         ag, opt = self.params["agent"], self.params["optimizer"]
         ns, dev, eng = self.ns, self.torch_device, self.engine
         var_eps = (ag["tight"]["dyn_eps"] + ag["tight"]["w_bound"]) * np.sqrt(opt["terminal_tightening"]["P"][1][1])
-        X_soln = torch.as_tensor(np.asarray(X_soln), dtype=F64).reshape(-1, ns, self.nx).to(dev)
+        # (sharded: X_soln holds every rank's samples; this rank rolls out its own block and the survivor resampling at the end
+        # is the one exchange of the population, rollout.resample_rejected)
+        X_soln = torch.as_tensor(np.asarray(X_soln), dtype=F64).reshape(-1, self.ns_global, self.nx)[:, self.s_lo:self.s_hi].contiguous().to(dev)
         X_kp1 = torch.as_tensor(np.asarray(X_kp1), dtype=F64).reshape(self.nx, -1).transpose(0, 1).to(dev)  # (1, nx)
         U_soln = torch.as_tensor(np.asarray(U_soln), dtype=F64).to(dev)
         n_stage = X_soln.shape[0]
@@ -348,8 +348,11 @@ class Agent:
         opts = eng.opts()  # the script-level draw: no truncation, no zero-variance rule (agent.py:375-377)
         for i in range(1, n_stage - 1):
             g_xu_hat = self.get_g_xu_hat(xu_hat)
-            eps = (base_samples[i - 1].to(dev, F64) if base_samples is not None else
-                   torch.randn(ns, self.g_ny, self.in_dim_y, 1, dtype=F64, device=dev).reshape(ns, self.g_ny, 1, self.in_dim_y))
+            if base_samples is not None:
+                eps = base_samples[i - 1]
+                eps = (eps[self.s_lo:self.s_hi] if eps.shape[0] == self.ns_global and self.world_size > 1 else eps).to(dev, F64).contiguous()
+            else:
+                eps = torch.randn(ns, self.g_ny, self.in_dim_y, 1, dtype=F64, device=dev).reshape(ns, self.g_ny, 1, self.in_dim_y)
             mean, var, y, jl = eng.posterior(g_xu_hat, eps, opts)
             self.model_i_call = _PosteriorView(mean, var, jl)
             last = i == n_stage - 2
@@ -363,18 +366,14 @@ class Agent:
             xu_hat = xu_next
         eng.truncate_hallucinated(n_h0)  # the forward-sampling set is dropped again
         self._data_version += 1
-        left = samples_left.cpu().numpy()
-        if left.sum() > 0 and (left == 0).any():
-            n_rep = int((left == 0).sum())
-            remaining = np.arange(ns)[left > 0]
-            Xh, Yh = eng.export_hallucinated()
-            dead = torch.as_tensor(np.nonzero(left == 0)[0], device=dev)
-            Xh[dead] = Xh[torch.as_tensor(np.random.choice(remaining, n_rep), device=dev)]
-            Yh[dead] = Yh[torch.as_tensor(np.random.choice(remaining, n_rep), device=dev)]
+        from .rollout import resample_rejected
+        Xh, Yh = eng.export_hallucinated()
+        changed, Xh, Yh, active = resample_rejected(samples_left, Xh, Yh, self.ns_global, self.rank, self.world_size)
+        if changed:
             # the replaced samples' factors: rebuilt by conditioning on the new data set (the reference re-fits, :438-441)
             eng.reset_hallucinated()
             step = max(1, 512 // self.in_dim_y)
-            active = (~Yh.isnan().any(1).any(0)).cpu().numpy().astype(np.uint8)  # GPyTorch's any-over-batch slot mask
+            active = active.reshape(-1, self.in_dim_y)  # (points, T): GPyTorch's any-over-batch slot mask
             for p0 in range(0, Xh.shape[2], step):
                 eng.append_masked(Xh[:, :, p0:p0 + step].contiguous(), Yh[:, :, p0:p0 + step].contiguous(), active[p0:p0 + step])
             self._data_version += 1

@@ -171,6 +171,46 @@ def gather_padded(local: torch.Tensor, ns_global: int, world_size: int) -> torch
     return out[:ns_global]
 
 
+
+def resample_rejected(samples_left: torch.Tensor, Xh: torch.Tensor, Yh: torch.Tensor, ns_global: int, rank: int, world_size: int):
+    """Survivor resampling of Agent.prepare_dynamics_set (src/agent.py:418-436) over a SHARDED population (SURVEY.md 8e:
+    "all-gather of samples_left + index broadcast").  samples_left (ns_local,) int, Xh (ns_local, g_ny, n, d) / Yh
+    (ns_local, g_ny, n, T) = this rank's hallucinated sets.  The reference replaces the data of every rejected sample by
+    that of a random surviving one -- two independent np.random.choice draws from numpy's global generator, one for the
+    inputs and one for the labels, over the WHOLE population: here samples_left and the data sets are all-gathered, rank 0
+    makes the two draws exactly as the reference does (its generator is THE generator) and broadcasts them, and every rank
+    rewrites its own rejected samples.  Returns (changed, Xh, Yh, active): changed = False if nobody or everybody was
+    rejected (nothing to do, like the reference); active (n * T,) uint8 = GPyTorch's any-over-batch slot mask of the new
+    label set, over every rank's samples."""
+    left = gather_padded(samples_left.reshape(-1, 1), ns_global, world_size).reshape(-1).cpu().numpy()
+    if not (left.sum() > 0 and (left == 0).any()):
+        return False, Xh, Yh, None
+    n_rep = int((left == 0).sum())
+    remaining = np.arange(ns_global)[left > 0]
+    if world_size > 1:
+        import torch.distributed as dist
+        pick = torch.zeros(2, n_rep, dtype=torch.int64)
+        if rank == 0:
+            pick[0] = torch.from_numpy(np.random.choice(remaining, n_rep))
+            pick[1] = torch.from_numpy(np.random.choice(remaining, n_rep))
+        pick = pick.to(Xh.device)
+        dist.broadcast(pick, src=0)
+        Xg, Yg = gather_padded(Xh, ns_global, world_size), gather_padded(Yh, ns_global, world_size)
+    else:
+        pick = torch.stack([torch.from_numpy(np.random.choice(remaining, n_rep)),
+                            torch.from_numpy(np.random.choice(remaining, n_rep))]).to(Xh.device)
+        Xg, Yg = Xh, Yh
+    dead = torch.as_tensor(np.nonzero(left == 0)[0], device=Xh.device)
+    Xg, Yg = Xg.clone(), Yg.clone()
+    # (advanced indexing reads the right-hand side before it writes: a rejected sample never copies from another rejected one
+    # anyway, the sources are survivors)
+    Xg[dead] = Xg[pick[0]]
+    Yg[dead] = Yg[pick[1]]
+    active = (~Yg.isnan().any(1).any(0)).reshape(-1).cpu().numpy().astype(np.uint8)
+    lo, hi = shard_bounds(ns_global, rank, world_size)
+    return True, Xg[lo:hi].contiguous(), Yg[lo:hi].contiguous(), active
+
+
 def reduce_filter_counts(counts: torch.Tensor, ns_global: int, world_size: int) -> np.ndarray:
     """counts (g_ny, H) int32 = this shard's samples whose new point h was filtered for output j
     (gpmpc_filter_new_points).  Sum over ranks, then the reference's flags (src/agent.py:186-191 and GPyTorch's

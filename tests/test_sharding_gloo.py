@@ -79,3 +79,67 @@ def test_shard_bounds_properties():
             assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) == -(-ns // world)  # weak scaling: the largest shard is ceil(ns / world)
+
+
+def _resample_worker(rank, world, port, ns_global, q):
+    from sampling_gpmpc_b200.rollout import resample_rejected
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        left, Xh, Yh = _resample_case(ns_global)
+        lo, hi = shard_bounds(ns_global, rank, world)
+        np.random.seed(11 if rank == 0 else 999)  # only rank 0's generator may matter
+        changed, Xl, Yl, active = resample_rejected(left[lo:hi].clone(), Xh[lo:hi].clone(), Yh[lo:hi].clone(), ns_global, rank, world)
+        q.put((rank, lo, hi, changed, Xl.numpy(), Yl.numpy(), None if active is None else active))
+    finally:
+        dist.destroy_process_group()
+
+
+def _resample_case(ns_global):
+    g = torch.Generator().manual_seed(21)
+    left = torch.ones(ns_global, dtype=torch.int32)
+    left[[1, ns_global - 2, ns_global - 1]] = 0          # rejected samples on both ranks
+    Xh = torch.rand(ns_global, 2, 5, 3, generator=g, dtype=torch.float64)
+    Yh = torch.rand(ns_global, 2, 5, 4, generator=g, dtype=torch.float64)
+    Yh[0, 1, 2, 3] = float("nan")                        # a masked label of a SURVIVOR: must reach every rank's slot mask
+    Yh[ns_global - 1, 0, 0, 0] = float("nan")            # ... and one of a rejected sample, which disappears with its data
+    return left, Xh, Yh
+
+
+@pytest.mark.parametrize("ns_global", [9, 8])
+def test_two_rank_survivor_resampling_equals_single_process(ns_global):
+    """prepare_dynamics_set's survivor resampling (src/agent.py:418-436) over a sharded population: all-gather of samples_left
+    and of the data sets, rank 0's two np.random.choice draws broadcast -- every rank ends up with exactly its block of what
+    ONE process computes from the same generator state, and with the population-wide NaN slot mask."""
+    from sampling_gpmpc_b200.rollout import resample_rejected
+    left, Xh, Yh = _resample_case(ns_global)
+    np.random.seed(11)
+    changed, X1, Y1, act1 = resample_rejected(left.clone(), Xh.clone(), Yh.clone(), ns_global, 0, 1)
+    assert changed and not torch.equal(X1, Xh)
+    # the reference's own statement sequence on the same generator state
+    np.random.seed(11)
+    remaining = np.arange(ns_global)[left.numpy() > 0]
+    dead = np.nonzero(left.numpy() == 0)[0]
+    Xr, Yr = Xh.clone(), Yh.clone()
+    Xr[dead] = Xr[np.random.choice(remaining, dead.size)]
+    Yr[dead] = Yr[np.random.choice(remaining, dead.size)]
+    assert torch.equal(X1, Xr) and torch.equal(torch.nan_to_num(Y1, nan=-7.0), torch.nan_to_num(Yr, nan=-7.0))
+    assert np.array_equal(act1, (~Yr.isnan().any(1).any(0)).reshape(-1).numpy().astype(np.uint8)) and act1.sum() < act1.size
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_resample_worker, args=(r, world, port, ns_global, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, lo, hi, ch, Xl, Yl, active in res:
+        assert ch
+        assert np.array_equal(Xl, X1[lo:hi].numpy())
+        assert np.array_equal(np.nan_to_num(Yl, nan=-7.0), np.nan_to_num(Y1[lo:hi].numpy(), nan=-7.0))
+        assert np.array_equal(active, act1)
+    # nobody rejected / everybody rejected: nothing happens, as in the reference
+    for pattern in (torch.ones(ns_global, dtype=torch.int32), torch.zeros(ns_global, dtype=torch.int32)):
+        ch, X2, Y2, _ = resample_rejected(pattern, Xh, Yh, ns_global, 0, 1)
+        assert not ch and X2 is Xh
