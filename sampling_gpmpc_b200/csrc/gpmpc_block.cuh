@@ -67,7 +67,7 @@ __device__ int block_cholesky_wide(double* A, int n, int ld, double* scol) {
 // The same factorisation on a PACKED lower triangle in shared memory (P[r(r+1)/2 + s], s <= r): the q x q matrices of
 // the SQP-mode draw / append are latency bound in global memory (three L2 round trips per pivot); in shared memory a
 // pivot step costs a few hundred cycles.  Same pivot test, same return value.
-__device__ int block_cholesky_packed(double* P, int n) {
+__device__ int block_cholesky_packed_pivotwise(double* P, int n) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;  // 16 columns x (nt / 16) rows of the trailing block per pass
   for (int k = 0; k < n; ++k) {
@@ -87,6 +87,84 @@ __device__ int block_cholesky_packed(double* P, int n) {
   }
   __syncthreads();
   return 0;
+}
+
+// The same arithmetic, entry by entry and in the same order (every entry takes its updates  a -= L[i][k] L[c][k]  for ascending
+// k, each one fused multiply-add, then the same division / square root: BIT-IDENTICAL factors), organised in panels of 8
+// columns: inside a panel a thread owns one row and keeps its 8 entries in registers (left-looking: column c takes the updates
+// of the panel's earlier columns when its turn comes; one CTA barrier per pivot, the pivot row handed on through shared
+// memory), then the trailing triangle takes all 8 updates of an entry in one pass (one load and one store per entry instead of
+// 8, two barriers per panel instead of 16).  The pivot-wise form above costs ~1100 clk per pivot at q = 51, nearly all of it
+// barriers and shared-memory round trips of the trailing update; here the chain per pivot is sqrt + division + one barrier.
+// n > blockDim.x: the pivot-wise form (a thread holds one row of the panel).  GPMPC_CHOL_PIVOTWISE=1 at build time selects
+// the pivot-wise form everywhere (tools/chol_ab.py: bit-equality and timing of the two).
+__device__ int block_cholesky_packed(double* P, int n) {
+#ifdef GPMPC_CHOL_PIVOTWISE
+  return block_cholesky_packed_pivotwise(P, n);
+#else
+  if (n > (int)blockDim.x) return block_cholesky_packed_pivotwise(P, n);
+  __shared__ double s_row[2][8];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;
+  int par = 0;
+  __syncthreads();  // the caller's fill is complete
+  for (int b0 = 0; b0 < n; b0 += 8) {
+    const int nbk = min(8, n - b0);
+    const int i = b0 + tid;  // this thread's row of the panel
+    const bool mine = i < n;
+    const int ro = i * (i + 1) / 2 + b0;
+    double a[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = (mine && c < nbk && b0 + c <= i) ? P[ro + c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      if (c < nbk) {  // (uniform)
+        if (tid == c) {  // the pivot row b0 + c: complete its diagonal entry, hand the row on
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < c) a[c] = fma(-a[k], a[k], a[c]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k <= c) s_row[par][k] = a[k];
+        }
+        __syncthreads();
+        const double akk = s_row[par][c];
+        if (!(akk > 0.0)) return b0 + c + 1;  // uniform: every thread reads the same value
+        const double lkk = sqrt(akk);
+        if (tid == c) {
+          a[c] = lkk;
+        } else if (mine && tid > c) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k < c) a[c] = fma(-a[k], s_row[par][k], a[c]);
+          a[c] = a[c] / lkk;
+        }
+        par ^= 1;  // (the buffer is rewritten two pivots later: every thread has passed the next pivot's barrier by then)
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (mine && c < nbk && b0 + c <= i) P[ro + c] = a[c];
+    __syncthreads();
+    const int t0 = b0 + nbk;  // first trailing column
+    for (int i2 = t0 + ty; i2 < n; i2 += ny) {
+      const int r2 = i2 * (i2 + 1) / 2;
+      double li[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) li[k] = k < nbk ? P[r2 + b0 + k] : 0.0;
+      for (int cc = t0 + tx; cc <= i2; cc += 16) {
+        const int rc = cc * (cc + 1) / 2 + b0;
+        double v = P[r2 + cc];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < nbk) v = fma(-li[k], P[rc + k], v);
+        P[r2 + cc] = v;
+      }
+    }
+    __syncthreads();
+  }
+  return 0;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
