@@ -64,6 +64,7 @@ struct gpmpc_handle {
   // chol(Sigma_app + noise) factorised beside the draw for the append that follows (k_pm_finish's second CTA row -> st.Lpre):
   // requested by gpmpc_linearise; pre_kind 1 = against the current factor (valid while factor_version == pre_version),
   // 2 = against the real data alone (valid for the append right after a reset), 0 = none
+  uint32_t* status_pinned = nullptr;  // pinned staging word of gpmpc_status
   bool prefactor_next = false;
   int pre_kind = 0, pre_H = 0;
   long long pre_version = -1;
@@ -350,7 +351,7 @@ static int dispatch_posterior_mma(gpmpc_handle* h, const DevState& st, const dou
 
 extern "C" {
 
-const char* gpmpc_version(void) { return "gpmpc_b200 0.3 (sm_100a)"; }
+const char* gpmpc_version(void) { return "gpmpc_b200 0.4 (sm_100a)"; }
 
 int64_t gpmpc_base_samples(uint8_t* rng_state, int64_t state_bytes, int64_t slots, int64_t n, double beta, double* out) {
   if (!rng_state || !out || state_bytes != (int64_t)gpmpc_rng::STATE_BYTES || slots < 0 || n < 1 || !(beta > 0.0))
@@ -413,6 +414,7 @@ int gpmpc_destroy(gpmpc_handle* h) {
   cudaFree((void*)st.Xr); cudaFree((void*)st.obs_pt); cudaFree((void*)st.obs_task); cudaFree((void*)st.y_obs);
   cudaFree((void*)st.ls); cudaFree((void*)st.os); cudaFree((void*)st.noise);
   cudaFree(st.Loo); cudaFree(st.LooP); cudaFree(st.beta_o); cudaFree(st.status); cudaFree(st.fin); cudaFree(st.Wo);
+  if (h->status_pinned) cudaFreeHost(h->status_pinned);
   cudaFree(st.W); cudaFree(st.S); cudaFree(st.C); cudaFree(st.mu); cudaFree(st.xc); cudaFree(st.E); cudaFree(st.Lpre); cudaFree(st.eig_flag);
   cudaFree(h->S2buf); cudaFree(h->mu2buf);
   cudaFree(h->r_xu); cudaFree(h->r_xstar); cudaFree(h->r_y); cudaFree(h->d_active); cudaFree(h->c_scratch);
@@ -1560,9 +1562,13 @@ int gpmpc_export_point_states(const gpmpc_handle* h_, uint8_t* out, void* stream
 int gpmpc_status(gpmpc_handle* h, uint32_t* status, int32_t clear, void* stream) {
   ON_HANDLE_DEVICE(h);
   if (!h || !status) return fail(h, GPMPC_ERR_ARG, "null argument");
-  CUDA_TRY(h, cudaMemcpyAsync(status, h->st.status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  // through a pinned staging word: a device->pageable copy goes through the driver's bounce buffer and costs ~10 us more per
+  // SQP linearisation (the status is read once per linearisation, behind the outputs' own copy)
+  if (!h->status_pinned) CUDA_TRY(h, cudaHostAlloc((void**)&h->status_pinned, sizeof(uint32_t), cudaHostAllocDefault));
+  CUDA_TRY(h, cudaMemcpyAsync(h->status_pinned, h->st.status, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   if (clear) CUDA_TRY(h, cudaMemsetAsync(h->st.status, 0, 4, (cudaStream_t)stream));
   CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+  *status = *h->status_pinned;
   return GPMPC_OK;
 }
 
