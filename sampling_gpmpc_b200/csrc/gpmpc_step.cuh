@@ -699,7 +699,11 @@ k_shared_rows(DevState st, const double* __restrict__ x, int k_lo, int k_hi) {
     // panels longest first, dealt to the warps in serpentine order (0 .. nw-1, nw-1 .. 0, ...): panel p costs 2 (p + 1)
     // k-steps, so plain round-robin leaves warp 0 with 90 of them and warp 7 with 48 at m = 180 (8 warps); this way 76 / 62
     for (int rnd = 0;; ++rnd) {
+#ifdef GPMPC_SR_ROUND_ROBIN
+      const int pi = rnd * nw + warp;
+#else
       const int pi = rnd * nw + ((rnd & 1) ? nw - 1 - warp : warp);
+#endif
       if (rnd * nw >= Pm - p_first) break;
       if (pi >= Pm - p_first) continue;
       const int p = Pm - 1 - pi;
