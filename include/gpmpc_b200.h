@@ -139,7 +139,9 @@ int gpmpc_export_point_states(const gpmpc_handle* h, uint8_t* out, void* stream)
  *                          the batch-wide eigen-root fallback of a failed jitter ladder: it flags GPMPC_ST_SAMPLE_NOT_PD and
  *                          the caller repeats the rollout with "rollout_fused" 0 -- rollout.ForwardRollout does),
  *        "hz_groups"      (cap on the samples one CTA of the fused kernel holds at a time; 0 = as many as fit),
- *        "hz_stagger_ns"  (spread of the sample groups' start times in the fused kernel; -1 = automatic, 0 = none).
+ *        "hz_stagger_ns"  (spread of the sample groups' start times in the fused kernel; -1 = automatic, 0 = none),
+ *        "step_warps_cap" / "step_grid_cap" (experiments: warps per CTA / CTAs of the fused step kernel, 0 = no cap; two handles
+ *                          on two streams can then share the SMs -- measured: no gain).
  * The results do not depend on any of them (bit-identical trajectories). */
 int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value);
 /* reads an option back; also "last_rollout_fused" (1 if the last gpmpc_rollout took the one-launch kernel) */
@@ -175,7 +177,8 @@ int gpmpc_set_hypers(gpmpc_handle* h, const double* lengthscale, const double* o
                      const double* noise, double jitter);
 
 /* Real training data (DEVICE): X[n_real*d], Y[g_ny*n_real*T] with NaN = unobserved slot.  Factorises the
- * shared block once per output (kernel K0) and clears the hallucinated set.  SYNCHRONISES once to read the
+ * shared block once per output (kernel K0; from 768 observed scalars on the blocked tensor-core form of csrc/gpmpc_k0.cuh,
+ * environment GPMPC_K0_BLOCKED_MIN_M moves that switch) and clears the hallucinated set.  SYNCHRONISES once to read the
  * observed-slot count.  Replaces: the real-data part of every ExactGP re-fit (src/agent.py:223-248 ->
  * gpytorch ExactGP / DefaultPredictionStrategy, psd_safe_cholesky of K_oo + Sigma). */
 int gpmpc_set_real_data(gpmpc_handle* h, const double* X, const double* Y, void* stream);
