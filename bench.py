@@ -326,6 +326,7 @@ def extras(torch, device, cpu_leg=True):
             ee = torch.randn(20, 3, Hc, 3, generator=gd, dtype=torch.float64, device=device).clamp(-3, 3)
             torch.cuda.synchronize()
             e0.record()
+            eng.set_option("prefactor_next", 1)  # the append below follows: its Cholesky runs beside the draw's (as in gpmpc_linearise)
             _, _, yq, _ = eng.posterior(xq, ee, eng.opts(beta=3.0))
             eng.append(xq, yq)
             e1.record()

@@ -1623,6 +1623,7 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
   else if (n == "step_grid_cap") h->step_grid_cap = (int)value;
   else if (n == "step_warps_cap") h->step_warps_cap = (int)value;
+  else if (n == "prefactor_next") h->prefactor_next = value != 0 && h->condition;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;
   else if (n == "force_block_fallback") h->force_block_fallback = value != 0;
