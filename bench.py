@@ -359,6 +359,7 @@ def extras(torch, device, cpu_leg=True):
 
 
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from sampling_gpmpc_b200 import configs
@@ -468,11 +469,32 @@ def run_ours(args):
         barrier()
         t_ag = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
         dist.all_reduce(t_ag, op=dist.ReduceOp.MAX)
+        # the same consumers without the gather: every rank reduces its own shard, only the reductions travel
+        # (ForwardRollout.stage_boxes / stage_hulls: an all-reduce of 2 x (nx, H+1) doubles, an all-gather of the hull vertices)
+        def reduced_step():
+            fr.run(u_dev, eps_dev, traj)
+            lo_r, hi_r = fr.stage_boxes(traj)
+            return lo_r, hi_r, fr.stage_hulls(traj, 0, 1)
+        lo_r, hi_r, hulls_r = reduced_step()
+        reduced_ok = bool(torch.equal(lo_r, lo)) and bool(torch.equal(hi_r, hi)) and len(hulls_r) == len(hulls) and \
+            all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(hulls_r, hulls))
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            reduced_step()
+        e1.record()
+        barrier()
+        t_r = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
         gathered = {"value": world * ns * HORIZON / (float(t_g.item()) / args.steps * 1e-3), "unit": UNIT,
                     "ms_per_step": float(t_g.item()) / args.steps,
                     "all_gather_ms": float(t_ag.item()) / args.steps, "all_gather_bytes": int(allt.numel() * 8),
                     "hull_vertices_stage_last": int(len(hulls[-1])),
-                    "what": "rollout + all_gather_into_tensor of the trajectories + stage boxes + stage hulls, max over ranks"}
+                    "what": "rollout + all_gather_into_tensor of the trajectories + stage boxes + stage hulls, max over ranks",
+                    "reduced": {"value": world * ns * HORIZON / (float(t_r.item()) / args.steps * 1e-3), "unit": UNIT,
+                                "ms_per_step": float(t_r.item()) / args.steps, "equal_to_gathered": reduced_ok,
+                                "what": "rollout + the same consumers WITHOUT the gather: local boxes / hulls per rank, all-reduce "
+                                        "of the boxes, all-gather of the hull vertices only (bit-identical results)"}}
         del allt
         # sharded vs single GPU, bit for bit, at a size one GPU holds: rank 0 rolls the WHOLE population out alone
         ns_chk = 2048

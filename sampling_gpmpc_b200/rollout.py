@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .agent import gp_hypers_from_params
-from .engine import GPEngine, make_env_struct
+from .engine import GPEngine, hull2d, make_env_struct
 from .envs import make_env_spec
 
 F64 = torch.float64
@@ -132,6 +132,56 @@ class ForwardRollout:
     def all_gather_trajectories(self, traj: torch.Tensor) -> torch.Tensor:
         """(ns_local, nx, steps+1) per rank -> (ns_global, nx, steps+1) on every rank: one NCCL all-gather."""
         return gather_padded(traj, self.ns_global, self.world_size)
+
+    # ---- the trajectory consumers WITHOUT the gather: each rank reduces its own shard, only the reductions travel ----------
+    def stage_boxes(self, traj: torch.Tensor, ref: Optional[torch.Tensor] = None):
+        """Per-stage bounding box [and max-deviation tightening max_n |x_k^n - ref_k|] of ALL ranks' trajectories
+        (generate_convex_hull.py:83-87; extra/approx_sampling_mpc/README.md:19-27) from this rank's shard traj
+        (ns_local, nx, H1): min / max are exact and order-free, so the local reduction (gpmpc_traj_stats) followed by an
+        all-reduce of the (nx, H1) results -- 3 x 1.6 KB at the car shape -- is bit-identical to the reduction over the
+        gathered array (1.63 GB at 10^6 samples).  Returns (lo, hi[, max_dev]), the same on every rank."""
+        out = self.engine.traj_stats(traj, ref)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(out[0], op=dist.ReduceOp.MIN)
+            for t in out[1:]:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out
+
+    def stage_hulls(self, traj: torch.Tensor, i0: int = 0, i1: int = 1, max_vertices: int = 512):
+        """Per-stage convex hull of (traj[:, i0, t], traj[:, i1, t]) over ALL ranks' samples (generate_convex_hull.py:88-104)
+        from this rank's shard: hull(union of the shards) = hull(union of the shards' hulls), so every rank takes the hull of its
+        own samples (gpmpc_stage_hulls), the hull VERTICES (coordinates + global sample index; tens of points per stage) are
+        all-gathered, and the final hull of the few candidates is taken on the host (gpmpc_hull2d: the same monotone chain,
+        identical points resolved to the lowest global sample index) -- the same vertex lists as the hull of the gathered
+        array.  Returns a list over the stages of GLOBAL sample-index arrays, counter-clockwise, the same on every rank."""
+        local = self.engine.stage_hulls(traj, i0, i1, max_vertices)
+        if self.world_size == 1:
+            return local
+        import torch.distributed as dist
+        H1 = traj.shape[2]
+        cnt = torch.tensor([max(len(v) for v in local)], dtype=torch.int64, device=traj.device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+        cmax = int(cnt.item())
+        idx = np.zeros((H1, cmax), dtype=np.int64)
+        live = np.zeros((H1, cmax), dtype=bool)
+        for t, v in enumerate(local):
+            idx[t, : len(v)] = v
+            live[t, : len(v)] = True
+        idx_d = torch.from_numpy(idx).to(traj.device)
+        tt = torch.arange(H1, device=traj.device)[:, None].expand(H1, cmax)
+        pack = torch.stack([traj[idx_d, i0, tt], traj[idx_d, i1, tt], (idx_d + self.s_lo).to(F64)], dim=-1)  # (H1, cmax, 3)
+        pack[~torch.from_numpy(live).to(traj.device)] = float("nan")
+        allp = torch.empty((self.world_size, H1, cmax, 3), dtype=F64, device=traj.device)
+        dist.all_gather_into_tensor(allp, pack.contiguous())
+        allp = allp.permute(1, 0, 2, 3).reshape(H1, self.world_size * cmax, 3).cpu().numpy()
+        out = []
+        for t in range(H1):
+            c = allp[t][~np.isnan(allp[t][:, 2])]
+            c = c[np.argsort(c[:, 2], kind="stable")]  # by global sample index: identical points resolve to the lowest one
+            pos = hull2d(np.ascontiguousarray(c[:, :2]))
+            out.append(c[pos, 2].astype(np.int32))
+        return out
 
 
 def save_X_traj(traj: torch.Tensor, save_dir: str, epistemic_idx: int, chunk: Optional[int] = None) -> list:

@@ -27,6 +27,8 @@ def test_sharded_rollout_and_all_gather_equal_single_gpu(ns):
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok"] and res["gathered_equals_single_gpu"] and res["traj_stats_equal"] and res["hulls_equal"]
+    # the consumers without the gather (local reduction, then all-reduce of the boxes / all-gather of the hull vertices only)
+    assert res["reduced_boxes_equal_gathered"] and res["reduced_hulls_equal_gathered"]
     assert res["status"] == [0, 0]
 
 

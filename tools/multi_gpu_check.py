@@ -36,7 +36,28 @@ gather_ms = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
 dist.all_reduce(gather_ms, op=dist.ReduceOp.MAX)
 stats = fr.engine.traj_stats(full)
 hulls = fr.engine.stage_hulls(full)
+# ... and the same consumers WITHOUT the gather: local reductions, only the reductions travel (3 x 1.6 KB + the hull vertices)
+ref_traj = full[0].contiguous()  # a reference trajectory for the max-deviation tightening (identical on every rank)
+stats_g = fr.engine.traj_stats(full, ref_traj)
+stats_d = fr.stage_boxes(traj, ref_traj)
+hulls_d = fr.stage_hulls(traj)
+torch.cuda.synchronize(); dist.barrier()
+e0.record()
+for _ in range(5):
+    fr.stage_boxes(traj, ref_traj); fr.stage_hulls(traj)
+e1.record(); torch.cuda.synchronize()
+red_ms = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
+dist.all_reduce(red_ms, op=dist.ReduceOp.MAX)
+e0.record()
+for _ in range(5):
+    f2 = fr.all_gather_trajectories(traj); fr.engine.traj_stats(f2, ref_traj); fr.engine.stage_hulls(f2)
+e1.record(); torch.cuda.synchronize()
+gat_ms = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
+dist.all_reduce(gat_ms, op=dist.ReduceOp.MAX)
 res = {"ok": True}
+res["reduced_boxes_equal_gathered"] = all(bool(torch.equal(a, b)) for a, b in zip(stats_d, stats_g))
+res["reduced_hulls_equal_gathered"] = len(hulls_d) == len(hulls) and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(hulls_d, hulls))
+res["consumers_ms"] = {"all_gather_then_reduce": float(gat_ms), "reduce_then_exchange": float(red_ms)}
 if rank == 0:
     one = ForwardRollout(params, condition=True)
     ref = one.run(u, eps)
