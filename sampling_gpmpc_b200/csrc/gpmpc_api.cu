@@ -113,6 +113,7 @@ struct gpmpc_handle {
   bool force_big = false;            // tests: k_step_big (+ k-slab GEMM) for any m
   int big_slab_cap = 0;              // tests: cap on the rows of K per GEMM pass (several slabs at small m)
   bool force_block_fallback = false;  // tests: gpmpc_step through posterior + append even where k_step_big applies
+  bool wo_slab_nb3 = true;  // k_step<WO> path, 1200 < m <= 3600: GEMM with 3 column blocks in k-slabs instead of 2 / 1 in one pass
   bool force_wo = false;  // experiment: the batched shared-rows GEMM also for small m (gpmpc_set_option "force_wo")
   int wo_max_nb = 3;  // GPMPC_WO_MAX_NB: cap on the column blocks per tile (tests reach the NB = 2 / 1 instantiations with it)
   // SQP-mode model call: tensor-core kernel k_posterior_mma (default) or the scalar substitution kernel k_posterior
@@ -378,6 +379,7 @@ int gpmpc_create(const gpmpc_dims* dims, gpmpc_handle** out) {
   if (const char* e = getenv("GPMPC_WO_MIN_M")) h->wo_min_m = atoi(e);
   if (const char* e = getenv("GPMPC_BLOCK_SCALAR")) h->block_mma = atoi(e) == 0;
   if (const char* e = getenv("GPMPC_WO_MAX_NB")) h->wo_max_nb = std::min(3, std::max(1, atoi(e)));
+  if (const char* e = getenv("GPMPC_WO_SLAB_NB3")) h->wo_slab_nb3 = atoi(e) != 0;
   if (const char* e = getenv("GPMPC_ROLLOUT_FUSED")) h->fused_rollout = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("GPMPC_HZ_GROUPS")) h->hz_groups_cap = atoi(e);
   if (const char* e = getenv("GPMPC_HZ_STAGGER_NS")) h->hz_stagger_ns = atoll(e);
@@ -976,7 +978,15 @@ static int launch_step(gpmpc_handle* h, const DevState& st, const double* x, con
       }
       DevState stw = st;
       stw.Wo = h->st.Wo;
-      int rc = nb == 3 ? launch_shared_rows<D, T, 3>(h, stw, x, stream)
+      // m beyond the one-pass limit of three column blocks (~1200): rather than fewer column blocks per tile -- inv(L_oo) is then
+      // re-streamed from L2 once per 5.3 / 2.7 samples and the GEMM turns L2-bound (0.28-0.35 of the DMMA peak at m = 2000-3000) --
+      // keep three and walk K in slabs of as many rows as fit, accumulating into Wo ("wo_slab_nb3" 0 switches this off)
+      int slab = 1 << 30;
+      if (nb < 3 && h->wo_max_nb >= 3 && h->wo_slab_nb3) {
+        nb = 3;
+        slab = (int)((budget - 2048) / ((size_t)64 * 3)) & ~7;
+      }
+      int rc = nb == 3 ? launch_shared_rows<D, T, 3>(h, stw, x, stream, slab)
                : nb == 2 ? launch_shared_rows<D, T, 2>(h, stw, x, stream)
                          : launch_shared_rows<D, T, 1>(h, stw, x, stream);
       if (rc) return rc;
@@ -1626,6 +1636,7 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   else if (n == "prefactor_next") h->prefactor_next = value != 0 && h->condition;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;
+  else if (n == "wo_slab_nb3") h->wo_slab_nb3 = value != 0;
   else if (n == "force_block_fallback") h->force_block_fallback = value != 0;
   else if (n == "force_big") h->force_big = value != 0;
   else if (n == "big_slab_cap") h->big_slab_cap = (int)value & ~7;

@@ -76,3 +76,30 @@ def test_m_in_the_thousands_takes_the_slab_path_by_itself():
         assert float((ma - mb).abs().max()) < 1e-8 and float((va - vb).abs().max()) < 1e-8 and float((ya - yb).abs().max()) < 1e-7
         x = (x + 0.05).clamp(-0.9, 0.9)
     assert eng.status() == 0
+
+
+@pytest.mark.parametrize("n_real,slab_on", [(1300, 1), (1300, 0), (2100, 1)])
+def test_mid_m_gemm_in_slabs_with_the_fused_step(n_real, slab_on):
+    """1200 < m <= 3600: k_step<WO> takes the shared rows from the batched GEMM with THREE column blocks walked in k-slabs
+    (accumulating into Wo) instead of two / one in one pass (option "wo_slab_nb3", default on) -- both forms against the scalar
+    substitution kernels."""
+    d, T, ns, g_ny, steps = 2, 3, 5, 2, 4
+    eng = _engine(ns, g_ny, d, T, n_real, 3, False)
+    eng.set_option("wo_slab_nb3", slab_on)
+    ref = _engine(ns, g_ny, d, T, n_real, 3, False)
+    ref.set_block_kernels(False)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(ns, 1, 1, d, generator=g, dtype=torch.float64) * 1.2 - 0.6
+    worst = 0.0
+    for t in range(steps):
+        xx = x.expand(ns, g_ny, 1, d).contiguous()
+        eps = torch.randn(ns, g_ny, 1, T, generator=g, dtype=torch.float64).clamp(-2.5, 2.5)
+        mb, vb, yb, jb = eng.step(xx, eps, eng.opts(beta=3.0))
+        mr, vr, yr, jr = ref.posterior(xx, eps, ref.opts(beta=3.0))
+        ref.append(xx, yb)  # teacher forcing
+        assert torch.equal(jb, jr)
+        for a, b in ((mb, mr), (vb, vr), (yb, yr)):
+            worst = max(worst, float(((a - b).abs() / (RTOL * torch.maximum(b.abs(), torch.tensor(1.0, device=b.device)))).max()))
+        x = (x + 0.1 * torch.randn(ns, 1, 1, d, generator=g, dtype=torch.float64)).clamp(-0.9, 0.9)
+    assert eng.status() == 0 and ref.status() == 0
+    assert worst <= 1.0, f"off by {worst:.3g} x tolerance"
