@@ -143,7 +143,7 @@ int gpmpc_export_point_states(const gpmpc_handle* h, uint8_t* out, void* stream)
  *        "prefactor_next" (1: the next gpmpc_posterior call that draws also factorises Sigma* + noise, beside the draw's own
  *                          Cholesky, for the gpmpc_append of the same points that follows -- what gpmpc_linearise does by itself;
  *                          one-shot, ignored where it does not apply),
- *        "step_warps_cap" / "step_grid_cap" (experiments: warps per CTA / CTAs of the fused step kernel, 0 = no cap; two handles
+ *        "step_warps_cap" / "step_grid_cap" / "sr_grid_cap" (experiments: warps per CTA / CTAs of the fused step kernel, 0 = no cap; two handles
  *                          on two streams can then share the SMs -- measured: no gain).
  * The results do not depend on any of them (bit-identical trajectories). */
 int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value);

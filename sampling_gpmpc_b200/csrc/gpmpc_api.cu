@@ -90,6 +90,7 @@ struct gpmpc_handle {
   int fused_rollout = 0;
   int hz_groups_cap = 0;
   int step_grid_cap = 0;             // > 0: CTAs (= SMs) the step kernel may take; the rest stay free for a concurrent stream
+  int sr_grid_cap = 0;               // > 0: CTAs (= SMs) the shared-rows GEMM may take (experiment: GEMM of one half beside the step of the other)
   int step_warps_cap = 0;            // > 0: warps per CTA of the step kernel (two such CTAs of two streams share an SM)
   long long hz_stagger_ns = -1;      // < 0: automatic (one sample-horizon of the previous fused rollout)
   double hz_last_ms = 0.0;           // device time of the previous fused launch (for the automatic stagger)
@@ -843,7 +844,9 @@ static int launch_shared_rows(gpmpc_handle* h, const DevState& st, const double*
   const int Pm = st.mo / 8;
   const int threads = Pm <= 32 ? 256 : SR_THREADS;
   const int per_sm = threads == 256 && 2 * (smem + 1024) <= (size_t)h->max_dyn_smem ? 2 : 1;
-  dim3 grid(std::min(n_tiles, std::max(1, h->num_sms * per_sm / st.g_ny)), st.g_ny);
+  int sms = h->num_sms;
+  if (h->sr_grid_cap > 0) sms = std::min(sms, h->sr_grid_cap);
+  dim3 grid(std::min(n_tiles, std::max(1, sms * per_sm / st.g_ny)), st.g_ny);
   for (int k_lo = 0; k_lo < st.mo; k_lo += slab) {
     kern<<<grid, threads, smem, stream>>>(st, x, k_lo, std::min(st.mo, k_lo + slab));
     h->launches++;
@@ -1633,6 +1636,7 @@ int gpmpc_set_option(gpmpc_handle* h, const char* name, int64_t value) {
   else if (n == "hz_groups") h->hz_groups_cap = (int)value;
   else if (n == "step_grid_cap") h->step_grid_cap = (int)value;
   else if (n == "step_warps_cap") h->step_warps_cap = (int)value;
+  else if (n == "sr_grid_cap") h->sr_grid_cap = (int)value;
   else if (n == "prefactor_next") h->prefactor_next = value != 0 && h->condition;
   else if (n == "hz_stagger_ns") h->hz_stagger_ns = value;
   else if (n == "force_wo") h->force_wo = value != 0;

@@ -54,6 +54,7 @@ def both():
 for cap in caps:
     for f in frs:
         f.engine.set_option("step_grid_cap", cap)
+        f.engine.set_option("sr_grid_cap", 148 - cap if cap else 0)  # the GEMM of the other half on exactly the SMs left free
     ms, out = timed(both)
     print(f"two engines, two streams, step kernel on <= {cap or 148} SMs each: {ms:.1f} ms  {ns * steps / ms / 1e3:.2f} M sample-steps/s"
           f"  bit-identical {bool(torch.equal(out, ref))}  status {[f.engine.status() for f in frs]}", flush=True)
