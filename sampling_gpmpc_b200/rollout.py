@@ -175,13 +175,7 @@ class ForwardRollout:
         allp = torch.empty((self.world_size, H1, cmax, 3), dtype=F64, device=traj.device)
         dist.all_gather_into_tensor(allp, pack.contiguous())
         allp = allp.permute(1, 0, 2, 3).reshape(H1, self.world_size * cmax, 3).cpu().numpy()
-        out = []
-        for t in range(H1):
-            c = allp[t][~np.isnan(allp[t][:, 2])]
-            c = c[np.argsort(c[:, 2], kind="stable")]  # by global sample index: identical points resolve to the lowest one
-            pos = hull2d(np.ascontiguousarray(c[:, :2]))
-            out.append(c[pos, 2].astype(np.int32))
-        return out
+        return [merge_shard_hulls(allp[t]) for t in range(H1)]
 
 
 def save_X_traj(traj: torch.Tensor, save_dir: str, epistemic_idx: int, chunk: Optional[int] = None) -> list:
@@ -220,6 +214,17 @@ def gather_padded(local: torch.Tensor, ns_global: int, world_size: int) -> torch
     dist.all_gather_into_tensor(out, pad)
     return out[:ns_global]
 
+
+
+def merge_shard_hulls(cand: np.ndarray) -> np.ndarray:
+    """cand (n, 3): x, y, global sample index of the hull vertices of every shard (NaN rows = padding).  hull(union of the
+    shards) = hull(union of the shards' hulls): the exact host hull (gpmpc_hull2d, monotone chain) of the candidates, taken in
+    the order of their global sample index so that identical points resolve to the lowest one -- exactly what the hull over
+    all samples returns.  -> global sample indices of the vertices, counter-clockwise."""
+    c = cand[~np.isnan(cand[:, 2])]
+    c = c[np.argsort(c[:, 2], kind="stable")]
+    pos = hull2d(np.ascontiguousarray(c[:, :2]))
+    return c[pos, 2].astype(np.int32)
 
 
 def resample_rejected(samples_left: torch.Tensor, Xh: torch.Tensor, Yh: torch.Tensor, ns_global: int, rank: int, world_size: int):

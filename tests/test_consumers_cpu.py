@@ -133,3 +133,30 @@ def test_reachable_set_ball_matches_the_reference_function():
     got_eps, got_ci = reachable_set_ball(params, V)
     assert np.array_equal(np.asarray(got_ci), np.asarray(want_ci))
     assert len(got_eps) == len(want_eps) and all(np.array_equal(a, b) for a, b in zip(got_eps, want_eps))
+
+
+@pytest.mark.parametrize("kind", ["gauss", "grid", "same"])
+def test_merged_shard_hulls_equal_the_hull_of_all_points(hull2d, kind):
+    """ForwardRollout.stage_hulls on several ranks: every shard's own hull, the vertices merged by rollout.merge_shard_hulls --
+    the same vertex list (global sample indices) as the hull over all samples, also with points repeated across shards (a grid;
+    stage 0 of a rollout, where every sample sits on the start state)."""
+    from sampling_gpmpc_b200.rollout import merge_shard_hulls, shard_bounds
+    rng = np.random.default_rng(4)
+    n, world = 1001, 3
+    if kind == "gauss":
+        p = rng.standard_normal((n, 2))
+    elif kind == "grid":
+        p = rng.integers(0, 7, size=(n, 2)).astype(np.float64)
+    else:
+        p = np.tile(np.array([[0.3, -1.2]]), (n, 1))
+    want = list(hull2d(p))
+    cands = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        local = hull2d(p[lo:hi])                       # positions inside the shard
+        c = np.full((16, 3), np.nan)                   # padded like the all-gathered buffer
+        c[: len(local), :2] = p[lo:hi][local]
+        c[: len(local), 2] = local + lo
+        cands.append(c)
+    got = list(merge_shard_hulls(np.concatenate(cands[::-1])))  # any rank order
+    assert got == want
