@@ -24,13 +24,15 @@
 #include "gpmpc_block.cuh"
 #include "gpmpc_step.cuh"
 
+#ifndef PM_WARPS
 #define PM_WARPS 4       // warps = column blocks per CTA of k_pm_solve
+#endif
 #define PM_NSP 8         // sub-panels per row block of the solve (64 rows share every W fragment)
 #define PM_SLABC 64      // storage columns per sub-panel per stage: a buffer is PM_NSP x PM_SLABC x 64 B = 32 KB, two resident
 #define PM_MAX_Q 2048    // test scalars per call served by this path (QB <= 256 column blocks)
 
 template <int D, int T>
-__global__ void __launch_bounds__(PM_WARPS * 32, 3)
+__global__ void __launch_bounds__(PM_WARPS * 32, PM_WARPS <= 4 ? 3 : (PM_WARPS <= 8 ? 2 : 1))
 k_pm_solve(DevState st, const double* __restrict__ x, int H) {
   extern __shared__ __align__(128) double sA[];  // [2][PM_NSP][PM_SLABC * 8] two stages of the factor stream (k-block layout)
   const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -224,41 +226,57 @@ k_pm_solve(DevState st, const double* __restrict__ x, int H) {
     // -- the block's triangle, sub-panel by sub-panel
     next_stage(blk, n1);
     if (has) {
+      // The block's finished sub-panels stay in registers (C-fragment layout: lane (gid, tig) holds rows gid, columns 2 tig and
+      // 2 tig + 1 of its column block) and reach the later sub-panels' products as B fragments through warp shuffles -- lane
+      // (gid, tig) needs row 4 kk + tig, column gid, i.e. lane (4 kk + tig, gid >> 1)'s element gid & 1 -- instead of a store
+      // to W and a dependent L2 load per k-step; the same for rhs -> inv(D) rhs.  Same values, same products, same order.
+      double wres[PM_NSP][2];
+      const int src_t = gid >> 1;
+      const bool odd = gid & 1;
 #pragma unroll
       for (int jj = 0; jj < PM_NSP; ++jj) {
         if (jj < nsp) {
           const int p = p0 + jj;
           const uint32_t tri = buf_s + (uint32_t)(32 * jj * (jj + 1)) * 8;
-          for (int kk = 0; kk < 2 * jj; ++kk) {  // in-block columns base .. base + 8 jj: W rows of this block, just written
-            const int row = m + 8 * p0 + 4 * kk + tig;
-            const double bq = cok ? __ldcg(W + (size_t)row * q + colB) : 0.0;
-            dmma(acc[jj][2 * (kk & 1)], acc[jj][2 * (kk & 1) + 1], lds(tri + kk * 256 + a_lane), bq);
+          const int nvalid = min(8, c - 8 * p);
+          const bool live = gid < nvalid;
+          double* wrow = W + (size_t)(m + 8 * p + gid) * q;
+          // the kernel entries of this sub-panel's rows (written by phase 0): in flight during the in-block products
+          const double k0 = (live && colC < q) ? __ldcg(wrow + colC) : 0.0;
+          const double k1 = (live && colC + 1 < q) ? __ldcg(wrow + colC + 1) : 0.0;
+#pragma unroll
+          for (int kk = 0; kk < 2 * PM_NSP; ++kk) {  // in-block columns base .. base + 8 jj: the block's earlier sub-panels
+            if (kk < 2 * jj) {
+              const int src = 4 * (4 * (kk & 1) + tig) + src_t;
+              const double v0 = __shfl_sync(0xffffffffu, wres[kk >> 1][0], src);
+              const double v1 = __shfl_sync(0xffffffffu, wres[kk >> 1][1], src);
+              const double bq = cok ? (odd ? v1 : v0) : 0.0;
+              dmma(acc[jj][2 * (kk & 1)], acc[jj][2 * (kk & 1) + 1], lds(tri + kk * 256 + a_lane), bq);
+            }
           }
           // rhs = K - dot, w_blk = inv(D) rhs (diagonal block = the last 8 columns of this sub-panel's part)
           const uint32_t dblk = tri + (uint32_t)(8 * jj) * 64;
-          const int nvalid = min(8, c - 8 * p);
           double a0 = 0.0, a1 = 0.0;
           if (tig <= gid) a0 = lds(dblk + (uint32_t)sp_idx(gid, tig) * 8);
           if (tig + 4 <= gid) a1 = lds(dblk + (uint32_t)sp_idx(gid, tig + 4) * 8);
-          double* wrow = W + (size_t)(m + 8 * p + gid) * q;
-          const bool live = gid < nvalid;
-          if (live) {
-            if (colC < q) __stcg(wrow + colC, __ldcg(wrow + colC) - (acc[jj][0] + acc[jj][2]));
-            if (colC + 1 < q) __stcg(wrow + colC + 1, __ldcg(wrow + colC + 1) - (acc[jj][1] + acc[jj][3]));
-          }
-          __syncwarp();
-          const double b0 = (cok && tig < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig) * q + colB) : 0.0;
-          const double b1 = (cok && tig + 4 < nvalid) ? __ldcg(W + (size_t)(m + 8 * p + tig + 4) * q + colB) : 0.0;
+          const double r0 = (live && colC < q) ? k0 - (acc[jj][0] + acc[jj][2]) : 0.0;
+          const double r1 = (live && colC + 1 < q) ? k1 - (acc[jj][1] + acc[jj][3]) : 0.0;
+          const double u0 = __shfl_sync(0xffffffffu, r0, 4 * tig + src_t), u1 = __shfl_sync(0xffffffffu, r1, 4 * tig + src_t);
+          const double w0 = __shfl_sync(0xffffffffu, r0, 4 * (tig + 4) + src_t), w1 = __shfl_sync(0xffffffffu, r1, 4 * (tig + 4) + src_t);
+          const double b0 = (cok && tig < nvalid) ? (odd ? u1 : u0) : 0.0;
+          const double b1 = (cok && tig + 4 < nvalid) ? (odd ? w1 : w0) : 0.0;
           double d0 = 0.0, d1 = 0.0;
           dmma(d0, d1, a0, b0);
-          dmma(d0, d1, a1, b1);  // mma.sync: every lane's rhs loads have completed
+          dmma(d0, d1, a1, b1);
           if (live) {
             if (colC < q) __stcg(wrow + colC, d0);
             if (colC + 1 < q) __stcg(wrow + colC + 1, d1);
           }
-          __syncwarp();
+          wres[jj][0] = d0;
+          wres[jj][1] = d1;
         }
       }
+      __syncwarp();  // this block's rows of W are complete before the next block's left part reads them back
     }
   }
 }
