@@ -445,7 +445,7 @@ class Agent:
             self._appended_since_train = True
             self.engine.raise_on_status()  # waits for the stream: `host` is complete
             h = host.numpy().copy()  # the pinned staging buffer is reused by the next call
-            return h[:, :, :, [0]], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]
+            return h[:, :, :, 0:1], h[:, :, :, 1:1 + self.nx], h[:, :, :, 1 + self.nx:1 + self.nx + self.nu]  # views of the copy
         y = self.dyn_fg_jacobians_device(xu_hat, sqp_iter)
         host = torch.empty(y.shape, dtype=F64, pin_memory=True)
         host.copy_(y, non_blocking=True)  # ONE device->host copy (the reference does three, agent.py:555-557)
