@@ -647,25 +647,46 @@ k_append(DevState st, const double* __restrict__ x, const double* __restrict__ y
     }
     const int wt = tid - 32, wnt = nt - 32;  // the writers
     // new rows k = c + rr, written column by column (rr fastest: contiguous within a column)
-    // (four entries per pass, their loads of W -- L2 round trips -- issued before the first store: one entry per pass made
-    // this copy a chain of dependent round trips, 0.15 ms of the 0.37 ms of an append at 900 factor rows, q = 150)
-    for (int idx0 = wt; idx0 < qa * n; idx0 += 4 * wnt) {
-      double v[4];
+    // The part left of the new block, one k-block (4 storage columns of one row = one 32-byte sector, gpmpc_state.cuh) per thread
+    // and two per pass: eight loads of W in flight (one entry per pass was a chain of dependent L2 round trips), the sector
+    // written whole by two 16-byte stores.  Lanes = consecutive new rows: their sectors are contiguous inside a k-block, so a
+    // warp's store covers whole 256-byte k-blocks.  Storage column t: t < m shared (W row t), [m, mo) padding (zero), t >= mo own
+    // (W row m + t - mo); the columns of a k-block that straddles the new block's first column go entry by entry below.
+    {
+      const int c0 = st.c, mo = st.mo, m = st.m;
+      const int nkb_full = (mo + c0) >> 2;
+      double* Le = st.Lh + (size_t)b * st.elem_stride;
+      for (int idx0 = wt; idx0 < qa * nkb_full; idx0 += 2 * wnt) {
+        double v[2][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = idx0 + u * wnt;
-        if (idx < qa * n) {
-          const int k = idx / qa, rr = idx - k * qa;
-          v[u] = __ldcg(W + (size_t)k * q + sh_act[rr]);
+        for (int u = 0; u < 2; ++u) {
+          const int idx = idx0 + u * wnt;
+          if (idx < qa * nkb_full) {
+            const int kb = idx / qa, rr = idx - kb * qa;
+            const double* wc = W + sh_act[rr];
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq) {
+              const int t = 4 * kb + jq;
+              const int r = t < m ? t : (t >= mo ? t - mo + m : -1);
+              v[u][jq] = r >= 0 ? __ldcg(wc + (size_t)r * q) : 0.0;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int idx = idx0 + u * wnt;
+          if (idx < qa * nkb_full) {
+            const int kb = idx / qa, rr = idx - kb * qa, row = c0 + rr;
+            double2* dst = reinterpret_cast<double2*>(Le + subpanel_off(row >> 3, mo) + (size_t)kb * 32 + (row & 7) * 4);
+            dst[0] = make_double2(v[u][0], v[u][1]);
+            dst[1] = make_double2(v[u][2], v[u][3]);
+          }
         }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = idx0 + u * wnt;
-        if (idx < qa * n) {
-          const int k = idx / qa, rr = idx - k * qa;
-          *own_entry(st, b, st.c + rr, k) = v[u];
-        }
+      const int t_rem = 4 * nkb_full, n_rem = mo + c0 - t_rem;  // 0 .. 3 own columns left of the new block
+      for (int idx = wt; idx < qa * n_rem; idx += wnt) {
+        const int tq = idx / qa, rr = idx - tq * qa, k = m + (t_rem + tq - mo);
+        *own_entry(st, b, c0 + rr, k) = W[(size_t)k * q + sh_act[rr]];
       }
     }
     for (int idx = wt; idx < qa * qa; idx += wnt) {
